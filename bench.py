@@ -1,0 +1,276 @@
+"""bench.py -- E2ENet hot-path benchmark on B200 (contract: see the task's Measurement section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|infer]
+
+Workload at every N: BASELINE.json configs[1] -- E2ENet BTCV-shaped training: batch 2 per GPU
+(weak scaling), 1x64x160x160 CT patches, 14 classes, DSFF density 0.2, SGD(nesterov) +
+clip + Masking.step() every iteration.  One "step" = one full training iteration of one batch.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PATCH = (64, 160, 160)
+BATCH = 2
+NCLS = 14
+IN_CH = 1
+DENSITY = 0.2
+# dense algorithmic FLOPs of the conv / tconv / 1x1 GEMMs, config 2, B=2
+FWD_GFLOP_B2 = 4536.6
+STEP_GFLOP_B2 = 13607.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no_samples"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline_patches_per_s(budget_s=20.0, crop=(32, 80, 80)):
+    """the oracle's fp32 torch-CPU restatement of the same training iteration (fwd + DS loss + bwd +
+    clip + SGD + apply_mask), on a bounded sample: one 1x1x32x80x80 crop = 1/8 of a patch."""
+    import numpy as np
+    import torch
+    from collections import OrderedDict
+    from oracle import masking as omask
+    from oracle import network as onet
+    from e2enet_medical_b200.training import POOLS
+    torch.set_num_threads(os.cpu_count() or 1)
+    pools = POOLS["btcv"]
+    shapes = onet.param_shapes(IN_CH, 48, NCLS, pools)
+    params = onet.det_params(shapes, seed=0)
+    plist = [v.requires_grad_(True) for v in params.values()]
+    opt = torch.optim.SGD(plist, 1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+    import random
+    random.seed(0)
+    masks = {k: torch.from_numpy(m) for k, m in omask.init_uniform(shapes, DENSITY).items()}
+    with torch.no_grad():
+        for k, m in masks.items():
+            params[k].mul_(m)
+    rs = np.random.RandomState(1)
+    x = torch.from_numpy(rs.rand(1, IN_CH, *crop).astype(np.float32))
+    tg, sp = [], np.array(crop)
+    for k in range(4):
+        tg.append(torch.from_numpy(np.round(rs.rand(1, 1, *sp) * (NCLS - 1)).astype(np.float32)))
+        sp = sp // np.array(pools[k])
+
+    def one():
+        opt.zero_grad()
+        outs = onet.unetpp_forward(params, x, pools)
+        l = onet.ds_loss(outs, tg)
+        l.backward()
+        torch.nn.utils.clip_grad_norm_(plist, 12)
+        opt.step()
+        with torch.no_grad():
+            for k, m in masks.items():
+                params[k].mul_(m)
+                st = opt.state[params[k]]
+                if 'momentum_buffer' in st:
+                    st['momentum_buffer'].mul_(m)
+        return float(l)
+
+    one()                                             # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one()
+        n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 8:
+            break
+    dt = (time.perf_counter() - t0) / n
+    frac = float(np.prod(crop)) / float(np.prod(PATCH))
+    return frac / dt, dt, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    import torch
+    # each "step" = the bounded sample below; warm-up folded into cpu_baseline_patches_per_s
+    t0 = time.perf_counter()
+    val, dt, n = cpu_baseline_patches_per_s(budget_s=max(10.0, 6.0 * max(args.steps, 1)))
+    line = {
+        "impl": "reference", "metric": "train patches/s", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
+        "steps": n, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "E2ENet BTCV-shaped training: batch 2, 1x64x160x160, 14 classes, density 0.2 "
+                               "(CPU sample: 1x1x32x80x80 crop per step, value scaled by voxel count)"},
+        "cpu_baseline": {"value": val, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "oracle (torch-CPU fp32 restatement of the reference path) fwd+DS loss+bwd+clip+SGD+"
+                                   "apply_mask on one 1x1x32x80x80 crop = 1/8 patch, %d timed steps" % n},
+        "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from e2enet_medical_b200 import _lib, ops
+    from e2enet_medical_b200.training import POOLS, TrainStep, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    ops.CONFIG["impl"] = args.kernel_impl
+    pools = POOLS["btcv"]
+    ts = TrainStep(IN_CH, NCLS, pools, PATCH, DENSITY, 0.5, 1200, dev, world, seed=0)
+    data_h, targets_h = synthetic_batch(BATCH, IN_CH, NCLS, PATCH, pools, seed=1 + rank)
+    data_h = data_h.pin_memory()
+    targets_h = [t.pin_memory() for t in targets_h]
+    data_d = data_h.to(dev)
+    targets_d = [t.to(dev) for t in targets_h]
+    h2d = data_h.numel() * 4 + sum(t.numel() * 4 for t in targets_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        ts.step(data_d, targets_d)
+
+    def step_e2e():
+        d = data_h.to(dev, non_blocking=True)
+        t = [x.to(dev, non_blocking=True) for x in targets_h]
+        l = ts.step(d, t)
+        return float(l.cpu())                      # loss read-back, like run_iteration's l.detach().cpu().numpy()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # kernel-level timing of the dominant kernel family (events on the launching stream)
+    ops.PROFILE["enabled"] = True
+    ops.PROFILE["records"] = []
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.launch_count() - n0
+    recs = ops.PROFILE["records"]
+    ops.PROFILE["enabled"] = False
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for (_, a, b, _) in recs)
+    gemm_flops = sum(f for (_, _, _, f) in recs)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    value = BATCH * world * args.steps / (ms / 1e3)
+    e2e = BATCH * world * args.steps / (ms_e2e / 1e3)
+    achieved = (gemm_flops / 1e12) / (gemm_ms / 1e3) if gemm_ms > 0 else 0.0
+    line = {
+        "metric": "train patches/s", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "E2ENet BTCV-shaped training: batch 2 per GPU, 1x64x160x160, 14 classes, density 0.2, "
+                               "SGD nesterov + clip 12 + Masking.step() (BASELINE.json configs[1])",
+                   "global_batch": BATCH * world, "parallelism": "dp%d" % world,
+                   "l2": "activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed",
+                   "kernel_impl": "tcgen05" if args.kernel_impl else "mma.sync"},
+        "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                     "kernel": "conv/tconv/seg GEMM launches (gather_gemm + gather_wgrad), dense 2MNK FLOPs",
+                     "share_of_step": gemm_ms / ms if ms > 0 else None, "peak_source": peaks["src"] + ", sustained bf16"},
+        "step_tflops": STEP_GFLOP_B2 / 1e3 * args.steps / (ms / 1e3),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, dt, n = cpu_baseline_patches_per_s()
+        line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x80x80 crop "
+                                          "(1/8 patch), %d steps of %.1f s" % (n, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel-impl", type=int, default=0, help="0: mma.sync gather kernels, 1: tcgen05 where available")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

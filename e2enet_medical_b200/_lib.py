@@ -1,0 +1,150 @@
+"""ctypes binding of libe2enet_b200.so (the C ABI declared in include/e2enet_b200.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, the
+product path raises.  (The CPU oracle lives in /oracle and is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libe2enet_b200.so")
+
+E2E_MAX_SRC = 4
+
+
+class CEntry(C.Structure):
+    _fields_ = [("src", C.c_int32), ("blk", C.c_int32), ("dd", C.c_int32), ("dh", C.c_int32), ("dw", C.c_int32)]
+
+
+class Tap(C.Structure):
+    _fields_ = [("dd", C.c_int32), ("dh", C.c_int32), ("dw", C.c_int32)]
+
+
+class ColBlk(C.Structure):
+    _fields_ = [("dst", C.c_int32), ("blk", C.c_int32), ("chmask", C.c_int32), ("od", C.c_int32),
+                ("oh", C.c_int32), ("ow", C.c_int32)]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("Di", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32),
+        ("Do", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("isd", C.c_int32), ("ish", C.c_int32), ("isw", C.c_int32),
+        ("ivd", C.c_int32), ("ivh", C.c_int32), ("ivw", C.c_int32),
+        ("Dd", C.c_int32), ("Hd", C.c_int32), ("Wd", C.c_int32),
+        ("osd", C.c_int32), ("osh", C.c_int32), ("osw", C.c_int32),
+        ("n_src", C.c_int32),
+        ("src", C.c_void_p * E2E_MAX_SRC),
+        ("src_cb", C.c_int32 * E2E_MAX_SRC),
+        ("n_cent", C.c_int32),
+        ("cents", C.c_void_p),
+        ("n_taps", C.c_int32),
+        ("taps", C.c_void_p),
+        ("wpacked", C.c_void_p),
+        ("Npad", C.c_int32),
+        ("cols", C.c_void_p),
+        ("n_dst", C.c_int32),
+        ("dst", C.c_void_p * E2E_MAX_SRC),
+        ("dst_cb", C.c_int32 * E2E_MAX_SRC),
+        ("out_mode", C.c_int32),
+        ("impl", C.c_int32),
+    ]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("Di", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32),
+        ("Do", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("isd", C.c_int32), ("ish", C.c_int32), ("isw", C.c_int32),
+        ("ivd", C.c_int32), ("ivh", C.c_int32), ("ivw", C.c_int32),
+        ("n_src", C.c_int32),
+        ("src", C.c_void_p * E2E_MAX_SRC),
+        ("src_cb", C.c_int32 * E2E_MAX_SRC),
+        ("n_cent", C.c_int32),
+        ("cents", C.c_void_p),
+        ("n_taps", C.c_int32),
+        ("taps", C.c_void_p),
+        ("grad", C.c_void_p),
+        ("grad_cb", C.c_int32),
+        ("Npad", C.c_int32),
+        ("dwp", C.c_void_p),
+        ("impl", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/e2enet_b200.h
+_VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+SIGNATURES = {
+    "e2e_last_error": (C.c_char_p, []),
+    "e2e_version": (C.c_int, []),
+    "e2e_launch_count": (C.c_longlong, []),
+    "e2e_gather_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
+    "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
+    "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_nc_to_c8": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),
+    "e2e_c8_to_nc": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),
+    "e2e_in_stats": (C.c_int, [_VP, _I32, _I32, _I64, _F, _VP, _I32, _VP, _VP, _VP]),
+    "e2e_in_apply": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP]),
+    "e2e_in_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _I32, _VP, _VP, _VP, _VP,
+                             _VP, _VP]),
+    "e2e_maxpool_fwd": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "e2e_maxpool_bwd": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "e2e_add_inplace": (C.c_int, [_VP, _VP, _I64, _VP]),
+    "e2e_mask_apply_multi": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _VP]),
+    "e2e_mask_kernel_l1": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_mask_kth": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP]),
+    "e2e_mask_kill": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP]),
+    "e2e_mask_dead_list": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "e2e_mask_grow": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
+    "e2e_mask_counts": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "e2e_window_accumulate": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                        _I32, _I32, _F, _I32, _I32, _VP]),
+    "e2e_window_finalize": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class E2EError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the CUDA library; raises (never falls back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise E2EError(
+                "libe2enet_b200.so is missing (%s). Build it with `python -m e2enet_medical_b200.build`; "
+                "this package has no CPU / eager fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().e2e_last_error()
+        raise E2EError("%s failed (rc=%d): %s" % (what or "e2enet_b200 call", rc, (msg or b"").decode()))
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().e2e_launch_count())

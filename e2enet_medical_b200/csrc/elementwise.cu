@@ -1,0 +1,451 @@
+// Bandwidth-bound stages of the E2ENet hot path on the C8 layout (bf16 [B][C/8][V][8]):
+// layout conversion, InstanceNorm statistics / apply (+LeakyReLU) / backward, MaxPool3d.
+// All kernels move 16-byte vectors (one voxel x 8 channels), grid sized in multiples of the
+// SM count, fp32 math, deterministic two-stage reductions (no float atomics).
+#include "common.cuh"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------ layout conversion
+__global__ void nc_to_c8_kernel(const float* __restrict__ x, uint4* __restrict__ y, int B, int C, long long V) {
+  const int Cb = (C + 7) / 8;
+  const long long total = (long long)B * Cb * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % V;
+    const long long t = i / V;
+    const int cb = (int)(t % Cb), b = (int)(t / Cb);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      f[j] = (c < C) ? x[((long long)b * C + c) * V + v] : 0.f;
+    }
+    y[i] = pack8(f);
+  }
+}
+
+__global__ void c8_to_nc_kernel(const uint4* __restrict__ x, float* __restrict__ y, int B, int C, long long V) {
+  const int Cb = (C + 7) / 8;
+  const long long total = (long long)B * Cb * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i % V;
+    const long long t = i / V;
+    const int cb = (int)(t % Cb), b = (int)(t / Cb);
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cb * 8 + j;
+      if (c < C) y[((long long)b * C + c) * V + v] = f[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ block reduction of 16 floats per thread
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(float* acc, float* out /* NV floats */) {
+  __shared__ float red[EW_THREADS / 32][NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k] = warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < EW_THREADS / 32; ++w) s += red[w][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
+// grid (nchunk, B*Cb): partial[plane][chunk][0..7] = sum, [8..15] = sum of squares
+__global__ void __launch_bounds__(EW_THREADS) in_stats_partial_kernel(const uint4* __restrict__ raw, long long V,
+                                                                      int nchunk, float* __restrict__ partial) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const long long per = (V + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(V, lo + per);
+  const uint4* base = raw + (long long)plane * V;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
+    float f[8];
+    unpack8(ld_nc_16(base + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += f[j];
+      acc[8 + j] += f[j] * f[j];
+    }
+  }
+  block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
+}
+
+// one thread per (plane, j)
+__global__ void in_stats_final_kernel(const float* __restrict__ partial, int planes, int nchunk, long long V, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes * 8) return;
+  const int plane = i >> 3, j = i & 7;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < nchunk; ++c) {
+    s += partial[((long long)plane * nchunk + c) * 16 + j];
+    q += partial[((long long)plane * nchunk + c) * 16 + 8 + j];
+  }
+  const double m = s / (double)V;
+  double var = q / (double)V - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// grid (nchunk, B*Cb)
+__global__ void __launch_bounds__(EW_THREADS) in_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float slope, int Cb,
+                                                              long long V, int nchunk, uint4* __restrict__ out) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int cb = plane % Cb;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float g = gamma[cb * 8 + j], r = rstd[plane * 8 + j];
+    sc[j] = g * r;
+    sh[j] = beta[cb * 8 + j] - mean[plane * 8 + j] * g * r;
+  }
+  const long long per = (V + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(V, lo + per);
+  const uint4* ib = raw + (long long)plane * V;
+  uint4* ob = out + (long long)plane * V;
+  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
+    float f[8];
+    unpack8(ld_nc_16(ib + v), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = f[j] * sc[j] + sh[j];
+      f[j] = z > 0.f ? z : z * slope;
+    }
+    ob[v] = pack8(f);
+  }
+}
+
+// backward pass 1: partial[plane][chunk][0..7] = sum dz, [8..15] = sum dz*xhat
+__global__ void __launch_bounds__(EW_THREADS) in_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ raw,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float slope, int Cb,
+                                                                   long long V, int nchunk, float* __restrict__ partial) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int cb = plane % Cb;
+  float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
+    ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
+  }
+  const long long per = (V + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(V, lo + per);
+  const uint4* xb = raw + (long long)plane * V;
+  const uint4* gb = dy + (long long)plane * V;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
+    float x[8], g[8];
+    unpack8(ld_nc_16(xb + v), x);
+    unpack8(ld_nc_16(gb + v), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mu[j]) * rs[j];
+      const float z = xh * ga[j] + be[j];
+      const float dz = z > 0.f ? g[j] : g[j] * slope;
+      acc[j] += dz;
+      acc[8 + j] += dz * xh;
+    }
+  }
+  block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
+}
+
+// sums[plane*16 + k] (fp32) = total over chunks
+__global__ void in_bwd_final_kernel(const float* __restrict__ partial, int planes, int nchunk, float* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= planes * 16) return;
+  const int plane = i >> 4, k = i & 15;
+  double s = 0.0;
+  for (int c = 0; c < nchunk; ++c) s += partial[((long long)plane * nchunk + c) * 16 + k];
+  sums[i] = (float)s;
+}
+
+// backward pass 2: draw = rstd*gamma*(dz - mean(dz) - xhat*mean(dz*xhat)); partial2[plane][chunk][0..7] = sum draw
+__global__ void __launch_bounds__(EW_THREADS) in_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ raw,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  const float* __restrict__ sums, float slope, int Cb,
+                                                                  long long V, int nchunk, uint4* __restrict__ draw,
+                                                                  float* __restrict__ partial2) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int cb = plane % Cb;
+  const float invV = 1.0f / (float)V;
+  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
+    ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
+    m1[j] = sums[plane * 16 + j] * invV;
+    m2[j] = sums[plane * 16 + 8 + j] * invV;
+  }
+  const long long per = (V + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(V, lo + per);
+  const uint4* xb = raw + (long long)plane * V;
+  const uint4* gb = dy + (long long)plane * V;
+  uint4* ob = draw + (long long)plane * V;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
+    float x[8], g[8], o[8];
+    unpack8(ld_nc_16(xb + v), x);
+    unpack8(ld_nc_16(gb + v), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (x[j] - mu[j]) * rs[j];
+      const float z = xh * ga[j] + be[j];
+      const float dz = z > 0.f ? g[j] : g[j] * slope;
+      o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+    }
+    const uint4 pk = pack8(o);
+    ob[v] = pk;
+    float ro[8];
+    unpack8(pk, ro);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+  }
+  block_reduce_store<8>(acc, partial2 + ((long long)plane * nchunk + chunk) * 8);
+}
+
+// dgamma[c] = sum_b sum dz*xhat ; dbeta[c] = sum_b sum dz ; dbias[c] = sum_b sum draw
+__global__ void in_bwd_param_kernel(const float* __restrict__ sums, const float* __restrict__ partial2, int B, int Cb,
+                                    int nchunk, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cb * 8) return;
+  const int cb = c >> 3, j = c & 7;
+  double g = 0.0, bt = 0.0, bi = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const int plane = b * Cb + cb;
+    bt += sums[plane * 16 + j];
+    g += sums[plane * 16 + 8 + j];
+    for (int k = 0; k < nchunk; ++k) bi += partial2[((long long)plane * nchunk + k) * 8 + j];
+  }
+  dgamma[c] = (float)g;
+  dbeta[c] = (float)bt;
+  if (dbias) dbias[c] = (float)bi;
+}
+
+// ------------------------------------------------------------------ MaxPool3d, kernel == stride
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                                 uint2* __restrict__ amax, int BCb, int D, int H, int W,
+                                                                 int kd, int kh, int kw) {
+  const int Do = D / kd, Ho = H / kh, Wo = W / kw;
+  const long long total = (long long)BCb * Do * Ho * Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % Wo);
+    long long t = i / Wo;
+    const int oh = (int)(t % Ho);
+    t /= Ho;
+    const int od = (int)(t % Do);
+    const long long plane = t / Do;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    int widx = 0;
+    for (int a = 0; a < kd; ++a)
+      for (int b = 0; b < kh; ++b)
+        for (int c = 0; c < kw; ++c, ++widx) {
+          const long long src = ((plane * D + od * kd + a) * H + oh * kh + b) * (long long)W + ow * kw + c;
+          float f[8];
+          unpack8(ld_nc_16(x + src), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (f[j] > best[j] || (f[j] != f[j] && best[j] == best[j])) { best[j] = f[j]; bi[j] = widx; }
+        }
+    y[i] = pack8(best);
+    uint2 am;
+    am.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    am.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    amax[i] = am;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ amax,
+                                                                 uint4* __restrict__ dx, int BCb, int D, int H, int W,
+                                                                 int kd, int kh, int kw) {
+  const int Do = D / kd, Ho = H / kh, Wo = W / kw;
+  const long long total = (long long)BCb * D * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int d = (int)(t % D);
+    const long long plane = t / D;
+    const int od = d / kd, oh = h / kh, ow = w / kw;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (od < Do && oh < Ho && ow < Wo) {
+      const int widx = ((d - od * kd) * kh + (h - oh * kh)) * kw + (w - ow * kw);
+      const long long oi = ((plane * Do + od) * Ho + oh) * (long long)Wo + ow;
+      const uint2 am = amax[oi];
+      float g[8], r[8];
+      unpack8(dy[oi], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = ((j < 4 ? am.x : am.y) >> ((j & 3) * 8)) & 0xffu;
+        r[j] = (a == (uint32_t)widx) ? g[j] : 0.f;
+      }
+      o = pack8(r);
+    }
+    dx[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) add_inplace_kernel(uint4* __restrict__ y, const uint4* __restrict__ x,
+                                                                 long long n16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    unpack8(y[i], a);
+    unpack8(ld_nc_16(x + i), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    y[i] = pack8(a);
+  }
+}
+
+inline int ew_blocks(long long n) {
+  long long b = (n + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = (long long)e2e_num_sms() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+
+extern "C" int e2e_nc_to_c8(const float* x, void* y, int32_t B, int32_t C, int64_t V, void* stream) {
+  E2E_ARG(x && y && B > 0 && C > 0 && V > 0, "nc_to_c8: bad arguments");
+  const long long total = (long long)B * ((C + 7) / 8) * V;
+  nc_to_c8_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>(x, (uint4*)y, B, C, V);
+  E2E_LAUNCHED("nc_to_c8");
+  return E2E_OK;
+}
+
+extern "C" int e2e_c8_to_nc(const void* x, float* y, int32_t B, int32_t C, int64_t V, void* stream) {
+  E2E_ARG(x && y && B > 0 && C > 0 && V > 0, "c8_to_nc: bad arguments");
+  const long long total = (long long)B * ((C + 7) / 8) * V;
+  c8_to_nc_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)x, y, B, C, V);
+  E2E_LAUNCHED("c8_to_nc");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, float eps, float* partial,
+                            int32_t nchunk, float* mean, float* rstd, void* stream) {
+  E2E_ARG(raw && partial && mean && rstd && B > 0 && Cb > 0 && V > 0 && nchunk > 0, "in_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  in_stats_partial_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, st>>>((const uint4*)raw, V, nchunk, partial);
+  E2E_LAUNCHED("in_stats_partial");
+  const int n = B * Cb * 8;
+  in_stats_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, V, eps, mean, rstd);
+  E2E_LAUNCHED("in_stats_final");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_apply(const void* raw, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, void* out,
+                            void* stream) {
+  E2E_ARG(raw && mean && rstd && gamma && beta && out && B > 0 && Cb > 0 && V > 0, "in_apply: bad arguments");
+  int nchunk = (int)((V + 4095) / 4096);
+  const int want = (e2e_num_sms() * 8 + B * Cb - 1) / (B * Cb);
+  if (nchunk > want) nchunk = want;
+  if (nchunk < 1) nchunk = 1;
+  in_apply_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, V, nchunk, (uint4*)out);
+  E2E_LAUNCHED("in_apply");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, const float* rstd, const float* gamma,
+                          const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* partial,
+                          int32_t nchunk, float* sums, void* draw, float* dgamma, float* dbeta, float* dbias,
+                          void* stream) {
+  E2E_ARG(dy && raw && mean && rstd && gamma && beta && partial && sums && draw && dgamma && dbeta,
+          "in_bwd: null pointer");
+  E2E_ARG(B > 0 && Cb > 0 && V > 0 && nchunk > 0, "in_bwd: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(nchunk, B * Cb);
+  in_bwd_reduce_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta,
+                                                    slope, Cb, V, nchunk, partial);
+  E2E_LAUNCHED("in_bwd_reduce");
+  const int n = B * Cb * 16;
+  in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
+  E2E_LAUNCHED("in_bwd_final");
+  in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, sums,
+                                                   slope, Cb, V, nchunk, (uint4*)draw, partial);
+  E2E_LAUNCHED("in_bwd_apply");
+  in_bwd_param_kernel<<<(Cb * 8 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  E2E_LAUNCHED("in_bwd_param");
+  return E2E_OK;
+}
+
+extern "C" int e2e_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t BCb, int32_t D, int32_t H, int32_t W,
+                               int32_t kd, int32_t kh, int32_t kw, void* stream) {
+  E2E_ARG(x && y && argmax, "maxpool_fwd: null pointer");
+  E2E_ARG(kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 255, "maxpool_fwd: bad window");
+  const long long total = (long long)BCb * (D / kd) * (H / kh) * (W / kw);
+  if (total <= 0) return E2E_OK;
+  maxpool_fwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y,
+                                                                                (uint2*)argmax, BCb, D, H, W, kd, kh, kw);
+  E2E_LAUNCHED("maxpool_fwd");
+  return E2E_OK;
+}
+
+extern "C" int e2e_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t BCb, int32_t D, int32_t H,
+                               int32_t W, int32_t kd, int32_t kh, int32_t kw, void* stream) {
+  E2E_ARG(dy && argmax && dx, "maxpool_bwd: null pointer");
+  const long long total = (long long)BCb * D * H * W;
+  if (total <= 0) return E2E_OK;
+  maxpool_bwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)argmax,
+                                                                                (uint4*)dx, BCb, D, H, W, kd, kh, kw);
+  E2E_LAUNCHED("maxpool_bwd");
+  return E2E_OK;
+}
+
+extern "C" int e2e_add_inplace(void* y, const void* x, int64_t n_elems, void* stream) {
+  E2E_ARG(y && x && n_elems % 8 == 0, "add_inplace: bad arguments");
+  if (n_elems == 0) return E2E_OK;
+  add_inplace_kernel<<<ew_blocks(n_elems / 8), EW_THREADS, 0, (cudaStream_t)stream>>>((uint4*)y, (const uint4*)x,
+                                                                                      n_elems / 8);
+  E2E_LAUNCHED("add_inplace");
+  return E2E_OK;
+}

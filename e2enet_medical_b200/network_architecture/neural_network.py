@@ -1,0 +1,311 @@
+"""Drop-in replacement for e2enet/network_architecture/neural_network.py (the inference mixin).
+
+Same class names and `predict_3D` signature / return types as the reference
+(neural_network.py:27-162): input np.ndarray (c,x,y,z) fp32 -> (seg int64 (x,y,z),
+softmax fp32 (ncls,x,y,z)).  The tile loop of `_internal_predict_3D_3Dconv_tiled`
+(:286-426) keeps its structure but everything per tile stays on the GPU: logits are
+soft-maxed, un-mirrored, Gaussian-weighted and accumulated into fp32 device accumulators by
+one fused kernel (e2e_window_accumulate), and `agg /= nb; argmax` is one more kernel; the
+only host<->device traffic is the volume going in and (seg, softmax) coming out.
+Tiles can be sharded over ranks (`set_tile_sharding`) with one NCCL reduce of the
+accumulators at the end.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple, Union
+
+import numpy as np
+import torch
+from scipy.ndimage import gaussian_filter
+from torch import nn
+
+from .. import _lib
+
+
+class no_op(object):
+    def __enter__(self):
+        pass
+
+    def __exit__(self, *args):
+        pass
+
+
+def maybe_to_torch(d):
+    if isinstance(d, list):
+        d = [maybe_to_torch(i) if not isinstance(i, torch.Tensor) else i for i in d]
+    elif not isinstance(d, torch.Tensor):
+        d = torch.from_numpy(d).float()
+    return d
+
+
+def pad_nd_image(image, new_shape=None, mode="constant", kwargs=None, return_slicer=False,
+                 shape_must_be_divisible_by=None):
+    """batchgenerators.augmentations.utils.pad_nd_image (0.24) semantics: symmetric pad of the
+    trailing axes up to new_shape / to a multiple of shape_must_be_divisible_by; the odd voxel
+    goes to the upper side.  (third-party dependency of the reference, neural_network.py:17,300)"""
+    if kwargs is None:
+        kwargs = {'constant_values': 0}
+    if new_shape is not None:
+        old_shape = np.array(image.shape[-len(new_shape):])
+    else:
+        assert shape_must_be_divisible_by is not None
+        new_shape = image.shape[-len(shape_must_be_divisible_by):]
+        old_shape = np.array(new_shape)
+    n_lead = image.ndim - len(new_shape)
+    target = np.array([max(int(a), int(b)) for a, b in zip(new_shape, old_shape)])
+    if shape_must_be_divisible_by is not None:
+        div = shape_must_be_divisible_by
+        if not isinstance(div, (list, tuple, np.ndarray)):
+            div = [div] * len(target)
+        target = np.array([int(t) if t % int(m) == 0 else int(t) + int(m) - int(t) % int(m)
+                           for t, m in zip(target, div)])
+    diff = target - old_shape
+    below, above = diff // 2, diff // 2 + diff % 2
+    pads = [[0, 0]] * n_lead + [[int(a), int(b)] for a, b in zip(below, above)]
+    res = np.pad(image, pads, mode, **kwargs) if diff.any() else image
+    if not return_slicer:
+        return res
+    slicer = [slice(p[0], res.shape[i] - p[1]) for i, p in enumerate(pads)]
+    return res, slicer
+
+
+class NeuralNetwork(nn.Module):
+    def __init__(self):
+        super(NeuralNetwork, self).__init__()
+
+    def get_device(self):
+        if next(self.parameters()).device.type == "cpu":
+            return "cpu"
+        return next(self.parameters()).device.index
+
+    def set_device(self, device):
+        if device == "cpu":
+            self.cpu()
+        else:
+            self.cuda(device)
+
+    def forward(self, x):
+        raise NotImplementedError
+
+
+# fixed mirror order of the reference (neural_network.py:529-560); entries are reference mirror axes
+_MIRRORS = [(), (2,), (1,), (2, 1), (0,), (2, 0), (1, 0), (2, 1, 0)]
+
+
+class SegmentationNetwork(NeuralNetwork):
+    def __init__(self):
+        super(NeuralNetwork, self).__init__()
+        self.input_shape_must_be_divisible_by = None
+        self.conv_op = None
+        self.num_classes = None
+        self.inference_apply_nonlin = lambda x: x
+        self._gaussian_3d = self._patch_size_for_gaussian_3d = None
+        self._gaussian_2d = self._patch_size_for_gaussian_2d = None
+        self._tile_shard = None         # (rank, world_size, process_group) or None
+
+    # ------------------------------------------------------------------ multi-GPU tile sharding
+    def set_tile_sharding(self, rank: int = 0, world_size: int = 1, group=None):
+        """tiles[rank::world_size] are predicted here; the accumulators are summed with one
+        NCCL all-reduce before normalisation (option A)."""
+        self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group)
+
+    # ------------------------------------------------------------------ public API
+    def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
+                   use_sliding_window: bool = False, step_size: float = 0.5, patch_size: Tuple[int, ...] = None,
+                   regions_class_order: Tuple[int, ...] = None, use_gaussian: bool = False,
+                   pad_border_mode: str = "constant", pad_kwargs: dict = None, all_in_gpu: bool = False,
+                   verbose: bool = True, mixed_precision: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        assert step_size <= 1, 'step_size must be smaller than 1. Otherwise there will be a gap between consecutive ' \
+                               'predictions'
+        if verbose:
+            print("debug: mirroring", do_mirroring, "mirror_axes", mirror_axes)
+        if pad_kwargs is None:
+            pad_kwargs = {'constant_values': 0}
+        if len(mirror_axes):
+            if self.conv_op == nn.Conv2d and max(mirror_axes) > 1:
+                raise ValueError("mirror axes. duh")
+            if self.conv_op == nn.Conv3d and max(mirror_axes) > 2:
+                raise ValueError("mirror axes. duh")
+        if self.training:
+            print('WARNING! Network is in train mode during inference. This may be intended, or not...')
+        assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
+        if self.conv_op != nn.Conv3d:
+            raise RuntimeError("Invalid conv op: the E2ENet B200 path is a 3-D network (2-D paths of the "
+                               "reference mixin are not on the hot path)")
+        # mixed_precision / all_in_gpu are accepted for API parity: compute is always bf16 with fp32
+        # accumulation, and the accumulators always live on the GPU in fp32.
+        with torch.no_grad():
+            if use_sliding_window:
+                return self._internal_predict_3D_3Dconv_tiled(x, step_size, do_mirroring, mirror_axes, patch_size,
+                                                              regions_class_order, use_gaussian, pad_border_mode,
+                                                              pad_kwargs=pad_kwargs, all_in_gpu=all_in_gpu,
+                                                              verbose=verbose)
+            return self._internal_predict_3D_3Dconv(x, patch_size, do_mirroring, mirror_axes, regions_class_order,
+                                                    pad_border_mode, pad_kwargs=pad_kwargs, verbose=verbose)
+
+    def predict_2D(self, *args, **kwargs):
+        raise RuntimeError("Cannot predict 2d if the network is 3d. Dummy.")
+
+    @staticmethod
+    def _get_gaussian(patch_size, sigma_scale=1. / 8) -> np.ndarray:
+        # computed on the host exactly like the reference (:244-258); scipy is the reference's own dependency
+        tmp = np.zeros(patch_size)
+        tmp[tuple(i // 2 for i in patch_size)] = 1
+        g = gaussian_filter(tmp, [i * sigma_scale for i in patch_size], 0, mode='constant', cval=0)
+        g = (g / np.max(g) * 1).astype(np.float32)
+        g[g == 0] = np.min(g[g != 0])
+        return g
+
+    @staticmethod
+    def _compute_steps_for_sliding_window(patch_size: Tuple[int, ...], image_size: Tuple[int, ...],
+                                          step_size: float) -> List[List[int]]:
+        assert [i >= j for i, j in zip(image_size, patch_size)], "image size must be as large or larger than patch_size"
+        assert 0 < step_size <= 1, 'step_size must be larger than 0 and smaller or equal to 1'
+        steps = []
+        for img, patch in zip(image_size, patch_size):
+            n = int(np.ceil((img - patch) / (patch * step_size))) + 1
+            span = img - patch
+            actual = span / (n - 1) if n > 1 else 99999999999
+            steps.append([int(np.round(actual * k)) for k in range(n)])
+        return steps
+
+    # ------------------------------------------------------------------ device-side accumulate
+    def _uses_softmax(self) -> bool:
+        return getattr(self.inference_apply_nonlin, "__name__", "") == "softmax_helper"
+
+    def _accumulate_tile(self, tile: torch.Tensor, mirror_axes, do_mirroring, gauss, agg, wsum, origin):
+        """tile: (1,c,px,py,pz) CUDA fp32.  Fuses softmax, un-mirroring, 1/num_mirrors, Gaussian and
+        the += into agg / wsum (reference :529-563 and :392-393)."""
+        lib = _lib.load()
+        ncls = self.num_classes
+        X, Y, Z = wsum.shape
+        px, py, pz = tile.shape[2:]
+        if do_mirroring:
+            combos = [m for m in _MIRRORS if all(a in mirror_axes for a in m)]
+            scale = 1.0 / (2 ** len(mirror_axes))
+        else:
+            combos, scale = [()], 1.0
+        fused = self._uses_softmax()
+        for n, m in enumerate(combos):
+            t = torch.flip(tile, tuple(a + 2 for a in m)) if m else tile
+            out = self(t)
+            if not fused:
+                out = self.inference_apply_nonlin(out)
+            out = out.float().contiguous()
+            assert out.shape[1] == ncls
+            flip = sum(1 << a for a in m)
+            _lib.check(lib.e2e_window_accumulate(
+                C.c_void_p(out.data_ptr()), C.c_void_p(gauss.data_ptr() if gauss is not None else 0),
+                C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z,
+                origin[0], origin[1], origin[2], flip, scale, 1 if n == 0 else 0, 1 if fused else 0,
+                _lib.stream_ptr()), "window_accumulate")
+
+    def _finalize(self, agg, wsum):
+        lib = _lib.load()
+        ncls = agg.shape[0]
+        X, Y, Z = wsum.shape
+        seg = torch.empty((X, Y, Z), dtype=torch.int64, device=agg.device)
+        _lib.check(lib.e2e_window_finalize(C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, X, Y, Z,
+                                           C.c_void_p(seg.data_ptr()), _lib.stream_ptr()), "window_finalize")
+        return seg
+
+    def _device(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("SegmentationNetwork (B200): the network must live on a CUDA device; no CPU fallback")
+        return dev
+
+    def _internal_predict_3D_3Dconv_tiled(self, x: np.ndarray, step_size: float, do_mirroring: bool,
+                                          mirror_axes: tuple, patch_size: tuple, regions_class_order: tuple,
+                                          use_gaussian: bool, pad_border_mode: str, pad_kwargs: dict,
+                                          all_in_gpu: bool, verbose: bool) -> Tuple[np.ndarray, np.ndarray]:
+        assert len(x.shape) == 4, "x must be (c, x, y, z)"
+        assert patch_size is not None, "patch_size cannot be None for tiled prediction"
+        dev = self._device()
+        data, slicer = pad_nd_image(x, patch_size, pad_border_mode, pad_kwargs, True, None)
+        data_shape = data.shape
+        steps = self._compute_steps_for_sliding_window(patch_size, data_shape[1:], step_size)
+        num_tiles = len(steps[0]) * len(steps[1]) * len(steps[2])
+        if verbose:
+            print("data shape:", data_shape, "patch size:", patch_size, "steps (x, y, and z):", steps,
+                  "number of tiles:", num_tiles)
+        gauss = None
+        if use_gaussian and num_tiles > 1:
+            if self._gaussian_3d is None or not all(i == j for i, j in zip(patch_size, self._patch_size_for_gaussian_3d)):
+                self._gaussian_3d = self._get_gaussian(patch_size, sigma_scale=1. / 8)
+                self._patch_size_for_gaussian_3d = patch_size
+            gauss = torch.from_numpy(self._gaussian_3d).to(dev, non_blocking=True).contiguous()
+
+        vol = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(dev, non_blocking=True)
+        agg = torch.zeros((self.num_classes,) + tuple(data_shape[1:]), dtype=torch.float32, device=dev)
+        wsum = torch.zeros(tuple(data_shape[1:]), dtype=torch.float32, device=dev)
+
+        tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
+        shard = self._tile_shard
+        if shard is not None:
+            tiles = tiles[shard[0]::shard[1]]
+        for (a, b, c) in tiles:
+            tile = vol[None, :, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]].contiguous()
+            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, (a, b, c))
+        if shard is not None:
+            import torch.distributed as dist
+            dist.all_reduce(agg, group=shard[2])
+            dist.all_reduce(wsum, group=shard[2])
+
+        seg = self._finalize(agg, wsum)                       # agg now holds agg / wsum
+        sp = tuple(slicer[1:])
+        probs = agg[(slice(None),) + sp]
+        seg = seg[sp]
+        if regions_class_order is None:
+            predicted_segmentation = seg.cpu().numpy()
+            class_probabilities = probs.cpu().numpy()
+        else:
+            class_probabilities = probs.cpu().numpy()
+            predicted_segmentation = np.zeros(class_probabilities.shape[1:], dtype=np.float32)
+            for i, c in enumerate(regions_class_order):
+                predicted_segmentation[class_probabilities[i] > 0.5] = c
+        if verbose:
+            print("prediction done")
+        return predicted_segmentation, class_probabilities
+
+    def _internal_predict_3D_3Dconv(self, x: np.ndarray, min_size: Tuple[int, ...], do_mirroring: bool,
+                                    mirror_axes: tuple = (0, 1, 2), regions_class_order: tuple = None,
+                                    pad_border_mode: str = "constant", pad_kwargs: dict = None,
+                                    verbose: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        """fully convolutional inference (reference :464-498): one 'tile' covering the padded image."""
+        assert len(x.shape) == 4, "x must be (c, x, y, z)"
+        assert self.input_shape_must_be_divisible_by is not None
+        dev = self._device()
+        data, slicer = pad_nd_image(x, min_size, pad_border_mode, pad_kwargs, True,
+                                    self.input_shape_must_be_divisible_by)
+        vol = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(dev)
+        agg = torch.zeros((self.num_classes,) + tuple(data.shape[1:]), dtype=torch.float32, device=dev)
+        wsum = torch.zeros(tuple(data.shape[1:]), dtype=torch.float32, device=dev)
+        self._accumulate_tile(vol[None], mirror_axes, do_mirroring, None, agg, wsum, (0, 0, 0))
+        seg = self._finalize(agg, wsum)
+        sp = tuple(slicer[1:])
+        probs = agg[(slice(None),) + sp].cpu().numpy()
+        if regions_class_order is None:
+            return seg[sp].cpu().numpy(), probs
+        out = np.zeros(probs.shape[1:], dtype=np.float32)
+        for i, c in enumerate(regions_class_order):
+            out[probs[i] > 0.5] = c
+        return out, probs
+
+    def _internal_maybe_mirror_and_pred_3D(self, x: Union[np.ndarray, torch.Tensor], mirror_axes: tuple,
+                                           do_mirroring: bool = True,
+                                           mult: np.ndarray or torch.Tensor = None) -> torch.Tensor:
+        """API-parity entry (reference :500-565): returns the mirrored / weighted prediction of one
+        tile as a (1, ncls, x, y, z) fp32 CUDA tensor."""
+        assert len(x.shape) == 5, 'x must be (b, c, x, y, z)'
+        dev = self._device()
+        x = maybe_to_torch(x).to(dev).float()
+        g = None
+        if mult is not None:
+            g = maybe_to_torch(mult).to(dev).float().contiguous()
+        sp = tuple(x.shape[2:])
+        agg = torch.zeros((self.num_classes,) + sp, dtype=torch.float32, device=dev)
+        wsum = torch.zeros(sp, dtype=torch.float32, device=dev)
+        self._accumulate_tile(x, mirror_axes, do_mirroring, g, agg, wsum, (0, 0, 0))
+        return agg[None]

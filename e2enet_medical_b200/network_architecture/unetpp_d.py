@@ -1,0 +1,411 @@
+"""Drop-in replacement for e2enet/network_architecture/unetpp_d.py (boqian333/E2ENet-Medical).
+
+Same public names, constructor signatures, sub-module names and state_dict layout as the
+reference (unetpp_d.py:25-591), so reference checkpoints load both ways and the reference's
+trainer can construct it positionally (nnUNetTrainer_simple.py:292-301).  The compute is not
+torch's: every conv / norm / pool on the path runs in hand-written sm_100a kernels from
+libe2enet_b200.so on channel-blocked bf16 activations ("C8"), the depth shift
+(torch_shift, :38-59) and the torch.cat of the fusion grid (:453-478) are folded into the
+kernels' operand fetch and never materialise.  CUDA only; no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..plans import build_seghead_plan, build_shiftconv_plan, build_tconv_plan
+from .neural_network import SegmentationNetwork
+
+
+def softmax_helper(x):
+    return F.softmax(x, 1)
+
+
+class InitWeights_He(object):
+    def __init__(self, neg_slope=1e-2):
+        self.neg_slope = neg_slope
+
+    def __call__(self, module):
+        if isinstance(module, (nn.Conv3d, nn.Conv2d, nn.ConvTranspose2d, nn.ConvTranspose3d)):
+            module.weight = nn.init.kaiming_normal_(module.weight, a=self.neg_slope)
+            if module.bias is not None:
+                module.bias = nn.init.constant_(module.bias, 0)
+
+
+class torch_shift(nn.Module):
+    """Kept for API parity (unetpp_d.py:38-59).  Inside ConvDropoutNormNonlin the shift is not
+    executed as an op: it becomes a per-channel-block depth offset of the conv's operand fetch."""
+
+    def __init__(self, shift_size, dim, dim_num):
+        super().__init__()
+        self.shift_size = shift_size
+        self.dim = dim
+        self.dim_num = dim_num
+
+    def forward(self, x):
+        raise RuntimeError("torch_shift is folded into the shift-conv kernel; call ConvDropoutNormNonlin instead")
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        return tuple(int(i) for i in v)
+    return (int(v),) * 3
+
+
+class ConvDropoutNormNonlin(nn.Module):
+    """depth shift -> Conv3d((1,3,3)) -> [dropout p=0] -> InstanceNorm3d(affine) -> LeakyReLU
+    (reference unetpp_d.py:61-111).  Parameters live in stock nn.Conv3d / nn.InstanceNorm3d
+    holders named `conv` / `instnorm`, so state_dict keys and optimizer wiring are unchanged."""
+
+    def __init__(self, input_channels, output_channels,
+                 conv_op=nn.Conv2d, conv_kwargs=None,
+                 norm_op=nn.BatchNorm2d, norm_op_kwargs=None,
+                 dropout_op=nn.Dropout2d, dropout_op_kwargs=None,
+                 nonlin=nn.LeakyReLU, nonlin_kwargs=None, shift_size=5):
+        super().__init__()
+        if nonlin_kwargs is None:
+            nonlin_kwargs = {'negative_slope': 1e-2, 'inplace': True}
+        if dropout_op_kwargs is None:
+            dropout_op_kwargs = {'p': 0.5, 'inplace': True}
+        if norm_op_kwargs is None:
+            norm_op_kwargs = {'eps': 1e-5, 'affine': True, 'momentum': 0.1}
+        if conv_kwargs is None:
+            conv_kwargs = {'kernel_size': 3, 'stride': 1, 'padding': 1, 'dilation': 1, 'bias': True}
+        self.nonlin_kwargs = nonlin_kwargs
+        self.nonlin = nonlin
+        self.dropout_op = dropout_op
+        self.dropout_op_kwargs = dropout_op_kwargs
+        self.norm_op_kwargs = norm_op_kwargs
+        self.conv_kwargs = conv_kwargs
+        self.conv_op = conv_op
+        self.norm_op = norm_op
+        self.shift_size = 5              # the reference ignores the argument (unetpp_d.py:89)
+
+        self.shift_D = torch_shift(self.shift_size, 2, 3)
+        self.conv = self.conv_op(input_channels, output_channels, **self.conv_kwargs)
+        if self.dropout_op is not None and self.dropout_op_kwargs['p'] is not None and self.dropout_op_kwargs['p'] > 0:
+            self.dropout = self.dropout_op(**self.dropout_op_kwargs)
+        else:
+            self.dropout = None
+        self.instnorm = self.norm_op(output_channels, **self.norm_op_kwargs)
+        self.lrelu = self.nonlin(**self.nonlin_kwargs)
+        self._plans = {}
+        self.e2e_weight_mask = None      # set by the drop-in Masking (same storage as Masking.masks[name])
+
+    # -- checks that the configuration is the one the kernels implement
+    def _check(self):
+        if not isinstance(self.conv, nn.Conv3d) or tuple(self.conv.kernel_size) != (1, 3, 3):
+            raise NotImplementedError("E2ENet B200 path implements Conv3d with kernel (1,3,3) only "
+                                      "(the reference forces it, unetpp_d.py:286-287); got %s" % (self.conv,))
+        if tuple(self.conv.padding) != (0, 1, 1) or tuple(self.conv.dilation) != (1, 1, 1) or self.conv.groups != 1:
+            raise NotImplementedError("unsupported conv padding/dilation/groups: %s" % (self.conv,))
+        if not isinstance(self.instnorm, nn.InstanceNorm3d) or not self.instnorm.affine or self.instnorm.track_running_stats:
+            raise NotImplementedError("E2ENet B200 path implements InstanceNorm3d(affine=True) only")
+        if not isinstance(self.lrelu, nn.LeakyReLU):
+            raise NotImplementedError("E2ENet B200 path implements LeakyReLU only")
+        if self.dropout is not None:
+            raise NotImplementedError("dropout p>0 is not on the E2ENet hot path (trainer passes p=0)")
+
+    def plan_for(self, src_channels):
+        key = tuple(int(c) for c in src_channels)
+        if key not in self._plans:
+            self._check()
+            assert sum(key) == self.conv.in_channels, (key, self.conv.in_channels)
+            self._plans[key] = build_shiftconv_plan(key, self.conv.out_channels, tuple(self.conv.stride))
+        return self._plans[key]
+
+    def forward_c8(self, srcs, src_channels):
+        """srcs: C8 tensors forming the (virtual) channel concat; returns a C8 tensor."""
+        plan = self.plan_for(src_channels)
+        return ops.ShiftConvINLReLU.apply(plan, float(self.lrelu.negative_slope), self.conv.weight, self.conv.bias,
+                                          self.instnorm.weight, self.instnorm.bias, self.e2e_weight_mask, *srcs)
+
+    def forward(self, x):
+        if isinstance(x, C8):
+            return C8(self.forward_c8(x.parts, x.channels), [self.conv.out_channels])
+        y = self.forward_c8([ops.ToC8.apply(x)], [x.shape[1]])
+        return ops.FromC8.apply(y, self.conv.out_channels)
+
+
+class C8(object):
+    """A (virtual concat of) channel-blocked activation(s) travelling between the drop-in modules."""
+    __slots__ = ("parts", "channels")
+
+    def __init__(self, parts, channels):
+        self.parts = list(parts) if isinstance(parts, (list, tuple)) else [parts]
+        self.channels = list(channels)
+
+    @property
+    def tensor(self):
+        assert len(self.parts) == 1
+        return self.parts[0]
+
+    @staticmethod
+    def cat(items):
+        p, c = [], []
+        for it in items:
+            p += it.parts
+            c += it.channels
+        return C8(p, c)
+
+
+class ConvDropoutNonlinNorm(ConvDropoutNormNonlin):
+    def forward(self, x):
+        raise NotImplementedError("ConvDropoutNonlinNorm is not used by the E2ENet path (basic_block is "
+                                  "ConvDropoutNormNonlin, nnUNetTrainer_simple.py:296-301)")
+
+
+class StackedConvLayers(nn.Module):
+    def __init__(self, input_feature_channels, output_feature_channels, num_convs,
+                 conv_op=nn.Conv2d, conv_kwargs=None,
+                 norm_op=nn.BatchNorm2d, norm_op_kwargs=None,
+                 dropout_op=nn.Dropout2d, dropout_op_kwargs=None,
+                 nonlin=nn.LeakyReLU, nonlin_kwargs=None, first_stride=None, basic_block=ConvDropoutNormNonlin):
+        self.input_channels = input_feature_channels
+        self.output_channels = output_feature_channels
+        if nonlin_kwargs is None:
+            nonlin_kwargs = {'negative_slope': 1e-2, 'inplace': True}
+        if dropout_op_kwargs is None:
+            dropout_op_kwargs = {'p': 0.5, 'inplace': True}
+        if norm_op_kwargs is None:
+            norm_op_kwargs = {'eps': 1e-5, 'affine': True, 'momentum': 0.1}
+        if conv_kwargs is None:
+            conv_kwargs = {'kernel_size': 3, 'stride': 1, 'padding': 1, 'dilation': 1, 'bias': True}
+        self.nonlin_kwargs = nonlin_kwargs
+        self.nonlin = nonlin
+        self.dropout_op = dropout_op
+        self.dropout_op_kwargs = dropout_op_kwargs
+        self.norm_op_kwargs = norm_op_kwargs
+        self.conv_kwargs = conv_kwargs
+        self.conv_op = conv_op
+        self.norm_op = norm_op
+        if first_stride is not None:
+            self.conv_kwargs_first_conv = deepcopy(conv_kwargs)
+            self.conv_kwargs_first_conv['stride'] = first_stride
+        else:
+            self.conv_kwargs_first_conv = conv_kwargs
+        super().__init__()
+        mk = lambda cin, kw: basic_block(cin, output_feature_channels, self.conv_op, kw, self.norm_op,
+                                         self.norm_op_kwargs, self.dropout_op, self.dropout_op_kwargs, self.nonlin,
+                                         self.nonlin_kwargs)
+        self.blocks = nn.Sequential(*([mk(input_feature_channels, self.conv_kwargs_first_conv)] +
+                                      [mk(output_feature_channels, self.conv_kwargs) for _ in range(num_convs - 1)]))
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class Upsample(nn.Module):
+    def __init__(self, size=None, scale_factor=None, mode='nearest', align_corners=False):
+        super().__init__()
+        self.align_corners = align_corners
+        self.mode = mode
+        self.scale_factor = scale_factor
+        self.size = size
+
+    def forward(self, x):
+        raise NotImplementedError("Upsample is unreachable on the E2ENet path (convolutional_upsampling=True)")
+
+
+class Generic_UNetPlusPlus(SegmentationNetwork):
+    """UNet++-style DSFF grid of depth-shifted convs (reference unetpp_d.py:210-591); 5 pooling
+    stages exactly, like the reference's forward."""
+    DEFAULT_BATCH_SIZE_3D = 2
+    DEFAULT_PATCH_SIZE_3D = (64, 192, 160)
+    SPACING_FACTOR_BETWEEN_STAGES = 2
+    BASE_NUM_FEATURES_3D = 30
+    MAX_NUMPOOL_3D = 999
+    MAX_NUM_FILTERS_3D = 320
+    DEFAULT_PATCH_SIZE_2D = (256, 256)
+    BASE_NUM_FEATURES_2D = 30
+    DEFAULT_BATCH_SIZE_2D = 50
+    MAX_NUMPOOL_2D = 999
+    MAX_FILTERS_2D = 480
+    use_this_for_batch_size_computation_2D = 19739648
+    use_this_for_batch_size_computation_3D = 520000000 * 2
+
+    def __init__(self, img_size, input_channels, base_num_features, num_classes, num_pool, num_conv_per_stage=2,
+                 feat_map_mul_on_downscale=2, conv_op=nn.Conv2d,
+                 norm_op=nn.BatchNorm2d, norm_op_kwargs=None,
+                 dropout_op=nn.Dropout2d, dropout_op_kwargs=None,
+                 nonlin=nn.LeakyReLU, nonlin_kwargs=None, deep_supervision=True, dropout_in_localization=False,
+                 final_nonlin=softmax_helper, weightInitializer=InitWeights_He(1e-2), pool_op_kernel_sizes=None,
+                 conv_kernel_sizes=None,
+                 upscale_logits=False, convolutional_pooling=False, convolutional_upsampling=False,
+                 max_num_features=None, basic_block=ConvDropoutNormNonlin,
+                 seg_output_use_bias=False):
+        super().__init__()
+        if conv_op != nn.Conv3d:
+            raise NotImplementedError("the E2ENet B200 path is 3-D only (reference trainer passes nn.Conv3d)")
+        if num_pool != 5:
+            raise ValueError("Generic_UNetPlusPlus.forward is hard-wired to 5 pooling stages "
+                             "(reference unetpp_d.py:451-478); got num_pool=%d" % num_pool)
+        if not (convolutional_pooling and convolutional_upsampling):
+            raise NotImplementedError("only convolutional_pooling=True, convolutional_upsampling=True is on the "
+                                      "E2ENet path (nnUNetTrainer_simple.py:300)")
+        if upscale_logits or seg_output_use_bias or num_conv_per_stage != 2:
+            raise NotImplementedError("upscale_logits / seg_output_use_bias / num_conv_per_stage != 2 unsupported")
+        self.convolutional_upsampling = convolutional_upsampling
+        self.convolutional_pooling = convolutional_pooling
+        self.upscale_logits = upscale_logits
+        if nonlin_kwargs is None:
+            nonlin_kwargs = {'negative_slope': 1e-2, 'inplace': True}
+        if dropout_op_kwargs is None:
+            dropout_op_kwargs = {'p': 0.5, 'inplace': True}
+        if norm_op_kwargs is None:
+            norm_op_kwargs = {'eps': 1e-5, 'affine': True, 'momentum': 0.1}
+        self.conv_kwargs = {'stride': 1, 'dilation': 1, 'bias': True}
+        self.nonlin = nonlin
+        self.nonlin_kwargs = nonlin_kwargs
+        self.dropout_op_kwargs = dropout_op_kwargs
+        self.norm_op_kwargs = norm_op_kwargs
+        self.weightInitializer = weightInitializer
+        self.conv_op = conv_op
+        self.norm_op = norm_op
+        self.dropout_op = dropout_op
+        self.num_classes = num_classes
+        self.final_nonlin = final_nonlin
+        self._deep_supervision = deep_supervision
+        self.do_ds = deep_supervision
+        self.input_channels = input_channels
+
+        if pool_op_kernel_sizes is None:
+            pool_op_kernel_sizes = [(2, 2, 2)] * num_pool
+        pools = [_triple(p) for p in pool_op_kernel_sizes]
+        conv_kernel_sizes = [(1, 3, 3)] * (num_pool + 1)          # forced, as in the reference (:286-287)
+        self.input_shape_must_be_divisible_by = np.prod(pool_op_kernel_sizes, 0, dtype=np.int64)
+        self.pool_op_kernel_sizes = pool_op_kernel_sizes
+        self.conv_kernel_sizes = conv_kernel_sizes
+        self.conv_pad_sizes = [[1 if i == 3 else 0 for i in k] for k in conv_kernel_sizes]
+        self.max_num_features = self.MAX_NUM_FILTERS_3D if max_num_features is None else max_num_features
+
+        feats = [base_num_features]
+        for _ in range(num_pool):
+            feats.append(min(int(np.round(feats[-1] * feat_map_mul_on_downscale)), self.max_num_features))
+        self._feats, self._pools = feats, pools
+
+        kw = dict(self.conv_kwargs, kernel_size=(1, 3, 3), padding=[0, 1, 1])
+        common = (self.conv_op, kw, self.norm_op, self.norm_op_kwargs, self.dropout_op, self.dropout_op_kwargs,
+                  self.nonlin, self.nonlin_kwargs)
+        p0 = self.dropout_op_kwargs['p']
+
+        # encoder column (reference :326-371)
+        ctx = []
+        cin = input_channels
+        for d in range(num_pool):
+            first_stride = pools[d - 1] if d != 0 else None
+            ctx.append(StackedConvLayers(cin, feats[d], num_conv_per_stage, *common, first_stride, basic_block=basic_block))
+            cin = feats[d]
+        ctx.append(nn.Sequential(
+            StackedConvLayers(cin, feats[num_pool], num_conv_per_stage - 1, *common, pools[-1], basic_block=basic_block),
+            StackedConvLayers(feats[num_pool], feats[num_pool], 1, *common, basic_block=basic_block)))
+
+        if not dropout_in_localization:
+            self.dropout_op_kwargs['p'] = 0.0
+        # nests (reference create_nest, :491-550): node x{i}_{j} <- loc{z}[j-1], z = 5-i-j
+        locs, ups, downs = [], [], []
+        for z in range(num_pool):
+            lz, uz, dz = [], [], []
+            for idx in range(num_pool - z):
+                i = num_pool - z - (idx + 1)
+                n_cat = 2 * feats[i] + (feats[i - 1] if i > 0 else 0)
+                blocks = [StackedConvLayers(n_cat, feats[i], num_conv_per_stage - 1, *common, basic_block=basic_block)]
+                if z == 0:
+                    blocks.append(StackedConvLayers(feats[i], feats[i], 1, *common, basic_block=basic_block))
+                lz.append(nn.Sequential(*blocks))
+                uz.append(nn.ConvTranspose3d(feats[i + 1], feats[i], pools[i], pools[i], bias=False))
+                if i > 0:
+                    dz.append(nn.MaxPool3d(pools[i - 1]))
+            locs.append(lz)
+            ups.append(uz)
+            downs.append(dz)
+        if not dropout_in_localization:
+            self.dropout_op_kwargs['p'] = p0
+
+        seg = [conv_op(feats[k], num_classes, 1, 1, 0, 1, 1, seg_output_use_bias) for k in range(4)]
+        self.upscale_logits_ops = [lambda x: x for _ in range(num_pool - 1)]
+
+        # registration order = reference (:418-438): it fixes named_parameters() order and thereby
+        # the Masking loop order and its Python-RNG stream
+        for z in range(5):
+            setattr(self, "loc%d" % z, nn.ModuleList(locs[z]))
+        self.conv_blocks_context = nn.ModuleList(ctx)
+        self.td = nn.ModuleList([])
+        for z in range(5):
+            setattr(self, "up%d" % z, nn.ModuleList(ups[z]))
+        for z in range(5):
+            setattr(self, "down%d" % z, nn.ModuleList(downs[z]))
+        self.seg_outputs = nn.ModuleList(seg)
+
+        self._tplans, self._splans = {}, {}
+        if self.weightInitializer is not None:
+            self.apply(self.weightInitializer)
+
+    # ------------------------------------------------------------------ helpers
+    def _tconv(self, mod: nn.ConvTranspose3d, x: C8) -> C8:
+        key = id(mod)
+        if key not in self._tplans:
+            if tuple(mod.kernel_size) != tuple(mod.stride) or mod.bias is not None:
+                raise NotImplementedError("transposed conv must have kernel == stride and no bias")
+            self._tplans[key] = build_tconv_plan(mod.in_channels, mod.out_channels, mod.kernel_size)
+        y = ops.TConv.apply(self._tplans[key], mod.weight, getattr(mod, "e2e_weight_mask", None), x.tensor)
+        return C8(y, [mod.out_channels])
+
+    def _pool(self, mod: nn.MaxPool3d, x: C8) -> C8:
+        return C8(ops.MaxPool.apply(x.tensor, _triple(mod.kernel_size)), x.channels)
+
+    def _seg(self, k: int, x: C8):
+        mod = self.seg_outputs[k]
+        if k not in self._splans:
+            self._splans[k] = build_seghead_plan(mod.in_channels, mod.out_channels)
+        return ops.SegHead.apply(self._splans[k], mod.weight, x.tensor)
+
+    # ------------------------------------------------------------------ forward (reference :447-488)
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("Generic_UNetPlusPlus (B200): input must be a CUDA tensor; there is no CPU fallback")
+        node = {}
+        h = C8(ops.ToC8.apply(x), [x.shape[1]])
+        for s in range(6):
+            h = self.conv_blocks_context[s](h)
+            node[(s, 0)] = h
+        for j in range(1, 6):
+            for i in range(5 - j, -1, -1):
+                z, idx = 5 - i - j, j - 1
+                parts = [node[(i, j - 1)], self._tconv(getattr(self, "up%d" % z)[idx], node[(i + 1, j - 1)])]
+                if i > 0:
+                    parts.append(self._pool(getattr(self, "down%d" % z)[idx], node[(i - 1, j - 1)]))
+                node[(i, j)] = getattr(self, "loc%d" % z)[idx](C8.cat(parts))
+        seg_outputs = [self.final_nonlin(self._seg(3, node[(3, 2)])), self.final_nonlin(self._seg(2, node[(2, 3)])),
+                       self.final_nonlin(self._seg(1, node[(1, 4)])), self.final_nonlin(self._seg(0, node[(0, 5)]))]
+        if self._deep_supervision and self.do_ds:
+            return list([seg_outputs[-1]] + [i(j) for i, j in zip(list(self.upscale_logits_ops)[::-1],
+                                                                   seg_outputs[:-1][::-1])])
+        return seg_outputs[-1]
+
+    @staticmethod
+    def compute_approx_vram_consumption(patch_size, num_pool_per_axis, base_num_features, max_num_features,
+                                        num_modalities, num_classes, pool_op_kernel_sizes, deep_supervision=False,
+                                        conv_per_stage=2):
+        if not isinstance(num_pool_per_axis, np.ndarray):
+            num_pool_per_axis = np.array(num_pool_per_axis)
+        npool = len(pool_op_kernel_sizes)
+        map_size = np.array(patch_size)
+        tmp = np.int64((conv_per_stage * 2 + 1) * np.prod(map_size, dtype=np.int64) * base_num_features +
+                       num_modalities * np.prod(map_size, dtype=np.int64) +
+                       num_classes * np.prod(map_size, dtype=np.int64))
+        num_feat = base_num_features
+        for p in range(npool):
+            for pi in range(len(num_pool_per_axis)):
+                map_size[pi] /= pool_op_kernel_sizes[p][pi]
+            num_feat = min(num_feat * 2, max_num_features)
+            num_blocks = (conv_per_stage * 2 + 1) if p < (npool - 1) else conv_per_stage
+            tmp += num_blocks * np.prod(map_size, dtype=np.int64) * num_feat
+            if deep_supervision and p < (npool - 2):
+                tmp += np.prod(map_size, dtype=np.int64) * num_classes
+        return tmp

@@ -1,0 +1,363 @@
+"""torch.autograd glue over the C ABI (include/e2enet_b200.h).
+
+Activations travel between ops in the "C8" layout: bf16 tensors of shape
+(B, C/8, D, H, W, 8).  Every op below enqueues hand-written CUDA kernels from
+libe2enet_b200.so on torch's current stream; torch is used for memory, streams and the
+autograd tape only.  There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
+
+EPS = 1e-5
+# 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
+CONFIG = {"impl": 0}
+# optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
+# (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
+PROFILE = {"enabled": False, "records": []}
+
+
+def _plan_flops(plan: GemmPlan, M: int) -> float:
+    if "_kn" not in plan._dev:
+        import numpy as np
+        plan._dev["_kn"] = (int((plan.centoff >= 0).sum()) * plan.n_taps, int((plan.rowoff >= 0).sum()))
+    k, n = plan._dev["_kn"]
+    return 2.0 * M * k * n
+
+
+class _Timed(object):
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE["enabled"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if PROFILE["enabled"]:
+            self.e1.record()
+            PROFILE["records"].append((self.kind, self.e0, self.e1, self.flops))
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.E2EError("%s: tensor is on %s; the E2ENet B200 ops run on CUDA only (no CPU fallback)" % (what, t.device))
+
+
+def c8_shape(x: torch.Tensor):
+    B, Cb, D, H, W, e = x.shape
+    assert e == 8 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    return B, Cb, D, H, W
+
+
+# ---------------------------------------------------------------------------------------- raw calls
+def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    lib = _lib.load()
+    dev = plan.dev(weight.device)
+    out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
+    w = weight.detach()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    if mask is not None:
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == w.shape
+    _lib.check(lib.e2e_pack_weights(_p(w), _p(mask), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]),
+                                    plan.n_cent, plan.n_taps, plan.Npad, _p(out), _lib.stream_ptr()), "pack_weights")
+    return out
+
+
+def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int,
+             dsts: Sequence[torch.Tensor], dst_grid, dst_cb: Sequence[int], impl: int = 0):
+    lib = _lib.load()
+    dev = plan.dev(srcs[0].device)
+    p = _lib.GemmParams()
+    p.B = B
+    p.Di, p.Hi, p.Wi = src_grid
+    p.Do, p.Ho, p.Wo = iter_grid
+    p.isd, p.ish, p.isw = plan.istride
+    p.ivd, p.ivh, p.ivw = plan.ivoff
+    p.Dd, p.Hd, p.Wd = dst_grid
+    p.osd, p.osh, p.osw = plan.ostride
+    p.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        p.src[i] = s.data_ptr()
+        p.src_cb[i] = s.shape[1]
+    p.n_cent = plan.n_cent
+    p.cents = dev["cents"].data_ptr()
+    p.n_taps = plan.n_taps
+    p.taps = dev["taps"].data_ptr()
+    p.wpacked = wpacked.data_ptr()
+    p.Npad = plan.Npad
+    p.cols = dev["cols"].data_ptr()
+    p.n_dst = len(dsts)
+    for i, d in enumerate(dsts):
+        p.dst[i] = d.data_ptr()
+        p.dst_cb[i] = dst_cb[i]
+    p.out_mode = plan.out_mode
+    p.impl = impl
+    with _Timed("gemm", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
+        _lib.check(lib.e2e_gather_gemm(C.byref(p), _lib.stream_ptr()), "gather_gemm")
+
+
+def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, grad: torch.Tensor,
+              weight_shape, impl: int = 0) -> torch.Tensor:
+    """returns the fp32 weight gradient in the reference's parameter layout."""
+    lib = _lib.load()
+    device = grad.device
+    dev = plan.dev(device)
+    dwp = torch.zeros(plan.packed_numel, dtype=torch.float32, device=device)
+    p = _lib.WgradParams()
+    p.B = B
+    p.Di, p.Hi, p.Wi = src_grid
+    p.Do, p.Ho, p.Wo = iter_grid
+    p.isd, p.ish, p.isw = plan.istride
+    p.ivd, p.ivh, p.ivw = (0, 0, 0)
+    p.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        p.src[i] = s.data_ptr()
+        p.src_cb[i] = s.shape[1]
+    p.n_cent = plan.n_cent
+    p.cents = dev["cents"].data_ptr()
+    p.n_taps = plan.n_taps
+    p.taps = dev["taps"].data_ptr()
+    p.grad = grad.data_ptr()
+    p.grad_cb = grad.shape[1]
+    p.Npad = plan.Npad
+    p.dwp = dwp.data_ptr()
+    p.impl = impl
+    with _Timed("wgrad", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
+        _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
+    gw = torch.zeros(weight_shape, dtype=torch.float32, device=device)
+    _lib.check(lib.e2e_unpack_wgrad(_p(dwp), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]), plan.n_cent,
+                                    plan.n_taps, plan.Npad, _p(gw), _lib.stream_ptr()), "unpack_wgrad")
+    return gw
+
+
+def nc_to_c8(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x, "nc_to_c8")
+    x = x.detach().contiguous().float()
+    B, Cc = x.shape[:2]
+    sp = tuple(x.shape[2:])
+    V = 1
+    for s in sp:
+        V *= s
+    y = torch.empty((B, (Cc + 7) // 8) + sp + (8,), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.load().e2e_nc_to_c8(_p(x), _p(y), B, Cc, V, _lib.stream_ptr()), "nc_to_c8")
+    return y
+
+
+def c8_to_nc(x: torch.Tensor, channels: int) -> torch.Tensor:
+    B, Cb, D, H, W = c8_shape(x)
+    y = torch.empty((B, channels, D, H, W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().e2e_c8_to_nc(_p(x), _p(y), B, channels, D * H * W, _lib.stream_ptr()), "c8_to_nc")
+    return y
+
+
+def _nchunk(V: int, planes: int) -> int:
+    n = max(1, min((V + 2047) // 2048, (148 * 8 + planes - 1) // planes))
+    return int(n)
+
+
+# ---------------------------------------------------------------------------------------- autograd ops
+class ToC8(torch.autograd.Function):
+    """fp32 NCDHW -> bf16 C8 (differentiable, used at the module boundary)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.channels = x.shape[1]
+        return nc_to_c8(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return c8_to_nc(dy.contiguous(), ctx.channels)
+
+
+class FromC8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, channels):
+        return c8_to_nc(x, channels)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return nc_to_c8(dy), None
+
+
+class ShiftConvINLReLU(torch.autograd.Function):
+    """depth-shift + Conv3d(1,3,3) + InstanceNorm3d(affine) + LeakyReLU over a virtual concat
+    of C8 sources (reference: ConvDropoutNormNonlin.forward, unetpp_d.py:102-111).
+    The conv bias is carried for state_dict/grad parity but not added: InstanceNorm removes
+    any per-channel constant exactly."""
+
+    @staticmethod
+    def forward(ctx, plan: ShiftConvPlan, slope: float, weight, bias, gamma, beta, mask, *srcs):
+        lib = _lib.load()
+        for s in srcs:
+            _need_cuda(s, "shiftconv")
+        B, _, D, H, W = c8_shape(srcs[0])
+        Do, Ho, Wo = plan.out_grid(D, H, W)
+        dev = srcs[0].device
+        Cb = plan.cout // 8
+        impl = CONFIG["impl"]
+        wp = pack_weights(plan.fwd, weight, mask)
+        raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
+        run_gemm(plan.fwd, wp, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], impl)
+        V = Do * Ho * Wo
+        nch = _nchunk(V, B * Cb)
+        partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+        mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        _lib.check(lib.e2e_in_stats(_p(raw), B, Cb, V, EPS, _p(partial), nch, _p(mean), _p(rstd), _lib.stream_ptr()),
+                   "in_stats")
+        y = torch.empty_like(raw)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(lib.e2e_in_apply(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, V, _p(y),
+                                    _lib.stream_ptr()), "in_apply")
+        ctx.plan, ctx.slope, ctx.mask, ctx.grid = plan, slope, mask, (B, D, H, W, Do, Ho, Wo)
+        ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, *srcs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        plan: ShiftConvPlan = ctx.plan
+        weight, gamma, beta, raw, mean, rstd = ctx.saved_tensors[:6]
+        srcs = ctx.saved_tensors[6:]
+        B, D, H, W, Do, Ho, Wo = ctx.grid
+        dev = dy.device
+        Cb = plan.cout // 8
+        V = Do * Ho * Wo
+        impl = CONFIG["impl"]
+        dy = dy.contiguous()
+        nch = _nchunk(V, B * Cb)
+        partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+        sums = torch.empty(B * Cb * 16, dtype=torch.float32, device=dev)
+        draw = torch.empty_like(raw)
+        dgamma = torch.empty(plan.cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty_like(dgamma)
+        dbias = torch.empty_like(dgamma)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        _lib.check(lib.e2e_in_bwd(_p(dy), _p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), ctx.slope, B, Cb, V,
+                                  _p(partial), nch, _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
+                                  _lib.stream_ptr()), "in_bwd")
+        # weight gradient (dense, also at masked positions: SURVEY H3)
+        gw = None
+        if ctx.needs_input_grad[2]:
+            gw = run_wgrad(plan.fwd, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl)
+        # data gradients of every source
+        need = [ctx.needs_input_grad[7 + i] for i in range(len(srcs))]
+        dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
+        if any(need):
+            outs = [torch.empty_like(s) for s in srcs]
+            sd, sh, sw = plan.stride
+            idx = 0
+            for var in plan.dgrad:
+                pd, ph, pw = int(var.cols[0][3]), int(var.cols[0][4]), int(var.cols[0][5])
+                it = ((D - pd + sd - 1) // sd, (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw)
+                idx += 1
+                if min(it) <= 0:
+                    continue
+                wpd = pack_weights(var, weight, ctx.mask)
+                run_gemm(var, wpd, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W), [s.shape[1] for s in srcs], 0)
+            dsrcs = [o if n else None for o, n in zip(outs, need)]
+        return (None, None, gw, dbias.to(weight.dtype) if ctx.needs_input_grad[3] else None,
+                dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, *dsrcs)
+
+
+class TConv(torch.autograd.Function):
+    """ConvTranspose3d(kernel == stride, bias=False) on C8 tensors (unetpp_d.py:521-522)."""
+
+    @staticmethod
+    def forward(ctx, plan: TConvPlan, weight, mask, x):
+        _need_cuda(x, "tconv")
+        B, Cb, D, H, W = c8_shape(x)
+        kd, kh, kw = plan.k
+        wp = pack_weights(plan.fwd, weight, mask)
+        y = torch.empty((B, plan.cout // 8, D * kd, H * kh, W * kw, 8), dtype=torch.bfloat16, device=x.device)
+        run_gemm(plan.fwd, wp, [x], (D, H, W), (D, H, W), B, [y], (D * kd, H * kh, W * kw), [plan.cout // 8], 0)
+        ctx.plan, ctx.mask = plan, mask
+        ctx.save_for_backward(weight, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan: TConvPlan = ctx.plan
+        weight, x = ctx.saved_tensors
+        B, Cb, D, H, W = c8_shape(x)
+        kd, kh, kw = plan.k
+        dy = dy.contiguous()
+        fine = (D * kd, H * kh, W * kw)
+        gw = dx = None
+        if ctx.needs_input_grad[1]:
+            gw = run_wgrad(plan.dgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), 0)
+        if ctx.needs_input_grad[3]:
+            wp = pack_weights(plan.dgrad, weight, ctx.mask)
+            dx = torch.empty_like(x)
+            run_gemm(plan.dgrad, wp, [dy], fine, (D, H, W), B, [dx], (D, H, W), [Cb], 0)
+        return None, gw, None, dx
+
+
+class MaxPool(torch.autograd.Function):
+    """MaxPool3d(kernel == stride) on C8 tensors (unetpp_d.py:523-524)."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        _need_cuda(x, "maxpool")
+        B, Cb, D, H, W = c8_shape(x)
+        kd, kh, kw = (int(v) for v in k)
+        y = torch.empty((B, Cb, D // kd, H // kh, W // kw, 8), dtype=torch.bfloat16, device=x.device)
+        am = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+        _lib.check(_lib.load().e2e_maxpool_fwd(_p(x), _p(y), _p(am), B * Cb, D, H, W, kd, kh, kw, _lib.stream_ptr()),
+                   "maxpool_fwd")
+        ctx.k, ctx.shape = (kd, kh, kw), (B, Cb, D, H, W)
+        ctx.save_for_backward(am)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (am,) = ctx.saved_tensors
+        B, Cb, D, H, W = ctx.shape
+        kd, kh, kw = ctx.k
+        dx = torch.empty((B, Cb, D, H, W, 8), dtype=torch.bfloat16, device=dy.device)
+        _lib.check(_lib.load().e2e_maxpool_bwd(_p(dy.contiguous()), _p(am), _p(dx), B * Cb, D, H, W, kd, kh, kw,
+                                               _lib.stream_ptr()), "maxpool_bwd")
+        return dx, None
+
+
+class SegHead(torch.autograd.Function):
+    """Conv3d(C, ncls, 1, bias=False): C8 bf16 in, fp32 NCDHW logits out (unetpp_d.py:394-401)."""
+
+    @staticmethod
+    def forward(ctx, plan: SegHeadPlan, weight, x):
+        _need_cuda(x, "seghead")
+        B, Cb, D, H, W = c8_shape(x)
+        wp = pack_weights(plan.fwd, weight, None)
+        y = torch.empty((B, plan.ncls, D, H, W), dtype=torch.float32, device=x.device)
+        run_gemm(plan.fwd, wp, [x], (D, H, W), (D, H, W), B, [y], (D, H, W), [plan.ncls], 0)
+        ctx.plan = plan
+        ctx.save_for_backward(weight, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan: SegHeadPlan = ctx.plan
+        weight, x = ctx.saved_tensors
+        B, Cb, D, H, W = c8_shape(x)
+        g = nc_to_c8(dy)
+        gw = dx = None
+        if ctx.needs_input_grad[1]:
+            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), 0)
+        if ctx.needs_input_grad[2]:
+            wp = pack_weights(plan.dgrad, weight, None)
+            dx = torch.empty_like(x)
+            run_gemm(plan.dgrad, wp, [g], (D, H, W), (D, H, W), B, [dx], (D, H, W), [Cb], 0)
+        return None, gw, dx

@@ -1,0 +1,238 @@
+"""Host-side plan builder for the plan-driven gather GEMMs (include/e2enet_b200.h).
+
+A plan is a handful of small int32 tables that tell the CUDA kernels
+  * which 8-channel blocks of which source tensors form the K dimension, and at which
+    spatial offset each block is fetched (this is where the reference's depth shift,
+    unetpp_d.py:45-59, and its torch.cat, unetpp_d.py:453-478, disappear),
+  * which filter taps exist and where each packed weight comes from in the reference's
+    fp32 parameter tensor (so state_dict layout stays the reference's),
+  * where each 8-column block of the result is stored.
+Plans depend only on layer geometry; they are built once and cached on the device.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+SHIFT_SIZE = 5
+
+
+def ceil_to(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def channel_shifts(C: int, shift_size: int = SHIFT_SIZE) -> np.ndarray:
+    """shift of every channel of a C-channel (concatenated) conv input: torch.chunk(x, 5, 1)
+    makes groups of ceil(C/5); group k is rolled by k - 2 (unetpp_d.py:54-56)."""
+    g = -(-C // shift_size)
+    return (np.arange(C) // g - shift_size // 2).astype(np.int64)
+
+
+@dataclass
+class GemmPlan:
+    cents: np.ndarray            # (n_cent, 5) src, blk, dd, dh, dw
+    taps: np.ndarray             # (n_taps, 3)
+    cols: np.ndarray             # (Npad/8, 6) dst, blk, chmask, od, oh, ow
+    rowoff: np.ndarray           # (Npad,)
+    centoff: np.ndarray          # (n_cent*8,)
+    tapoff: np.ndarray           # (n_taps,)
+    Npad: int
+    istride: Tuple[int, int, int] = (1, 1, 1)
+    ivoff: Tuple[int, int, int] = (0, 0, 0)
+    ostride: Tuple[int, int, int] = (1, 1, 1)
+    out_mode: int = 0
+    _dev: Dict = field(default_factory=dict, repr=False)
+
+    @property
+    def n_cent(self) -> int:
+        return int(self.cents.shape[0])
+
+    @property
+    def n_taps(self) -> int:
+        return int(self.taps.shape[0])
+
+    @property
+    def packed_numel(self) -> int:
+        return self.n_cent * self.n_taps * self.Npad * 8
+
+    def dev(self, device):
+        """device copies of the tables (uploaded once per device)."""
+        import torch
+        key = str(device)
+        if key not in self._dev:
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+            self._dev[key] = dict(cents=t(self.cents), taps=t(self.taps), cols=t(self.cols), rowoff=t(self.rowoff),
+                                  centoff=t(self.centoff), tapoff=t(self.tapoff))
+        return self._dev[key]
+
+
+def _pad_even(cents: List[List[int]], centoff: List[List[int]]):
+    if len(cents) % 2:
+        cents.append([0, 0, 0, 0, 0])
+        centoff.append([-1] * 8)
+
+
+def _finish(cents, centoff, taps, tapoff, cols, rowoff, **kw) -> GemmPlan:
+    Npad = ceil_to(max(len(rowoff), 1), 16)
+    rowoff = list(rowoff) + [-1] * (Npad - len(rowoff))
+    cols = list(cols)
+    while len(cols) < Npad // 8:
+        cols.append([-1, 0, 0, 0, 0, 0])
+    return GemmPlan(cents=np.asarray(cents, np.int32).reshape(-1, 5), taps=np.asarray(taps, np.int32).reshape(-1, 3),
+                    cols=np.asarray(cols, np.int32).reshape(-1, 6), rowoff=np.asarray(rowoff, np.int32),
+                    centoff=np.asarray(centoff, np.int32).reshape(-1), tapoff=np.asarray(tapoff, np.int32),
+                    Npad=Npad, **kw)
+
+
+# ----------------------------------------------------------------------------------------
+# depth-shifted (1,3,3) conv over a virtual concat of sources
+# ----------------------------------------------------------------------------------------
+@dataclass
+class ShiftConvPlan:
+    src_channels: List[int]
+    cin: int
+    cout: int
+    stride: Tuple[int, int, int]
+    fwd: GemmPlan
+    dgrad: List[GemmPlan]        # variants; every element of every source gradient is written exactly once
+
+    def out_grid(self, D, H, W):
+        sd, sh, sw = self.stride
+        return (D - 1) // sd + 1, (H + 2 - 3) // sh + 1, (W + 2 - 3) // sw + 1
+
+
+def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1), shift: bool = True) -> ShiftConvPlan:
+    src_channels = [int(c) for c in src_channels]
+    cin = sum(src_channels)
+    stride = tuple(int(s) for s in stride)
+    assert cout % 8 == 0, "Cout must be a multiple of 8 (C8 layout)"
+    sh_c = channel_shifts(cin) if shift else np.zeros(cin, np.int64)
+    src_off = np.concatenate([[0], np.cumsum(src_channels)]).astype(int)
+
+    # ---- forward: K = (source block, shift) entries x 9 taps
+    cents, centoff = [], []
+    for i, ci in enumerate(src_channels):
+        for blk in range((ci + 7) // 8):
+            chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
+            for s in sorted({int(sh_c[c]) for c in chans if c >= 0}):
+                cents.append([i, blk, -s, 0, 0])                  # x~[d] = x[d - s]
+                centoff.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
+    _pad_even(cents, centoff)
+    taps = [[0, kh - 1, kw - 1] for kh in range(3) for kw in range(3)]
+    tapoff = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+    cols = [[0, q, 0xff, 0, 0, 0] for q in range(cout // 8)]
+    rowoff = [n * cin * 9 for n in range(cout)]
+    fwd = _finish(cents, centoff, taps, tapoff, cols, rowoff, istride=stride)
+
+    # ---- dgrad: source of the GEMM is d(raw) on the conv's output grid, K = Cout x taps
+    g_cents = [[0, e, 0, 0, 0] for e in range(cout // 8)]
+    g_centoff = [[(e * 8 + j) * cin * 9 for j in range(8)] for e in range(cout // 8)]
+    _pad_even(g_cents, g_centoff)
+    sd, shh, sww = stride
+    variants: List[GemmPlan] = []
+    for s in sorted({int(v) for v in sh_c}):
+        vcols, vrow = [], []
+        for i, ci in enumerate(src_channels):
+            for blk in range((ci + 7) // 8):
+                chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
+                m = 0
+                for j, c in enumerate(chans):
+                    if c >= 0 and sh_c[c] == s:
+                        m |= 1 << j
+                if m:
+                    vcols.append((i, blk, m))
+                    vrow.extend([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
+        for pd in range(sd):
+            for ph in range(shh):
+                for pw in range(sww):
+                    # dx[c, d'] = dx~[c, d'+s];  dx~ lives on depths that are multiples of sd
+                    ok_d = (pd + s) % sd == 0
+                    vt, vto = [], []
+                    if ok_d:
+                        for kh in range(3):
+                            if (ph - kh + 1) % shh:
+                                continue
+                            for kw in range(3):
+                                if (pw - kw + 1) % sww:
+                                    continue
+                                vt.append([0, (ph - kh + 1) // shh, (pw - kw + 1) // sww])
+                                vto.append(kh * 3 + kw)
+                    live = bool(vt)
+                    if not live:
+                        vt, vto = [[0, 0, 0]], [0]
+                    cols_v = [[i, blk, m, pd, ph, pw] for (i, blk, m) in vcols]
+                    row_v = list(vrow) if live else [-1] * len(vrow)
+                    variants.append(_finish([list(c) for c in g_cents], [list(c) for c in g_centoff], vt, vto, cols_v,
+                                            row_v, istride=(1, 1, 1),
+                                            ivoff=((pd + s) // sd if ok_d else 0, 0, 0), ostride=stride))
+    return ShiftConvPlan(src_channels, cin, cout, stride, fwd, variants)
+
+
+# ----------------------------------------------------------------------------------------
+# ConvTranspose3d with kernel == stride (the up* modules), weight (Cin, Cout, kd, kh, kw)
+# ----------------------------------------------------------------------------------------
+@dataclass
+class TConvPlan:
+    cin: int
+    cout: int
+    k: Tuple[int, int, int]
+    fwd: GemmPlan
+    dgrad: GemmPlan               # also the wgrad gather plan (same entries, grad = x)
+
+
+def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
+    k = tuple(int(v) for v in k)
+    kd, kh, kw = k
+    kv = kd * kh * kw
+    assert cin % 8 == 0 and cout % 8 == 0
+    tl = [(a, b, c) for a in range(kd) for b in range(kh) for c in range(kw)]
+    # forward: K = Cin, N = (tap, Cout)
+    cents = [[0, e, 0, 0, 0] for e in range(cin // 8)]
+    centoff = [[(e * 8 + j) * cout * kv for j in range(8)] for e in range(cin // 8)]
+    _pad_even(cents, centoff)
+    cols, rowoff = [], []
+    for t, (a, b, c) in enumerate(tl):
+        for q in range(cout // 8):
+            cols.append([0, q, 0xff, a, b, c])
+            rowoff.extend([(q * 8 + j) * kv + t for j in range(8)])
+    fwd = _finish(cents, centoff, [[0, 0, 0]], [0], cols, rowoff, ostride=k)
+    # dgrad: K = (tap, Cout block) gathered from dy at u*k + tap, N = Cin
+    cents, centoff = [], []
+    for t, (a, b, c) in enumerate(tl):
+        for q in range(cout // 8):
+            cents.append([0, q, a, b, c])
+            centoff.append([(q * 8 + j) * kv + t for j in range(8)])
+    _pad_even(cents, centoff)
+    cols = [[0, q, 0xff, 0, 0, 0] for q in range(cin // 8)]
+    rowoff = [n * cout * kv for n in range(cin)]
+    dgrad = _finish(cents, centoff, [[0, 0, 0]], [0], cols, rowoff, istride=k)
+    return TConvPlan(cin, cout, k, fwd, dgrad)
+
+
+# ----------------------------------------------------------------------------------------
+# 1x1x1 seg head, weight (ncls, C, 1, 1, 1), logits returned as fp32 NCDHW
+# ----------------------------------------------------------------------------------------
+@dataclass
+class SegHeadPlan:
+    cin: int
+    ncls: int
+    fwd: GemmPlan
+    dgrad: GemmPlan
+
+
+def build_seghead_plan(cin: int, ncls: int) -> SegHeadPlan:
+    assert cin % 8 == 0
+    cents = [[0, e, 0, 0, 0] for e in range(cin // 8)]
+    centoff = [[e * 8 + j for j in range(8)] for e in range(cin // 8)]
+    _pad_even(cents, centoff)
+    rowoff = [n * cin for n in range(ncls)]
+    fwd = _finish(cents, centoff, [[0, 0, 0]], [0], [], rowoff, out_mode=1)
+    ncb = (ncls + 7) // 8
+    cents = [[0, e, 0, 0, 0] for e in range(ncb)]
+    centoff = [[(e * 8 + j) * cin if e * 8 + j < ncls else -1 for j in range(8)] for e in range(ncb)]
+    _pad_even(cents, centoff)
+    cols = [[0, q, 0xff, 0, 0, 0] for q in range(cin // 8)]
+    dgrad = _finish(cents, centoff, [[0, 0, 0]], [0], cols, list(range(cin)))
+    return SegHeadPlan(cin, ncls, fwd, dgrad)

@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference's training iteration for synthetic-data runs
+(nnUNetTrainer_simple.run_iteration, nnUNetTrainer_simple.py:529-583, and the setup in
+simple_main.py:145-168): zero_grad -> forward -> deep-supervision loss -> backward ->
+clip_grad_norm_(12) -> SGD(nesterov) step -> mask.step() -> loss read-back.
+
+The loss (DC_and_CE_loss wrapped in MultipleOutputLoss2; dice_loss.py:302-359,
+deep_supervision.py:18-43) and the optimizer are NOT part of the hot path this package
+replaces (SURVEY 8(f) ranks them "next"); they stay plain torch here exactly as the
+unchanged reference trainer would run them.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+POOLS = {
+    "btcv": [[1, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
+    "brats": [[2, 2, 2]] * 5,
+    "hippo": [[2, 2, 2]] * 3 + [[1, 1, 1]] * 2,
+}
+
+
+def build_network(in_ch: int, num_classes: int, pools, patch, base: int = 48, deep_supervision: bool = True):
+    """constructs the drop-in network with the positional arguments the reference trainer uses
+    (nnUNetTrainer_simple.py:292-301)."""
+    from .network_architecture.unetpp_d import Generic_UNetPlusPlus, InitWeights_He
+    return Generic_UNetPlusPlus(tuple(patch), in_ch, base, num_classes, len(pools), 2, 2, nn.Conv3d,
+                                nn.InstanceNorm3d, {'eps': 1e-5, 'affine': True}, nn.Dropout3d,
+                                {'p': 0, 'inplace': True}, nn.LeakyReLU, {'negative_slope': 1e-2, 'inplace': True},
+                                deep_supervision, False, lambda x: x, InitWeights_He(1e-2), pools, None, False, True,
+                                True)
+
+
+def ds_loss_weights(n_outputs: int = 4, net_numpool: int = 5) -> List[float]:
+    w = np.array([1 / (2 ** i) for i in range(net_numpool)])
+    w[-1] = 0
+    w = w / w.sum()
+    return [float(v) for v in w[:n_outputs]]
+
+
+def dc_and_ce_loss(logits: torch.Tensor, target: torch.Tensor, smooth: float = 1e-5) -> torch.Tensor:
+    """DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False}, {})"""
+    ce = F.cross_entropy(logits, target[:, 0].long())
+    prob = torch.softmax(logits, 1)
+    onehot = torch.zeros_like(prob).scatter_(1, target.long(), 1.0)
+    axes = tuple(range(2, logits.ndim))
+    tp = (prob * onehot).sum(axes)
+    fp = (prob * (1 - onehot)).sum(axes)
+    fn = ((1 - prob) * onehot).sum(axes)
+    dc = (2 * tp + smooth) / (2 * tp + fp + fn + smooth + 1e-8)
+    return ce - dc[:, 1:].mean()
+
+
+def multiple_output_loss(outs: Sequence[torch.Tensor], targets: Sequence[torch.Tensor]) -> torch.Tensor:
+    w = ds_loss_weights(len(outs))
+    l = w[0] * dc_and_ce_loss(outs[0], targets[0])
+    for i in range(1, len(outs)):
+        if w[i] != 0:
+            l = l + w[i] * dc_and_ce_loss(outs[i], targets[i])
+    return l
+
+
+def synthetic_batch(batch: int, in_ch: int, num_classes: int, patch, pools, seed: int = 1):
+    """the reference's dummy-load convention (nnUNetTrainerV2_dummyLoad.py:29-31): uniform data,
+    targets = round(rand * (ncls-1)) at the 4 deep-supervision scales.  Host tensors."""
+    g = torch.Generator().manual_seed(seed)
+    data = torch.rand((batch, in_ch) + tuple(patch), generator=g)
+    targets = []
+    sp = np.array(patch)
+    for k in range(4):
+        targets.append(torch.round(torch.rand((batch, 1) + tuple(int(v) for v in sp), generator=g) * (num_classes - 1)))
+        sp = sp // np.array(pools[k])
+    return data, targets
+
+
+class SparseArgs(argparse.Namespace):
+    adv = False
+    fix = False
+    update_frequency = 1200
+    final_density = 0.05
+
+
+class TrainStep(object):
+    """one data-parallel replica of the reference's training iteration on synthetic data."""
+
+    def __init__(self, in_ch=1, num_classes=14, pools=None, patch=(64, 160, 160), density=0.2, death_rate=0.5,
+                 update_frequency=1200, device="cuda", world_size=1, seed=0, base=48, total_steps=250000):
+        from .sparselearning.core_channel import CosineDecay, Masking
+        import random
+        pools = POOLS["btcv"] if pools is None else pools
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        self.pools, self.patch, self.in_ch, self.num_classes = pools, tuple(patch), in_ch, num_classes
+        self.network = build_network(in_ch, num_classes, pools, patch, base).to(self.device)
+        self.optimizer = torch.optim.SGD(self.network.parameters(), 1e-2, weight_decay=3e-5, momentum=0.99,
+                                         nesterov=True)
+        args = SparseArgs()
+        args.update_frequency = update_frequency
+        random.seed(seed)
+        self.mask = Masking(self.optimizer, death_rate=death_rate, death_mode='magnitude',
+                            death_rate_decay=CosineDecay(death_rate, total_steps), growth_mode='random',
+                            redistribution_mode='none', args=args)
+        self.mask.add_module(self.network, sparse_init='uniform', density=density)
+        self.world_size = world_size
+        self._flat = None
+
+    def _allreduce_grads(self):
+        """data-parallel gradient mean over NCCL (one flat bucket; grads are ~95 MB fp32)."""
+        import torch.distributed as dist
+        grads = [p.grad for p in self.network.parameters() if p.grad is not None]
+        flat = torch._utils._flatten_dense_tensors(grads)
+        dist.all_reduce(flat)
+        flat.div_(self.world_size)
+        for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+            g.copy_(s)
+
+    def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
+        self.optimizer.zero_grad()
+        output = self.network(data)
+        l = multiple_output_loss(output, targets)
+        l.backward()
+        if self.world_size > 1:
+            self._allreduce_grads()
+        torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+        self.optimizer.step()
+        self.mask.step()
+        return l.detach()

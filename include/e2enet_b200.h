@@ -1,0 +1,188 @@
+/*
+ * e2enet_b200.h -- C ABI of the B200-native E2ENet hot-path library (libe2enet_b200.so).
+ *
+ * Plain C, no torch types: device pointers, sizes and a cudaStream_t (passed as void*).
+ * Every entry point returns 0 on success or a negative error code; e2e_last_error()
+ * returns a human readable message for the calling thread.  All buffers (incl. scratch)
+ * are owned by the caller; the library only caches TMA tensor maps keyed by pointer+shape.
+ * Entry points only enqueue work on `stream`; none synchronises.
+ *
+ * Activation layout ("C8"): bf16 [B][C/8][D][H][W][8] -- channel-blocked so that one
+ * voxel's 8 channels are one 16-byte vector.  A [rows][8ch] slab of it is at the same
+ * time a K-major UMMA operand (fwd / dgrad: K = channels) and an MN-major one (wgrad:
+ * K = voxels), and a TMA box of it can be shifted per 8-channel block along D, which is
+ * how the reference's depth shift (unetpp_d.py:45-59) is folded into the operand fetch.
+ *
+ * Reference interfaces replaced (file:line in boqian333/E2ENet-Medical):
+ *   e2e_gather_gemm     torch_shift.forward + Conv3d fwd / dgrad, ConvTranspose3d fwd / dgrad,
+ *                       1x1x1 seg heads      e2enet/network_architecture/unetpp_d.py:45-59,102-108,394-401,521-522
+ *   e2e_gather_wgrad    Conv3d / ConvTranspose3d weight gradients (autograd of the above)
+ *   e2e_in_*            InstanceNorm3d(affine) + LeakyReLU fwd/bwd      unetpp_d.py:99-100,111
+ *   e2e_maxpool_*       MaxPool3d (down* modules)                       unetpp_d.py:523-524
+ *   e2e_pack_weights    `w.data * mask` on weight load                  core_channel.py:427-434
+ *   e2e_mask_*          Masking.apply_mask / kernel_death / kernel_growth / counts
+ *                       e2enet/training/network_training/sparselearning/core_channel.py:338-347,427-434,647-666,721-739,861-876
+ *   e2e_window_*        softmax + mirror + gaussian + `agg[:,tile] += ...`, `agg /= nb`, argmax
+ *                       e2enet/network_architecture/neural_network.py:370-407,529-563
+ */
+#ifndef E2ENET_B200_H
+#define E2ENET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2E_MAX_SRC 4
+
+#define E2E_OK 0
+#define E2E_ERR_ARG -1
+#define E2E_ERR_CUDA -2
+#define E2E_ERR_UNSUPPORTED -3
+
+const char* e2e_last_error(void);
+int e2e_version(void);
+/* number of kernels launched by this library in this process so far (bench: gpu_launches) */
+long long e2e_launch_count(void);
+
+/* ---------------------------------------------------------------- plan-driven gather GEMM */
+
+/* 8 input channels (one C8 block) of source `src`, fetched at spatial offset (dd,dh,dw) */
+typedef struct { int32_t src, blk, dd, dh, dw; } e2e_centry_t;
+/* one filter tap: additional spatial offset applied to every channel entry */
+typedef struct { int32_t dd, dh, dw; } e2e_tap_t;
+/* one 8-column block of the GEMM result: where it is stored */
+typedef struct { int32_t dst, blk, chmask, od, oh, ow; } e2e_colblk_t;
+
+/*
+ * out[o, n] = sum_{e, t, j}  src[cent[e].src][b, cent[e].blk, (o*is + iv + cent[e].off + tap[t].off), j]
+ *                            * wpacked[e/2][t][e%2][n][j]
+ * for every voxel o of the iteration grid (B, Do, Ho, Wo); out-of-range reads are 0.
+ * Column block q (columns 8q..8q+7) goes to dst[cols[q].dst], channel block cols[q].blk,
+ * voxel o*os + cols[q].off (skipped when outside the destination grid), channels selected
+ * by cols[q].chmask.
+ */
+typedef struct {
+  int32_t B, Di, Hi, Wi;       /* grid of every source tensor */
+  int32_t Do, Ho, Wo;          /* iteration grid (GEMM M = B*Do*Ho*Wo) */
+  int32_t isd, ish, isw;       /* input stride */
+  int32_t ivd, ivh, ivw;       /* input offset of this call (variant) */
+  int32_t Dd, Hd, Wd;          /* grid of every destination tensor */
+  int32_t osd, osh, osw;       /* output stride */
+  int32_t n_src;
+  const void* src[E2E_MAX_SRC];      /* device, bf16 C8 */
+  int32_t src_cb[E2E_MAX_SRC];       /* channel blocks of each source */
+  int32_t n_cent;                    /* even */
+  const e2e_centry_t* cents;         /* device */
+  int32_t n_taps;
+  const e2e_tap_t* taps;             /* device */
+  const void* wpacked;               /* device bf16 [n_cent/2][n_taps][2][Npad][8] */
+  int32_t Npad;                      /* multiple of 16 */
+  const e2e_colblk_t* cols;          /* device, Npad/8 entries */
+  int32_t n_dst;
+  void* dst[E2E_MAX_SRC];
+  int32_t dst_cb[E2E_MAX_SRC];       /* channel blocks (out_mode 0) or channel count (out_mode 1) */
+  int32_t out_mode;                  /* 0: bf16 C8   1: fp32 NCDHW (dst[0], column n -> channel n) */
+  int32_t impl;                      /* 0: mma.sync gather kernel   1: tcgen05/TMA kernel (stride-1 halo form) */
+} e2e_gemm_t;
+
+int e2e_gather_gemm(const e2e_gemm_t* p, void* stream);
+
+/*
+ * dwp[e/2][t][e%2][n][j] += sum_o grad[b, n/8, o, n%8] * src[...][(o*is + iv + cent[e].off + tap[t].off), j]
+ * (fp32, atomically accumulated: the caller zeroes dwp first).
+ */
+typedef struct {
+  int32_t B, Di, Hi, Wi;
+  int32_t Do, Ho, Wo;
+  int32_t isd, ish, isw;
+  int32_t ivd, ivh, ivw;
+  int32_t n_src;
+  const void* src[E2E_MAX_SRC];
+  int32_t src_cb[E2E_MAX_SRC];
+  int32_t n_cent;
+  const e2e_centry_t* cents;
+  int32_t n_taps;
+  const e2e_tap_t* taps;
+  const void* grad;                  /* device bf16 C8 on the iteration grid */
+  int32_t grad_cb;
+  int32_t Npad;                      /* multiple of 16, <= 8*grad_cb rounded up */
+  float* dwp;                        /* device fp32 [n_cent/2][n_taps][2][Npad][8] */
+  int32_t impl;
+} e2e_wgrad_t;
+
+int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream);
+
+/*
+ * wpacked[e/2][t][e%2][n][j] = bf16( w[rowoff[n] + centoff[e*8+j] + tapoff[t]] * (mask ? mask[same] : 1) )
+ * (0 where rowoff or centoff is negative).  This is where the DSFF mask meets the weights.
+ */
+int e2e_pack_weights(const float* w, const float* mask, const int32_t* rowoff, const int32_t* centoff,
+                     const int32_t* tapoff, int32_t n_cent, int32_t n_taps, int32_t Npad,
+                     void* wpacked, void* stream);
+/* grad[rowoff[n] + centoff[e*8+j] + tapoff[t]] = dwp[...]  (inverse scatter; every weight appears once) */
+int e2e_unpack_wgrad(const float* dwp, const int32_t* rowoff, const int32_t* centoff, const int32_t* tapoff,
+                     int32_t n_cent, int32_t n_taps, int32_t Npad, float* grad, void* stream);
+
+/* ---------------------------------------------------------------- layout conversion */
+int e2e_nc_to_c8(const float* x, void* y, int32_t B, int32_t C, int64_t V, void* stream);     /* fp32 NCDHW -> bf16 C8 (C padded to 8) */
+int e2e_c8_to_nc(const void* x, float* y, int32_t B, int32_t C, int64_t V, void* stream);     /* bf16 C8 -> fp32 NCDHW */
+
+/* ---------------------------------------------------------------- InstanceNorm + LeakyReLU */
+/* per (b, c): mean and rstd of raw over V voxels; partial: scratch fp32 [B*Cb][nchunk][16] */
+int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, float eps, float* partial, int32_t nchunk,
+                 float* mean, float* rstd, void* stream);
+int e2e_in_apply(const void* raw, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 float slope, int32_t B, int32_t Cb, int64_t V, void* out, void* stream);
+/* backward: sums[b][c] = {sum dz, sum dz*xhat}; then draw, dgamma, dbeta, dbias */
+int e2e_in_bwd(const void* dy, const void* raw, const float* mean, const float* rstd, const float* gamma,
+               const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* partial, int32_t nchunk,
+               float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
+
+/* ---------------------------------------------------------------- MaxPool3d (kernel == stride) */
+int e2e_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t BCb, int32_t D, int32_t H, int32_t W,
+                    int32_t kd, int32_t kh, int32_t kw, void* stream);
+int e2e_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t BCb, int32_t D, int32_t H, int32_t W,
+                    int32_t kd, int32_t kh, int32_t kw, void* stream);
+/* y += x  (gradient fan-in of an activation with several consumers) */
+int e2e_add_inplace(void* y, const void* x, int64_t n_elems, void* stream);
+
+/* ---------------------------------------------------------------- DSFF Masking */
+/* multi-tensor apply_mask: w[i] *= m[i]; mom[i] *= m[i] (mom may be null); ptr tables are device arrays */
+int e2e_mask_apply_multi(float* const* w, float* const* mom, const float* const* mask, const int64_t* numel,
+                         int32_t n_tensors, int64_t max_numel, void* stream);
+/* kernel L1: l1[a*C1+b] = nested fp32 sums over (kd,kh,kw) of |w| with the reference's association */
+int e2e_mask_kernel_l1(const float* w, int32_t n_kernels, int32_t kd, int32_t kh, int32_t kw, float* l1, void* stream);
+/* k-th smallest (0-based rank) of l1[0..n): exact radix select; result -> *thr (device) */
+int e2e_mask_kth(const float* l1, int32_t n, int32_t rank, float* thr, uint32_t* scratch, void* stream);
+/* mask[kernel,:] = 0 for l1 <= *thr; counts[0] = kernels alive after; counts[1] = dead kernels after */
+int e2e_mask_kill(const float* l1, const float* thr, float* mask, int32_t n_kernels, int32_t ksize,
+                  int32_t* counts, void* stream);
+/* row-major ordered list of dead kernels (mask row sums < 1): dead[0..*n_dead) */
+int e2e_mask_dead_list(const float* mask, int32_t n_kernels, int32_t ksize, int32_t* dead, int32_t* n_dead,
+                       int32_t* scratch, void* stream);
+/* mask[dead[pick[i]], :] = 1 */
+int e2e_mask_grow(float* mask, const int32_t* dead, const int32_t* pick, int32_t n_pick, int32_t ksize, void* stream);
+/* nnz[0] = #(mask != 0); fired |= mask; nnz[1] = #(fired != 0) */
+int e2e_mask_counts(const float* mask, uint8_t* fired, int64_t numel, int32_t* nnz, void* stream);
+
+/* ---------------------------------------------------------------- sliding-window accumulate */
+/*
+ * logits fp32 [ncls][px][py][pz] of one tile (possibly predicted on a flipped input: flip bit0=x,
+ * bit1=y, bit2=z) -> softmax over classes (skipped when apply_softmax == 0: input already holds
+ * the network's inference non-linearity), un-flip, * scale (1/num_mirrors) * gauss[px][py][pz]
+ * (gauss may be null = 1), += into agg[ncls][X][Y][Z] at (x0,y0,z0); if add_weight, wsum[X][Y][Z] += gauss.
+ */
+int e2e_window_accumulate(const float* logits, const float* gauss, float* agg, float* wsum, int32_t ncls,
+                          int32_t px, int32_t py, int32_t pz, int32_t X, int32_t Y, int32_t Z,
+                          int32_t x0, int32_t y0, int32_t z0, int32_t flip, float scale, int32_t add_weight,
+                          int32_t apply_softmax, void* stream);
+/* agg /= wsum (in place, cropped region), seg = argmax over classes (first max wins) */
+int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
+                        int64_t* seg, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,181 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares, and the plan builder (shift folding, virtual concat, stride-parity dgrad variants,
+transposed convs, seg heads) reproduces the oracle when its tables are executed by a numpy
+interpreter of the documented kernel semantics (tests/plan_interp.py).  No GPU needed."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import plan_interp as pi
+from oracle import network as onet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_declared_symbols():
+    from e2enet_medical_b200 import _lib, build
+    build.build_library()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "e2enet_b200.h")).read()
+    declared = set(re.findall(r"\b(e2e_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no entry points found in the header"
+    assert declared == set(_lib.SIGNATURES.keys())
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.e2e_version() >= 100
+    assert lib.e2e_launch_count() == 0          # nothing may launch on import / load
+
+
+def test_product_has_no_cpu_fallback():
+    from e2enet_medical_b200.network_architecture.unetpp_d import ConvDropoutNormNonlin
+    from torch import nn
+    blk = ConvDropoutNormNonlin(8, 8, nn.Conv3d, {'kernel_size': (1, 3, 3), 'stride': 1, 'padding': (0, 1, 1),
+                                                  'dilation': 1, 'bias': True}, nn.InstanceNorm3d,
+                                {'eps': 1e-5, 'affine': True}, nn.Dropout3d, {'p': 0, 'inplace': True})
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 8, 2, 4, 4))
+    # and the product never imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "e2enet_medical_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("src,cout,stride,spatial", [
+    ([12], 8, (1, 1, 1), (5, 4, 5)),
+    ([8, 8], 8, (1, 1, 1), (6, 3, 4)),         # virtual concat, groups of 4 straddle the 8-blocks
+    ([1], 8, (1, 1, 1), (6, 4, 4)),
+    ([4], 8, (1, 1, 1), (6, 3, 3)),
+    ([8], 8, (1, 2, 2), (5, 6, 4)),
+    ([16], 8, (2, 2, 2), (6, 4, 6)),
+    ([8], 8, (2, 2, 2), (5, 5, 3)),            # odd sizes under stride
+])
+def test_shiftconv_plans_reproduce_oracle(src, cout, stride, spatial):
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    rs = np.random.RandomState(1)
+    cin = sum(src)
+    B = 1
+    xs = [rs.standard_normal((B, c) + spatial) for c in src]
+    w = rs.standard_normal((cout, cin, 1, 3, 3))
+    plan = build_shiftconv_plan(src, cout, stride)
+    D, H, W = spatial
+    Do, Ho, Wo = plan.out_grid(D, H, W)
+    # forward
+    tx = [torch.from_numpy(a).requires_grad_(True) for a in xs]
+    tw = torch.from_numpy(w).requires_grad_(True)
+    ref = F.conv3d(onet.shift_depth(torch.cat(tx, 1)), tw, None, stride=stride, padding=(0, 1, 1))
+    assert tuple(ref.shape[2:]) == (Do, Ho, Wo)
+    raw = np.zeros((B, cout // 8, Do, Ho, Wo, 8))
+    pi.gemm(plan.fwd, pi.pack(plan.fwd, w), [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo))
+    np.testing.assert_allclose(pi.from_c8(raw, cout), ref.detach().numpy(), atol=1e-9)
+    # backward
+    gy = rs.standard_normal(tuple(ref.shape))
+    (ref * torch.from_numpy(gy)).sum().backward()
+    g8 = pi.to_c8(gy)
+    gw = pi.wgrad(plan.fwd, [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, g8, w.shape)
+    np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
+    outs = [np.full(pi.to_c8(a).shape, np.nan) for a in xs]
+    sd, sh, sw = stride
+    for var in plan.dgrad:
+        pd, ph, pw = (int(v) for v in var.cols[0][3:6])
+        it = ((D - pd + sd - 1) // sd, (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw)
+        if min(it) <= 0:
+            continue
+        pi.gemm(var, pi.pack(var, w), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W))
+    for o, t, c in zip(outs, tx, src):
+        got = pi.from_c8(o, c)
+        assert not np.isnan(got).any(), "dgrad variants must write every element of every source gradient"
+        np.testing.assert_allclose(got, t.grad.numpy(), atol=1e-9)
+
+
+def test_shiftconv_plan_applies_mask_on_pack():
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    rs = np.random.RandomState(2)
+    w = rs.standard_normal((8, 16, 1, 3, 3))
+    m = (rs.rand(8, 16, 1, 1, 1) < 0.3).astype(np.float64) * np.ones_like(w)
+    plan = build_shiftconv_plan([16], 8)
+    np.testing.assert_array_equal(pi.pack(plan.fwd, w, m), pi.pack(plan.fwd, w * m))
+
+
+@pytest.mark.parametrize("cin,cout,k,spatial", [(16, 8, (1, 2, 2), (3, 3, 4)), (8, 16, (2, 2, 2), (2, 3, 2)),
+                                               (8, 8, (1, 1, 1), (2, 2, 3))])
+def test_tconv_plans_reproduce_torch(cin, cout, k, spatial):
+    from e2enet_medical_b200.plans import build_tconv_plan
+    rs = np.random.RandomState(4)
+    B = 1
+    x = rs.standard_normal((B, cin) + spatial)
+    w = rs.standard_normal((cin, cout) + k)
+    tx = torch.from_numpy(x).requires_grad_(True)
+    tw = torch.from_numpy(w).requires_grad_(True)
+    ref = F.conv_transpose3d(tx, tw, stride=k)
+    plan = build_tconv_plan(cin, cout, k)
+    fine = tuple(s * kk for s, kk in zip(spatial, k))
+    y = np.full((B, cout // 8) + fine + (8,), np.nan)
+    pi.gemm(plan.fwd, pi.pack(plan.fwd, w), [pi.to_c8(x)], spatial, spatial, B, [y], fine)
+    np.testing.assert_allclose(pi.from_c8(y, cout), ref.detach().numpy(), atol=1e-9)
+    gy = rs.standard_normal(tuple(ref.shape))
+    (ref * torch.from_numpy(gy)).sum().backward()
+    dx = np.full(pi.to_c8(x).shape, np.nan)
+    pi.gemm(plan.dgrad, pi.pack(plan.dgrad, w), [pi.to_c8(gy)], fine, spatial, B, [dx], spatial)
+    np.testing.assert_allclose(pi.from_c8(dx, cin), tx.grad.numpy(), atol=1e-9)
+    gw = pi.wgrad(plan.dgrad, [pi.to_c8(gy)], fine, spatial, B, pi.to_c8(x), w.shape)
+    np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
+
+
+def test_seghead_plans_reproduce_torch():
+    from e2enet_medical_b200.plans import build_seghead_plan
+    rs = np.random.RandomState(6)
+    cin, ncls, spatial, B = 16, 14, (2, 3, 3), 1
+    x = rs.standard_normal((B, cin) + spatial)
+    w = rs.standard_normal((ncls, cin, 1, 1, 1))
+    tx = torch.from_numpy(x).requires_grad_(True)
+    tw = torch.from_numpy(w).requires_grad_(True)
+    ref = F.conv3d(tx, tw)
+    plan = build_seghead_plan(cin, ncls)
+    y = pi.gemm_planar(plan.fwd, pi.pack(plan.fwd, w), [pi.to_c8(x)], spatial, spatial, B, ncls)
+    np.testing.assert_allclose(y, ref.detach().numpy(), atol=1e-9)
+    gy = rs.standard_normal(tuple(ref.shape))
+    (ref * torch.from_numpy(gy)).sum().backward()
+    g8 = pi.to_c8(gy)
+    dx = np.full(pi.to_c8(x).shape, np.nan)
+    pi.gemm(plan.dgrad, pi.pack(plan.dgrad, w), [g8], spatial, spatial, B, [dx], spatial)
+    np.testing.assert_allclose(pi.from_c8(dx, cin), tx.grad.numpy(), atol=1e-9)
+    gw = pi.wgrad(plan.fwd, [pi.to_c8(x)], spatial, spatial, B, g8, w.shape)
+    np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
+
+
+def test_real_layer_plans_are_consistent():
+    """every weight of every real layer shape is packed exactly once in fwd, and the dgrad
+    variants cover every input channel exactly once per stride parity"""
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    for src, cout, stride in (([48, 48], 48, (1, 1, 1)), ([96, 96, 48], 96, (1, 1, 1)), ([192, 192, 96], 192, (1, 1, 1)),
+                              ([320, 320, 192], 320, (1, 1, 1)), ([320, 320, 320], 320, (1, 1, 1)),
+                              ([48], 96, (1, 2, 2)), ([192], 320, (2, 2, 2)), ([1], 48, (1, 1, 1))):
+        plan = build_shiftconv_plan(src, cout, stride)
+        cin = sum(src)
+        f = plan.fwd
+        co = f.centoff[f.centoff >= 0]
+        assert sorted(co.tolist()) == [c * 9 for c in range(cin)], (src, cout)
+        assert f.n_cent % 2 == 0 and f.Npad % 16 == 0
+        nvar = stride[0] * stride[1] * stride[2]
+        seen = {}
+        for var in plan.dgrad:
+            par = tuple(int(v) for v in var.cols[0][3:6])
+            live = var.rowoff[var.rowoff >= 0] // 9
+            # columns of a variant address distinct channels
+            cols = []
+            for q, (dst, blk, chmask, *_r) in enumerate(var.cols):
+                if dst < 0:
+                    continue
+                base = int(np.cumsum([0] + src)[dst]) + blk * 8
+                cols += [base + j for j in range(8) if chmask & (1 << j)]
+            assert len(cols) == len(set(cols))
+            seen.setdefault(par, []).extend(cols)
+        assert len(seen) == nvar
+        for par, cols in seen.items():
+            assert sorted(cols) == list(range(cin)), (src, stride, par)
