@@ -68,9 +68,9 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_baseline_patches_per_s(budget_s=20.0, crop=(32, 80, 80)):
+def cpu_baseline_patches_per_s(budget_s=20.0, crop=(32, 96, 96)):
     """the oracle's fp32 torch-CPU restatement of the same training iteration (fwd + DS loss + bwd +
-    clip + SGD + apply_mask), on a bounded sample: one 1x1x32x80x80 crop = 1/8 of a patch."""
+    clip + SGD + apply_mask), on a bounded sample: one 1x1x32x96x96 crop = 0.18 patch."""
     import numpy as np
     import torch
     from collections import OrderedDict
@@ -138,10 +138,10 @@ def run_reference(args):
         "steps": n, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "E2ENet BTCV-shaped training: batch 2, 1x64x160x160, 14 classes, density 0.2 "
-                               "(CPU sample: 1x1x32x80x80 crop per step, value scaled by voxel count)"},
+                               "(CPU sample: 1x1x32x96x96 crop per step, value scaled by voxel count)"},
         "cpu_baseline": {"value": val, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": "oracle (torch-CPU fp32 restatement of the reference path) fwd+DS loss+bwd+clip+SGD+"
-                                   "apply_mask on one 1x1x32x80x80 crop = 1/8 patch, %d timed steps" % n},
+                                   "apply_mask on one 1x1x32x96x96 crop = 0.18 patch, %d timed steps" % n},
         "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -250,8 +250,8 @@ def run_ours(args):
     if not args.no_cpu_baseline and world == 1:
         v, dt, n = cpu_baseline_patches_per_s()
         line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x80x80 crop "
-                                          "(1/8 patch), %d steps of %.1f s" % (n, dt)}
+                                "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x96x96 crop "
+                                          "(0.18 patch), %d steps of %.1f s" % (n, dt)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
