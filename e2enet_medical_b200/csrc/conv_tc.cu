@@ -1,9 +1,380 @@
-// tcgen05 / TMA implicit-GEMM kernel for the stride-1 depth-shifted (1,3,3) convolutions.
-// (placeholder until the kernel lands: the dispatcher reports it as unsupported)
+// tcgen05 / TMA implicit-GEMM kernel for the stride-1 depth-shifted (1,3,3) convolutions of
+// E2ENet (forward of every stride-1 ConvDropoutNormNonlin, and the data gradients of those
+// layers, which are stride-1 correlations too).  Reference math: unetpp_d.py:45-59 (shift),
+// :102-108 (conv), with the torch.cat of :453-478 folded in.
+//
+// Data flow per CTA (persistent, one CTA per SM, static round-robin over tiles):
+//   tile  = 16 (H) x 8m (W) output voxels of one depth slice d of one sample b
+//   K loop over channel-entry PAIRS (16 channels): per pair
+//     A: 2 TMA tensor loads (one per 8-channel block) of the HALOED input window
+//        [18][8m+2][8ch] at depth d - shift(block): TMA's out-of-bounds zero fill provides
+//        both the conv padding and the shift's zero fill; all 9 filter taps and all m
+//        sub-tiles read the same window through different UMMA descriptor start addresses
+//        (no-swizzle K-major "interleaved" layout: a core matrix is 8 W-consecutive voxels
+//        x 8 channels = 128 contiguous bytes, SBO = one window row).
+//     B: 1 bulk copy of the pre-packed bf16 weights [9 taps][2][Npad][8] of this pair.
+//     9*m tcgen05.mma (M=128, N=Npad, K=16) accumulate into m TMEM accumulators.
+//   epilogue warps: tcgen05.ld -> bf16 -> 16-byte coalesced stores into the C8 destination(s);
+//   TMEM is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 #include "common.cuh"
 
-int e2e_conv_tc_fwd(const e2e_gemm_t* p, cudaStream_t st) {
-  (void)p; (void)st;
-  e2e_set_error("conv_tc_fwd: tcgen05 path not built");
-  return E2E_ERR_UNSUPPORTED;
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TH = 16;                 // tile rows (H)
+constexpr int MAX_CENT = 320;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct TcParams {
+  int B, D, H, W;
+  int n_cent, Npad, m, stages, acc_stages;
+  int ivd;
+  int tiles_h, tiles_w, n_tiles;
+  int a_slab_bytes;      // padded to 128
+  int a_stage_bytes, b_stage_bytes, stage_bytes;
+  int src_cb[E2E_MAX_SRC];
+  const e2e_centry_t* cents;
+  const e2e_tap_t* taps;
+  const bf16* wpacked;
+  const e2e_colblk_t* cols;
+  void* dst[E2E_MAX_SRC];
+  int dst_cb[E2E_MAX_SRC];
+};
+
+struct alignas(64) TcMaps {
+  CUtensorMap m[E2E_MAX_SRC];
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (launch error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[32];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ e2e_centry_t s_cents[MAX_CENT];
+  __shared__ int s_tapoff[9];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = p.m, Npad = p.Npad, S = p.stages, AS = p.acc_stages;
+  const int rowpitch = (8 * m + 2) * 16;             // bytes per window row
+  const int npairs = p.n_cent >> 1;
+  // barrier indices
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto tfull_bar = [&](int a) { return smem_u32(&bars[16 + a]); };
+  auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
+
+  for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS) s_cents[i] = p.cents[i];
+  if (threadIdx.x < 9) {
+    const e2e_tap_t t = p.taps[threadIdx.x];
+    s_tapoff[threadIdx.x] = (1 + t.dh) * rowpitch + (1 + t.dw) * 16;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;     // TMA destinations need 128 B; keep 1 KB
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      const uint32_t tx = 2u * 18u * (uint32_t)rowpitch + (uint32_t)p.b_stage_bytes;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int d = t % p.D;
+        const int b = t / p.D;
+        const int h0 = ht * TH, w0 = wt * 8 * m;
+        for (int pr = 0; pr < npairs; ++pr) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const e2e_centry_t ce = s_cents[2 * pr + hf];
+            tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
+                        d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+          }
+          bulk_copy_g2s(sa + p.a_stage_bytes, p.wpacked + (size_t)pr * (p.b_stage_bytes / 2), p.b_stage_bytes,
+                        full_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=Npad, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
+      int stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * m * Npad);
+        for (int pr = 0; pr < npairs; ++pr) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + p.a_stage_bytes;
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const uint64_t bdesc = make_desc(sb + t * (2 * Npad * 16), Npad * 16, 128);
+            const uint32_t a_t = sa + s_tapoff[t];
+            for (int j = 0; j < m; ++j) {
+              const uint64_t adesc = make_desc(a_t + j * 128, p.a_slab_bytes, rowpitch);
+              tc_mma_f16(acc0 + j * Npad, adesc, bdesc, idesc, (pr | t) ? 1u : 0u);
+            }
+          }
+          tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(as));                 // accumulators of this tile are complete
+        if (++as == AS) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================= epilogue (warps 2..5 -> TMEM lane quadrants)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                  // accumulator row = voxel (r / 8, r % 8) of a sub-tile
+    int as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int b = t / p.D;
+      const int h = ht * TH + (r >> 3);
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * m * Npad);
+      for (int j = 0; j < m; ++j) {
+        const int w = wt * 8 * m + j * 8 + (r & 7);
+        const bool inb = (h < p.H) && (w < p.W);
+        for (int cq = 0; cq < Npad / 8; cq += 2) {
+          uint32_t v[16];
+          tc_ld8(acc0 + j * Npad + cq * 8, v);
+          tc_ld8(acc0 + j * Npad + cq * 8 + 8, v + 8);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const e2e_colblk_t col = p.cols[cq + u];
+            if (!inb || col.dst < 0 || col.chmask == 0) continue;
+            bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) +
+                       (((((size_t)b * p.dst_cb[col.dst] + col.blk) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
+            const uint32_t* vv = v + u * 8;
+            uint4 o = make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
+                                 pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
+                                 pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
+                                 pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
+            if (col.chmask == 0xff) {
+              *reinterpret_cast<uint4*>(dp) = o;
+            } else {
+              const bf16* ov = reinterpret_cast<const bf16*>(&o);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (col.chmask & (1 << e)) dp[e] = ov[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == AS) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// returns E2E_ERR_UNSUPPORTED (without setting a launch) when the call does not have the halo form
+int e2e_conv_tc_supported(const e2e_gemm_t* p) {
+  if (p->out_mode != 0 || p->n_taps != 9) return 0;
+  if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->osd != 1 || p->osh != 1 || p->osw != 1) return 0;
+  if (p->ivh != 0 || p->ivw != 0) return 0;
+  if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
+  if (p->Dd != p->Di || p->Hd != p->Hi || p->Wd != p->Wi) return 0;
+  if (p->Npad > 256 || p->Npad % 16 != 0 || p->n_cent > MAX_CENT) return 0;
+  return 1;
+}
+
+int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
+  if (!e2e_conv_tc_supported(g)) {
+    e2e_set_error("conv_tc_fwd: call is not a stride-1 3x3 halo-form GEMM with Npad <= 256");
+    return E2E_ERR_UNSUPPORTED;
+  }
+  auto encode = get_encode_fn();
+  if (!encode) {
+    e2e_set_error("conv_tc_fwd: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return E2E_ERR_CUDA;
+  }
+  // host copies of the plan tables are not available here: taps / cents must have the halo form
+  // (|dh|,|dw| <= 1 for taps; dh = dw = 0 for channel entries).  The Python plan builder guarantees
+  // it for the calls it flags with impl = 1.
+  TcParams p{};
+  p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
+  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  int m = 256 / g->Npad;
+  if (m > 4) m = 4;
+  if (m < 1) m = 1;
+  while (m > 1 && 8 * (m - 1) >= g->Wi) --m;          // do not tile wider than the row
+  p.m = m;
+  p.acc_stages = (2 * m * g->Npad <= 512) ? 2 : 1;
+  const int rowpitch = (8 * m + 2) * 16;
+  p.a_slab_bytes = (18 * rowpitch + 127) / 128 * 128;
+  p.a_stage_bytes = 2 * p.a_slab_bytes;
+  p.b_stage_bytes = 9 * 2 * g->Npad * 16;
+  p.stage_bytes = (p.a_stage_bytes + p.b_stage_bytes + 127) / 128 * 128;
+  int stages = SMEM_BUDGET / p.stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) {
+    e2e_set_error("conv_tc_fwd: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  p.tiles_h = (p.H + TH - 1) / TH;
+  p.tiles_w = (p.W + 8 * m - 1) / (8 * m);
+  p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  p.cents = g->cents; p.taps = g->taps; p.cols = g->cols;
+  p.wpacked = reinterpret_cast<const bf16*>(g->wpacked);
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+    const int si = i < g->n_src ? i : 0;
+    p.src_cb[i] = g->src_cb[si];
+    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)(8 * m + 2), 18, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("conv_tc_fwd: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
+      return E2E_ERR_CUDA;
+    }
+  }
+  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+    p.dst[i] = i < g->n_dst ? g->dst[i] : nullptr;
+    p.dst_cb[i] = i < g->n_dst ? g->dst_cb[i] : 0;
+  }
+  const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    attr_done = true;
+  }
+  int grid = e2e_num_sms();
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  conv_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
+  E2E_LAUNCHED("conv_tc_fwd");
+  return E2E_OK;
 }

@@ -450,6 +450,7 @@ int launch_wgrad(const e2e_wgrad_t* p, cudaStream_t st) {
 }  // namespace
 
 int e2e_conv_tc_fwd(const e2e_gemm_t* p, cudaStream_t st);   // conv_tc.cu
+int e2e_conv_tc_supported(const e2e_gemm_t* p);
 
 extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) {
   E2E_ARG(p != nullptr, "gather_gemm: null params");
@@ -461,7 +462,7 @@ extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
-  if (p->impl == 1) return e2e_conv_tc_fwd(p, st);
+  if (p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, st);
   const int N = p->Npad;
   if (N % 128 == 0) return launch_gemm<8>(p, st);
   if (N % 96 == 0) return launch_gemm<6>(p, st);

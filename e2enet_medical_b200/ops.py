@@ -267,7 +267,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
                 if min(it) <= 0:
                     continue
                 wpd = pack_weights(var, weight, ctx.mask)
-                run_gemm(var, wpd, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W), [s.shape[1] for s in srcs], 0)
+                run_gemm(var, wpd, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W), [s.shape[1] for s in srcs], impl)
             dsrcs = [o if n else None for o, n in zip(outs, need)]
         return (None, None, gw, dbias.to(weight.dtype) if ctx.needs_input_grad[3] else None,
                 dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, *dsrcs)
