@@ -110,6 +110,18 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a converged warp; the compiler knows the guarded region is single-threaded and keeps
+// descriptor arithmetic / UTCHMMA operands in uniform registers without a divergence waterfall
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -188,11 +200,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       }
     }
   } else if (warp == 1) {
-    // ================================================= MMA issuer
-    if (lane == 0) {
+    // ================================================= MMA issuer (warp-uniform loop, one elected lane issues)
+    {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=Npad, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
       int stage = 0, phase = 0, as = 0, aphase = 0;
+      const uint64_t adesc_hi = make_desc(0, p.a_slab_bytes, rowpitch) & 0xffffffff00000000ull;
+      const uint32_t adesc_lo_hi = (uint32_t)(make_desc(0, p.a_slab_bytes, rowpitch) & 0xffff0000ull);
+      const uint64_t bdesc_hi = make_desc(0, Npad * 16, 128) & 0xffffffff00000000ull;
+      const uint32_t bdesc_lo_hi = (uint32_t)(make_desc(0, Npad * 16, 128) & 0xffff0000ull);
+      const int b_tap_units = (2 * Npad * 16) >> 4;
+      int tapoff_units[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tapoff_units[t] = s_tapoff[t] >> 4;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
@@ -200,21 +220,26 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         for (int pr = 0; pr < npairs; ++pr) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sb = sa + p.a_stage_bytes;
-#pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
-            const uint64_t bdesc = make_desc(sb + t * (2 * Npad * 16), Npad * 16, 128);
-            const uint32_t a_t = sa + s_tapoff[t];
-            for (int j = 0; j < m; ++j) {
-              const uint64_t adesc = make_desc(a_t + j * 128, p.a_slab_bytes, rowpitch);
-              tc_mma_f16(acc0 + j * Npad, adesc, bdesc, idesc, (pr | t) ? 1u : 0u);
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + stage * p.stage_bytes;
+            const uint32_t sb = sa + p.a_stage_bytes;
+            // descriptors differ only in the 14-bit start-address field (units of 16 B): add to the low word
+            const uint64_t a0 = adesc_hi | (uint64_t)(adesc_lo_hi | (sa >> 4));
+            const uint64_t b0 = bdesc_hi | (uint64_t)(bdesc_lo_hi | (sb >> 4));
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              const uint64_t bdesc = b0 + (uint64_t)(t * b_tap_units);
+              const uint64_t a_t = a0 + (uint64_t)tapoff_units[t];
+              for (int j = 0; j < m; ++j)
+                tc_mma_f16(acc0 + j * Npad, a_t + (uint64_t)(j * 8), bdesc, idesc, (pr | t) ? 1u : 0u);
             }
+            tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
           }
-          tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull_bar(as));                 // accumulators of this tile are complete
+        if (elect_one_sync()) tc_commit(tfull_bar(as));   // accumulators of this tile are complete
+        __syncwarp();
         if (++as == AS) { as = 0; aphase ^= 1; }
       }
     }
@@ -376,5 +401,267 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   if (grid > p.n_tiles) grid = p.n_tiles;
   conv_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
+  return E2E_OK;
+}
+
+// =====================================================================================
+// tcgen05 weight-gradient kernel (same halo form): K = voxels.
+//
+//   dwp[(cent e, tap t)][n][j] += sum_v  x_e[v + tap_t][j] * g[v][n]
+//
+// GEMM view per tap: D[M = 16 channel entries x 8 ch = 128][N = Npad] += A^T B with K = the 128
+// voxels of a 16(H) x 8(W) tile, 16 voxels (2 rows) per tcgen05.mma.  Both operands are read
+// straight from C8 slabs as MN-major no-swizzle UMMA operands: a core matrix is 8 W-consecutive
+// voxels x 8 channels (128 contiguous bytes); LBO = one tile/window row (next 8 voxels),
+// SBO = one slab (next 8 channels).  The 9 taps read the same haloed x window through different
+// descriptor start addresses and accumulate into 9 (or fewer, when 9*Npad > 512) TMEM
+// accumulators that live across ALL voxel tiles of the CTA; one fp32 atomic flush at the end.
+// Jobs: (16-entry group mg) x (tap group tg) x (voxel split); one CTA per job.
+// =====================================================================================
+namespace {
+
+struct WgParams {
+  int B, D, H, W;
+  int n_cent, Npad, ivd;
+  int tiles_h, tiles_w, n_tiles;
+  int n_tg, taps_per_group, splits, tiles_per_split;
+  int x_slab_bytes, g_slab_bytes, x_bytes, stage_bytes, stages;
+  int src_cb[E2E_MAX_SRC];
+  int grad_cb;
+  const e2e_centry_t* cents;
+  const e2e_tap_t* taps;
+  float* dwp;
+};
+
+struct alignas(64) WgMaps {
+  CUtensorMap x[E2E_MAX_SRC];
+  CUtensorMap g;
+};
+
+constexpr int WG_ROWPITCH = 10 * 16;       // haloed window row: (8 + 2) voxels x 16 B
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ e2e_centry_t s_cents[16];
+  __shared__ int s_tapoff[9];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Npad = p.Npad, S = p.stages;
+  int job = blockIdx.x;
+  const int split = job % p.splits; job /= p.splits;
+  const int tg = job % p.n_tg;
+  const int mg = job / p.n_tg;
+  const int e0 = mg * 16;
+  const int ne = min(16, p.n_cent - e0);                    // channel entries of this group
+  const int t0 = tg * p.taps_per_group;
+  const int nt = min(p.taps_per_group, 9 - t0);             // taps of this group
+  const int tile_lo = split * p.tiles_per_split;
+  const int tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
+  const int my_tiles = tile_hi - tile_lo;
+
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
+  const uint32_t done_bar = smem_u32(&bars[16]);
+
+  if (threadIdx.x < ne) s_cents[threadIdx.x] = p.cents[e0 + threadIdx.x];
+  if (threadIdx.x < 9) {
+    const e2e_tap_t t = p.taps[threadIdx.x];
+    s_tapoff[threadIdx.x] = (1 + t.dh) * WG_ROWPITCH + (1 + t.dw) * 16;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+  if (my_tiles > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0, phase = 0;
+        const uint32_t tx = (uint32_t)ne * 18u * WG_ROWPITCH + (uint32_t)Npad * 256u;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+          int t = tile;
+          const int wt = t % p.tiles_w; t /= p.tiles_w;
+          const int ht = t % p.tiles_h; t /= p.tiles_h;
+          const int d = t % p.D;
+          const int b = t / p.D;
+          const int h0 = ht * TH, w0 = wt * 8;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sx = smem_base + stage * p.stage_bytes;
+          for (int e = 0; e < ne; ++e) {
+            const e2e_centry_t ce = s_cents[e];
+            tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
+                        d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+          }
+          tma_load_5d(sx + p.x_bytes, &maps.g, full_bar(stage), 0, w0, h0, d, b * p.grad_cb);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      {
+        // D=f32, A=B=bf16, A and B MN-major, N=Npad, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
+        int stage = 0, phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sx = smem_base + stage * p.stage_bytes;
+            const uint32_t sg = sx + p.x_bytes;
+            const uint64_t a0 = make_desc(sx, WG_ROWPITCH, p.x_slab_bytes);
+            const uint64_t b0 = make_desc(sg, 128, p.g_slab_bytes);
+            for (int tl = 0; tl < nt; ++tl) {
+              const uint64_t a_t = a0 + (uint64_t)(s_tapoff[t0 + tl] >> 4);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                // 16 voxels = tile rows 2k, 2k+1; start-address field is in units of 16 B
+                tc_mma_f16(tmem_base + tl * Npad, a_t + (uint64_t)(2 * k * (WG_ROWPITCH >> 4)), b0 + (uint64_t)(k * 16),
+                           idesc, (it | k) ? 1u : 0u);
+              }
+            }
+            tc_commit(empty_bar(stage));
+          }
+          __syncwarp();
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) tc_commit(done_bar);
+        __syncwarp();
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;             // accumulator row = (entry r/8, channel r%8)
+      const int el = r >> 3, j = r & 7;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int e = e0 + el;
+      const bool valid = el < ne;
+      for (int tl = 0; tl < nt; ++tl) {
+        const int t = t0 + tl;
+        // dwp index of (entry e, tap t): slab = ((e/2)*9 + t)*2 + e%2
+        float* base = p.dwp + ((size_t)(((e >> 1) * 9 + t) * 2 + (e & 1)) * Npad) * 8 + j;
+        for (int c = 0; c < Npad; c += 16) {
+          uint32_t v[16];
+          tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + tl * Npad + c, v);
+          tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + tl * Npad + c + 8, v + 8);
+          tc_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+}  // namespace
+
+int e2e_wgrad_tc_supported(const e2e_wgrad_t* p) {
+  if (p->n_taps != 9) return 0;
+  if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->ivh != 0 || p->ivw != 0) return 0;
+  if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
+  if (p->Npad > 256 || p->Npad % 16 != 0) return 0;
+  return 1;
+}
+
+int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
+  if (!e2e_wgrad_tc_supported(g)) {
+    e2e_set_error("wgrad_tc: call is not a stride-1 3x3 halo-form weight gradient with Npad <= 256");
+    return E2E_ERR_UNSUPPORTED;
+  }
+  auto encode = get_encode_fn();
+  if (!encode) {
+    e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+    return E2E_ERR_CUDA;
+  }
+  WgParams p{};
+  p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
+  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  p.tiles_h = (p.H + TH - 1) / TH;
+  p.tiles_w = (p.W + 7) / 8;
+  p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  p.taps_per_group = 512 / g->Npad;
+  if (p.taps_per_group > 9) p.taps_per_group = 9;
+  p.n_tg = (9 + p.taps_per_group - 1) / p.taps_per_group;
+  p.taps_per_group = (9 + p.n_tg - 1) / p.n_tg;            // balance the groups
+  const int n_mg = (g->n_cent + 15) / 16;
+  p.x_slab_bytes = (18 * WG_ROWPITCH + 127) / 128 * 128;
+  p.g_slab_bytes = 128 * 16;
+  p.x_bytes = 16 * p.x_slab_bytes;
+  p.stage_bytes = (p.x_bytes + (g->Npad / 8) * p.g_slab_bytes + 127) / 128 * 128;
+  int stages = SMEM_BUDGET / p.stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) {
+    e2e_set_error("wgrad_tc: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  p.stages = stages;
+  const int jobs = n_mg * p.n_tg;
+  int splits = (e2e_num_sms() + jobs - 1) / jobs;
+  if (splits > p.n_tiles) splits = p.n_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+  splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.splits = splits;
+  p.cents = g->cents; p.taps = g->taps; p.dwp = g->dwp; p.grad_cb = g->grad_cb;
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+    const int si = i < g->n_src ? i : 0;
+    p.src_cb[i] = g->src_cb[si];
+    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[5] = {8, 10, 18, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
+      return E2E_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[5] = {8, 8, 16, 1, (cuuint32_t)(g->Npad / 8)};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&maps.g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->grad), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d (grad)", (int)r);
+      return E2E_ERR_CUDA;
+    }
+  }
+  const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4 * 1024));
+    attr_done = true;
+  }
+  wgrad_tc_kernel<<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+  E2E_LAUNCHED("wgrad_tc");
   return E2E_OK;
 }

@@ -451,6 +451,8 @@ int launch_wgrad(const e2e_wgrad_t* p, cudaStream_t st) {
 
 int e2e_conv_tc_fwd(const e2e_gemm_t* p, cudaStream_t st);   // conv_tc.cu
 int e2e_conv_tc_supported(const e2e_gemm_t* p);
+int e2e_wgrad_tc(const e2e_wgrad_t* p, cudaStream_t st);
+int e2e_wgrad_tc_supported(const e2e_wgrad_t* p);
 
 extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) {
   E2E_ARG(p != nullptr, "gather_gemm: null params");
@@ -480,6 +482,7 @@ extern "C" int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
+  if (p->impl == 1 && e2e_wgrad_tc_supported(p)) return e2e_wgrad_tc(p, st);
   const int N = p->Npad;
   if (N <= 16) return launch_wgrad<1>(p, st);
   if (N <= 32) return launch_wgrad<2>(p, st);

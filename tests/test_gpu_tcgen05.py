@@ -50,10 +50,18 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     ref = F.conv3d(onet.shift_depth(xc), w, None, padding=(0, 1, 1))
     assert rel(outs[1], ref) < ULP
     assert rel(outs[1], outs[0]) < ULP
-    # data gradient variants (one per shift group) through the same kernel
+    # weight gradient: tcgen05 kernel (K = voxels, MN-major operands) vs mma.sync kernel vs torch
     g = bf(torch.from_numpy(rs.standard_normal((B, cout, D, H, W)).astype(np.float32))).to(dev)
-    (ref * g).sum().backward()
     g8 = ops.nc_to_c8(g)
+    gw0 = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 0)
+    gw1 = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 1)
+    torch.cuda.synchronize()
+    wc = w.clone().requires_grad_(True)
+    (F.conv3d(onet.shift_depth(torch.cat(xs, 1)), wc, None, padding=(0, 1, 1)) * g).sum().backward()
+    assert rel(gw1, wc.grad) < 2e-4, rel(gw1, wc.grad)
+    assert rel(gw1, gw0) < 2e-4
+    # data gradient variants (one per shift group) through the same kernel
+    (ref * g).sum().backward()
     douts = [torch.full_like(s, float("nan")) for s in xs8]
     for var in plan.dgrad:
         ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (D, H, W), (D, H, W), B, douts, (D, H, W),

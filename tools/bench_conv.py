@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--B", type=int, default=2)
+    ap.add_argument("--wgrad", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B = a.B
@@ -56,6 +57,17 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
             line += f" | impl{impl}: {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF/s {byts / ms / 1e6:6.0f} GB/s"
+            if a.wgrad:
+                for _ in range(2):
+                    ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, raw, tuple(w.shape), impl)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(a.iters):
+                    ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, raw, tuple(w.shape), impl)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / a.iters
+                line += f" wgrad {ms:7.3f} ms {flops / ms / 1e9:7.1f} TF/s"
         print(line, flush=True)
 
 
