@@ -263,7 +263,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kernel-impl", type=int, default=0, help="0: mma.sync gather kernels, 1: tcgen05 where available")
+    ap.add_argument("--kernel-impl", type=int, default=1, help="0: mma.sync gather kernels, 1: tcgen05 where available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

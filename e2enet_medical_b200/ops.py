@@ -17,7 +17,7 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 0}
+CONFIG = {"impl": 1}
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
