@@ -17,6 +17,12 @@
 //   epilogue warps: tcgen05.ld -> bf16 -> 16-byte coalesced stores into the C8 destination(s);
 //   TMEM is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
+//
+// The same kernel has a second, "point" form (template HALO = false) for the 1-tap GEMMs of the
+// path -- ConvTranspose3d(kernel == stride) forward (unetpp_d.py:521-522: every coarse voxel
+// produces kd*kh*kw fine voxels; column block q is stored at fine voxel o*k + cols[q].off) and its
+// data gradient (each K entry is a (tap, channel block) of dy fetched at o*k + tap: a TMA box with
+// elementStrides = k and a per-entry start offset).  No halo, one MMA per (K step, sub-tile).
 #include "common.cuh"
 
 #include <cuda.h>
@@ -30,7 +36,11 @@ constexpr int MAX_CENT = 320;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
-  int B, D, H, W;
+  int B, D, H, W;        // iteration grid (D, H, W); sources have Dsrc slices, destinations (Ddst, Hd, Wd)
+  int Dsrc, Ddst, Hd, Wd;
+  int isd, ish, isw, ivh, ivw;     // point form: source voxel = o * is + iv + entry offset
+  int osd, osh, osw;               // destination voxel = o * os + column-block offset
+  int rows;                        // window rows per slab: 18 (halo) or 16 (point)
   int n_cent, Npad, m, stages, acc_stages;
   int ivd;
   int tiles_h, tiles_w, n_tiles;
@@ -132,8 +142,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+template <bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
+  constexpr int NT = HALO ? 9 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_s;
@@ -142,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = p.m, Npad = p.Npad, S = p.stages, AS = p.acc_stages;
-  const int rowpitch = (8 * m + 2) * 16;             // bytes per window row
+  const int rowpitch = (8 * m + (HALO ? 2 : 0)) * 16;   // bytes per window row
   const int npairs = p.n_cent >> 1;
   // barrier indices
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
@@ -152,8 +164,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
 
   for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS) s_cents[i] = p.cents[i];
   if (threadIdx.x < 9) {
-    const e2e_tap_t t = p.taps[threadIdx.x];
-    s_tapoff[threadIdx.x] = (1 + t.dh) * rowpitch + (1 + t.dw) * 16;
+    int off = 0;
+    if (HALO) {
+      const e2e_tap_t t = p.taps[threadIdx.x];
+      off = (1 + t.dh) * rowpitch + (1 + t.dw) * 16;
+    }
+    s_tapoff[threadIdx.x] = off;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -175,7 +191,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     // ================================================= TMA producer
     if (lane == 0) {
       int stage = 0, phase = 0;
-      const uint32_t tx = 2u * 18u * (uint32_t)rowpitch + (uint32_t)p.b_stage_bytes;
+      const uint32_t tx = 2u * (uint32_t)p.rows * (uint32_t)rowpitch + (uint32_t)p.b_stage_bytes;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         int t = tile;
         const int wt = t % p.tiles_w; t /= p.tiles_w;
@@ -190,8 +206,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const e2e_centry_t ce = s_cents[2 * pr + hf];
-            tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
-                        d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+            if (HALO)
+              tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
+                          d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+            else
+              tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
+                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
           }
           bulk_copy_g2s(sa + p.a_stage_bytes, p.wpacked + (size_t)pr * (p.b_stage_bytes / 2), p.b_stage_bytes,
                         full_bar(stage));
@@ -210,9 +230,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       const uint64_t bdesc_hi = make_desc(0, Npad * 16, 128) & 0xffffffff00000000ull;
       const uint32_t bdesc_lo_hi = (uint32_t)(make_desc(0, Npad * 16, 128) & 0xffff0000ull);
       const int b_tap_units = (2 * Npad * 16) >> 4;
-      int tapoff_units[9];
+      int tapoff_units[NT];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) tapoff_units[t] = s_tapoff[t] >> 4;
+      for (int t = 0; t < NT; ++t) tapoff_units[t] = s_tapoff[t] >> 4;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(as), aphase ^ 1);
         tc_fence_after();
@@ -227,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             const uint64_t a0 = adesc_hi | (uint64_t)(adesc_lo_hi | (sa >> 4));
             const uint64_t b0 = bdesc_hi | (uint64_t)(bdesc_lo_hi | (sb >> 4));
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
+            for (int t = 0; t < NT; ++t) {
               const uint64_t bdesc = b0 + (uint64_t)(t * b_tap_units);
               const uint64_t a_t = a0 + (uint64_t)tapoff_units[t];
               for (int j = 0; j < m; ++j)
@@ -261,6 +281,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       for (int j = 0; j < m; ++j) {
         const int w = wt * 8 * m + j * 8 + (r & 7);
         const bool inb = (h < p.H) && (w < p.W);
+        const int hs = h * p.osh, ws = w * p.osw, ds = d * p.osd;
         for (int cq = 0; cq < Npad / 8; cq += 2) {
           uint32_t v[16];
           tc_ld8(acc0 + j * Npad + cq * 8, v);
@@ -270,8 +291,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
           for (int u = 0; u < 2; ++u) {
             const e2e_colblk_t col = p.cols[cq + u];
             if (!inb || col.dst < 0 || col.chmask == 0) continue;
+            // per-column-block destination offset: depth for the shift-folded dgrad, all three for tconv
+            const int dd = ds + col.od, hh = hs + col.oh, ww = ws + col.ow;
+            if ((unsigned)dd >= (unsigned)p.Ddst || (unsigned)hh >= (unsigned)p.Hd || (unsigned)ww >= (unsigned)p.Wd)
+              continue;
             bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) +
-                       (((((size_t)b * p.dst_cb[col.dst] + col.blk) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
+                       (((((size_t)b * p.dst_cb[col.dst] + col.blk) * p.Ddst + dd) * p.Hd + hh) * (size_t)p.Wd + ww) * 8;
             const uint32_t* vv = v + u * 8;
             uint4 o = make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
                                  pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
@@ -280,10 +305,30 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             if (col.chmask == 0xff) {
               *reinterpret_cast<uint4*>(dp) = o;
             } else {
-              const bf16* ov = reinterpret_cast<const bf16*>(&o);
+              // shift groups are contiguous channel ranges: store the selected channels in the widest
+              // aligned pieces (8 / 4 / 2 bytes)
+              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+              const int cm = col.chmask;
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (col.chmask & (1 << e)) dp[e] = ov[e];
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int m4 = (cm >> (4 * h2)) & 0xf;
+                if (m4 == 0xf) {
+                  *reinterpret_cast<uint2*>(dp + 4 * h2) = make_uint2(ow[2 * h2], ow[2 * h2 + 1]);
+                } else {
+#pragma unroll
+                  for (int q2 = 0; q2 < 2; ++q2) {
+                    const int m2 = (m4 >> (2 * q2)) & 3;
+                    const int e = 4 * h2 + 2 * q2;
+                    if (m2 == 3) {
+                      *reinterpret_cast<uint32_t*>(dp + e) = ow[2 * h2 + q2];
+                    } else if (m2) {
+                      const bf16* ov = reinterpret_cast<const bf16*>(&ow[2 * h2 + q2]);
+                      if (m2 & 1) dp[e] = ov[0];
+                      if (m2 & 2) dp[e + 1] = ov[1];
+                    }
+                  }
+                }
+              }
             }
           }
         }
@@ -320,46 +365,60 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 }  // namespace
 
-// returns E2E_ERR_UNSUPPORTED (without setting a launch) when the call does not have the halo form
+// 1: stride-1 3x3 halo form, 2: 1-tap point form, 0: not served by this kernel
 int e2e_conv_tc_supported(const e2e_gemm_t* p) {
-  if (p->out_mode != 0 || p->n_taps != 9) return 0;
-  if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->osd != 1 || p->osh != 1 || p->osw != 1) return 0;
-  if (p->ivh != 0 || p->ivw != 0) return 0;
-  if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
-  if (p->Dd != p->Di || p->Hd != p->Hi || p->Wd != p->Wi) return 0;
+  if (p->out_mode != 0) return 0;
   if (p->Npad > 256 || p->Npad % 16 != 0 || p->n_cent > MAX_CENT) return 0;
-  return 1;
+  if (p->n_taps == 9) {
+    if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->osd != 1 || p->osh != 1 || p->osw != 1) return 0;
+    if (p->ivh != 0 || p->ivw != 0) return 0;
+    if (p->Ho != p->Hi || p->Wo != p->Wi) return 0;      // depth counts may differ (shift-folded dgrad)
+    if (p->Hd != p->Hi || p->Wd != p->Wi) return 0;
+    return 1;
+  }
+  if (p->n_taps == 1) {
+    if (p->isd < 1 || p->ish < 1 || p->isw < 1 || p->isd > 8 || p->ish > 8 || p->isw > 8) return 0;
+    if (16 * p->ish > 256 || 32 * p->isw > 256) return 0;
+    return 2;
+  }
+  return 0;
 }
 
 int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
-  if (!e2e_conv_tc_supported(g)) {
-    e2e_set_error("conv_tc_fwd: call is not a stride-1 3x3 halo-form GEMM with Npad <= 256");
+  const int form = e2e_conv_tc_supported(g);
+  if (!form) {
+    e2e_set_error("conv_tc_fwd: call is neither a stride-1 3x3 halo-form nor a 1-tap GEMM with Npad <= 256");
     return E2E_ERR_UNSUPPORTED;
   }
+  const bool halo = form == 1;
   auto encode = get_encode_fn();
   if (!encode) {
     e2e_set_error("conv_tc_fwd: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return E2E_ERR_CUDA;
   }
-  // host copies of the plan tables are not available here: taps / cents must have the halo form
-  // (|dh|,|dw| <= 1 for taps; dh = dw = 0 for channel entries).  The Python plan builder guarantees
-  // it for the calls it flags with impl = 1.
+  // host copies of the plan tables are not available here: in the halo form taps must have
+  // |dh|,|dw| <= 1 and channel entries dh = dw = 0; the Python plan builder guarantees it.
   TcParams p{};
-  p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
+  p.B = g->B; p.D = g->Do; p.H = g->Ho; p.W = g->Wo;
+  p.Dsrc = g->Di; p.Ddst = g->Dd; p.Hd = g->Hd; p.Wd = g->Wd;
+  p.isd = g->isd; p.ish = g->ish; p.isw = g->isw; p.ivh = g->ivh; p.ivw = g->ivw;
+  p.osd = g->osd; p.osh = g->osh; p.osw = g->osw;
   p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  const int n_taps = halo ? 9 : 1;
   int m = 256 / g->Npad;
   if (m > 4) m = 4;
   if (m < 1) m = 1;
-  while (m > 1 && 8 * (m - 1) >= g->Wi) --m;          // do not tile wider than the row
+  while (m > 1 && 8 * (m - 1) >= g->Wo) --m;          // do not tile wider than the row
   p.m = m;
   p.acc_stages = (2 * m * g->Npad <= 512) ? 2 : 1;
-  const int rowpitch = (8 * m + 2) * 16;
-  p.a_slab_bytes = (18 * rowpitch + 127) / 128 * 128;
+  p.rows = halo ? 18 : 16;
+  const int rowpitch = (8 * m + (halo ? 2 : 0)) * 16;
+  p.a_slab_bytes = (p.rows * rowpitch + 127) / 128 * 128;
   p.a_stage_bytes = 2 * p.a_slab_bytes;
-  p.b_stage_bytes = 9 * 2 * g->Npad * 16;
+  p.b_stage_bytes = n_taps * 2 * g->Npad * 16;
   p.stage_bytes = (p.a_stage_bytes + p.b_stage_bytes + 127) / 128 * 128;
   int stages = SMEM_BUDGET / p.stage_bytes;
-  if (stages > 6) stages = 6;
+  if (stages > 8) stages = 8;
   if (stages < 2) {
     e2e_set_error("conv_tc_fwd: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
     return E2E_ERR_UNSUPPORTED;
@@ -375,10 +434,16 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
     const int si = i < g->n_src ? i : 0;
     p.src_cb[i] = g->src_cb[si];
-    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint64_t gdim[5] = {8, (cuuint64_t)g->Wi, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16,
+                          (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
     cuuint32_t box[5] = {8, (cuuint32_t)(8 * m + 2), 18, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (!halo) {
+      // traversal strides: ceil(box / stride) elements are loaded per dimension
+      box[1] = (cuuint32_t)(8 * m * g->isw); box[2] = (cuuint32_t)(16 * g->ish);
+      estr[1] = (cuuint32_t)g->isw; estr[2] = (cuuint32_t)g->ish;
+    }
     CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -394,12 +459,16 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   const int smem_bytes = p.stages * p.stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
     attr_done = true;
   }
   int grid = e2e_num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  conv_tc_kernel<<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
+  if (halo)
+    conv_tc_kernel<true><<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
+  else
+    conv_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
 }
@@ -582,6 +651,9 @@ int e2e_wgrad_tc_supported(const e2e_wgrad_t* p) {
   if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->ivh != 0 || p->ivw != 0) return 0;
   if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
   if (p->Npad > 256 || p->Npad % 16 != 0) return 0;
+  // two pipeline stages of (16 x-windows + Npad/8 gradient slabs) must fit in shared memory
+  const int x_slab = (18 * WG_ROWPITCH + 127) / 128 * 128;
+  if (2 * (16 * x_slab + (p->Npad / 8) * 2048) > SMEM_BUDGET) return 0;
   return 1;
 }
 

@@ -63,9 +63,24 @@ def c8_shape(x: torch.Tensor):
 
 
 # ---------------------------------------------------------------------------------------- raw calls
+# Packed operands are cached per plan until the weights (or their mask) change.  torch's version
+# counters see optimizer / load_state_dict updates; updates made through the C ABI (the drop-in
+# Masking writes weights and masks with raw pointers) are announced with bump_weight_epoch().
+_WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    _WEIGHT_EPOCH[0] += 1
+
+
 def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
     lib = _lib.load()
     dev = plan.dev(weight.device)
+    key = (weight.data_ptr(), weight._version, None if mask is None else (mask.data_ptr(), mask._version),
+           _WEIGHT_EPOCH[0], torch.is_grad_enabled() and weight.requires_grad)
+    hit = dev.get("_wp")
+    if hit is not None and hit[0] == key:
+        return hit[1]
     out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
     w = weight.detach()
     assert w.dtype == torch.float32 and w.is_contiguous()
@@ -73,6 +88,7 @@ def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tens
         assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == w.shape
     _lib.check(lib.e2e_pack_weights(_p(w), _p(mask), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]),
                                     plan.n_cent, plan.n_taps, plan.Npad, _p(out), _lib.stream_ptr()), "pack_weights")
+    dev["_wp"] = (key, out)
     return out
 
 
@@ -258,12 +274,8 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(need):
             outs = [torch.empty_like(s) for s in srcs]
-            sd, sh, sw = plan.stride
-            idx = 0
             for var in plan.dgrad:
-                pd, ph, pw = int(var.cols[0][3]), int(var.cols[0][4]), int(var.cols[0][5])
-                it = ((D - pd + sd - 1) // sd, (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw)
-                idx += 1
+                it = plan.dgrad_iter_grid(var, D, H, W)
                 if min(it) <= 0:
                     continue
                 wpd = pack_weights(var, weight, ctx.mask)
@@ -281,9 +293,11 @@ class TConv(torch.autograd.Function):
         _need_cuda(x, "tconv")
         B, Cb, D, H, W = c8_shape(x)
         kd, kh, kw = plan.k
-        wp = pack_weights(plan.fwd, weight, mask)
+        impl = CONFIG["impl"]
         y = torch.empty((B, plan.cout // 8, D * kd, H * kh, W * kw, 8), dtype=torch.bfloat16, device=x.device)
-        run_gemm(plan.fwd, wp, [x], (D, H, W), (D, H, W), B, [y], (D * kd, H * kh, W * kw), [plan.cout // 8], 0)
+        for chunk in plan.fwd:
+            run_gemm(chunk, pack_weights(chunk, weight, mask), [x], (D, H, W), (D, H, W), B, [y],
+                     (D * kd, H * kh, W * kw), [plan.cout // 8], impl)
         ctx.plan, ctx.mask = plan, mask
         ctx.save_for_backward(weight, x)
         return y
@@ -296,13 +310,15 @@ class TConv(torch.autograd.Function):
         kd, kh, kw = plan.k
         dy = dy.contiguous()
         fine = (D * kd, H * kh, W * kw)
+        impl = CONFIG["impl"]
         gw = dx = None
         if ctx.needs_input_grad[1]:
-            gw = run_wgrad(plan.dgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), 0)
+            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl)
         if ctx.needs_input_grad[3]:
-            wp = pack_weights(plan.dgrad, weight, ctx.mask)
             dx = torch.empty_like(x)
-            run_gemm(plan.dgrad, wp, [dy], fine, (D, H, W), B, [dx], (D, H, W), [Cb], 0)
+            for chunk in plan.dgrad:
+                run_gemm(chunk, pack_weights(chunk, weight, ctx.mask), [dy], fine, (D, H, W), B, [dx], (D, H, W),
+                         [Cb], impl)
         return None, gw, None, dx
 
 

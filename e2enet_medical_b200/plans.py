@@ -43,6 +43,11 @@ class GemmPlan:
     ivoff: Tuple[int, int, int] = (0, 0, 0)
     ostride: Tuple[int, int, int] = (1, 1, 1)
     out_mode: int = 0
+    # iteration grid of a data-gradient variant over a destination grid (D, H, W) with conv stride s:
+    # it = ceil((D - iter_off) / s) + iter_extra   (see ShiftConvPlan.dgrad_iter_grid)
+    iter_off: Tuple[int, int, int] = (0, 0, 0)
+    iter_extra: Tuple[int, int, int] = (0, 0, 0)
+    halo: bool = False          # stride-1 3x3 halo form (tcgen05 kernel eligible)
     _dev: Dict = field(default_factory=dict, repr=False)
 
     @property
@@ -102,6 +107,11 @@ class ShiftConvPlan:
         sd, sh, sw = self.stride
         return (D - 1) // sd + 1, (H + 2 - 3) // sh + 1, (W + 2 - 3) // sw + 1
 
+    def dgrad_iter_grid(self, var: GemmPlan, D, H, W):
+        """iteration grid of data-gradient variant `var` for a source grid (D, H, W)."""
+        return tuple((n - o + s - 1) // s + e
+                     for n, o, s, e in zip((D, H, W), var.iter_off, self.stride, var.iter_extra))
+
 
 def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1), shift: bool = True) -> ShiftConvPlan:
     src_channels = [int(c) for c in src_channels]
@@ -124,7 +134,7 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
     tapoff = [kh * 3 + kw for kh in range(3) for kw in range(3)]
     cols = [[0, q, 0xff, 0, 0, 0] for q in range(cout // 8)]
     rowoff = [n * cin * 9 for n in range(cout)]
-    fwd = _finish(cents, centoff, taps, tapoff, cols, rowoff, istride=stride)
+    fwd = _finish(cents, centoff, taps, tapoff, cols, rowoff, istride=stride, halo=(stride == (1, 1, 1)))
 
     # ---- dgrad: source of the GEMM is d(raw) on the conv's output grid, K = Cout x taps
     g_cents = [[0, e, 0, 0, 0] for e in range(cout // 8)]
@@ -132,6 +142,35 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
     _pad_even(g_cents, g_centoff)
     sd, shh, sww = stride
     variants: List[GemmPlan] = []
+    if stride == (1, 1, 1):
+        # One GEMM over the depth range of d(raw) that any shift group needs: iteration depth o reads
+        # d(raw) at depth o + smin and stores the columns of a group shifted by s at depth o + smin - s
+        # (dx[c, d] = dx~[c, d + s_c]); depths outside d(raw) read zeros, which also writes the zero
+        # slices of dx the shift leaves uncovered.  Columns are chunked to <= 256 per GEMM.
+        shifts = sorted({int(v) for v in sh_c})
+        smin, smax = shifts[0], shifts[-1]
+        ucols, urow = [], []
+        for i, ci in enumerate(src_channels):
+            for blk in range((ci + 7) // 8):
+                chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
+                for s in sorted({int(sh_c[c]) for c in chans if c >= 0}):
+                    m = 0
+                    for j, c in enumerate(chans):
+                        if c >= 0 and sh_c[c] == s:
+                            m |= 1 << j
+                    ucols.append([i, blk, m, smin - s, 0, 0])
+                    urow.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
+        taps_d = [[0, 1 - kh, 1 - kw] for kh in range(3) for kw in range(3)]
+        tapoff_d = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+        n_chunks = -(-len(ucols) // 32)
+        per = -(-len(ucols) // n_chunks)
+        per += per % 2
+        for c0 in range(0, len(ucols), per):
+            cc, rr = ucols[c0:c0 + per], [v for r in urow[c0:c0 + per] for v in r]
+            variants.append(_finish([list(c) for c in g_cents], [list(c) for c in g_centoff], taps_d, tapoff_d,
+                                    cc, rr, istride=(1, 1, 1), ivoff=(smin, 0, 0), ostride=(1, 1, 1),
+                                    iter_extra=(smax - smin, 0, 0), halo=True))
+        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, variants)
     for s in sorted({int(v) for v in sh_c}):
         vcols, vrow = [], []
         for i, ci in enumerate(src_channels):
@@ -166,20 +205,30 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
                     row_v = list(vrow) if live else [-1] * len(vrow)
                     variants.append(_finish([list(c) for c in g_cents], [list(c) for c in g_centoff], vt, vto, cols_v,
                                             row_v, istride=(1, 1, 1),
-                                            ivoff=((pd + s) // sd if ok_d else 0, 0, 0), ostride=stride))
+                                            ivoff=((pd + s) // sd if ok_d else 0, 0, 0), ostride=stride,
+                                            iter_off=(pd, ph, pw)))
     return ShiftConvPlan(src_channels, cin, cout, stride, fwd, variants)
 
 
 # ----------------------------------------------------------------------------------------
 # ConvTranspose3d with kernel == stride (the up* modules), weight (Cin, Cout, kd, kh, kw)
 # ----------------------------------------------------------------------------------------
+def _col_chunks(n_blocks: int, max_blocks: int = 32) -> List[Tuple[int, int]]:
+    """balanced split of n_blocks 8-column blocks into chunks of <= max_blocks (even sizes: Npad % 16 == 0)"""
+    n_chunks = -(-n_blocks // max_blocks)
+    per = -(-n_blocks // n_chunks)
+    per += per % 2
+    return [(c0, min(n_blocks, c0 + per)) for c0 in range(0, n_blocks, per)]
+
+
 @dataclass
 class TConvPlan:
     cin: int
     cout: int
     k: Tuple[int, int, int]
-    fwd: GemmPlan
-    dgrad: GemmPlan               # also the wgrad gather plan (same entries, grad = x)
+    fwd: List[GemmPlan]           # column chunks of <= 256 (N = taps x Cout)
+    dgrad: List[GemmPlan]         # column chunks of <= 256 (N = Cin)
+    wgrad: GemmPlan               # gather plan of the weight gradient (dgrad's K entries, all Cin columns, grad = x)
 
 
 def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
@@ -197,7 +246,8 @@ def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
         for q in range(cout // 8):
             cols.append([0, q, 0xff, a, b, c])
             rowoff.extend([(q * 8 + j) * kv + t for j in range(8)])
-    fwd = _finish(cents, centoff, [[0, 0, 0]], [0], cols, rowoff, ostride=k)
+    fwd = [_finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols[a:b],
+                   rowoff[8 * a:8 * b], ostride=k) for a, b in _col_chunks(len(cols))]
     # dgrad: K = (tap, Cout block) gathered from dy at u*k + tap, N = Cin
     cents, centoff = [], []
     for t, (a, b, c) in enumerate(tl):
@@ -207,8 +257,10 @@ def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
     _pad_even(cents, centoff)
     cols = [[0, q, 0xff, 0, 0, 0] for q in range(cin // 8)]
     rowoff = [n * cout * kv for n in range(cin)]
-    dgrad = _finish(cents, centoff, [[0, 0, 0]], [0], cols, rowoff, istride=k)
-    return TConvPlan(cin, cout, k, fwd, dgrad)
+    wgrad = _finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols, rowoff, istride=k)
+    dgrad = [_finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols[a:b],
+                     rowoff[8 * a:8 * b], istride=k) for a, b in _col_chunks(len(cols))]
+    return TConvPlan(cin, cout, k, fwd, dgrad, wgrad)
 
 
 # ----------------------------------------------------------------------------------------

@@ -360,6 +360,8 @@ class Masking(object):
         if not params:
             return
         lib = _lib.load()
+        from .. import ops
+        ops.bump_weight_epoch()          # weights / masks change below through raw pointers
         moms = []
         for name, p in params:
             self._check_cuda(p, "parameter " + name)
@@ -455,6 +457,8 @@ class Masking(object):
 
     # -- reference-signature entry points (standalone use; they sync like the reference does)
     def kernel_death(self, mask, weight, name):
+        from .. import ops
+        ops.bump_weight_epoch()
         lib = _lib.load()
         k_size = int(np.prod(weight.shape[-3:]))
         n_kernels = weight.shape[0] * weight.shape[1]
@@ -476,6 +480,8 @@ class Masking(object):
         return mask, prune_num
 
     def kernel_growth(self, name, new_mask, weight):
+        from .. import ops
+        ops.bump_weight_epoch()
         lib = _lib.load()
         num_growth = self.num_death[name]
         out = new_mask.float().contiguous().clone()
@@ -492,6 +498,8 @@ class Masking(object):
         return out.to(new_mask.dtype)
 
     def kernel_grad_growth(self, name, new_mask, weight):
+        from .. import ops
+        ops.bump_weight_epoch()
         # reference :771-790 (growth='gradient'); bookkeeping-sized torch ops on (C0, C1) matrices
         num_growth = self.num_death[name]
         if num_growth == 0:

@@ -359,8 +359,7 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial):
     outs = [torch.full_like(s, float("nan")) for s in xs8]
     sd, sh, sw = stride
     for var in plan.dgrad:
-        pd, ph, pw = (int(v) for v in var.cols[0][3:6])
-        it = ((D - pd + sd - 1) // sd, (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw)
+        it = plan.dgrad_iter_grid(var, D, H, W)
         if min(it) <= 0:
             continue
         ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W),

@@ -64,8 +64,8 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     (ref * g).sum().backward()
     douts = [torch.full_like(s, float("nan")) for s in xs8]
     for var in plan.dgrad:
-        ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (D, H, W), (D, H, W), B, douts, (D, H, W),
-                     [s.shape[1] for s in xs8], 1)
+        ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (D, H, W), plan.dgrad_iter_grid(var, D, H, W), B,
+                     douts, (D, H, W), [s.shape[1] for s in xs8], 1)
     torch.cuda.synchronize()
     off = 0
     for o, c in zip(douts, src):
@@ -73,3 +73,48 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
         assert not torch.isnan(got).any()
         assert rel(got, xc.grad[:, off:off + c]) < ULP
         off += c
+
+
+@pytest.mark.parametrize("cin,cout,k,spatial,B", [
+    (96, 48, (1, 2, 2), (3, 20, 40), 2),      # up4-style: N = 192, m = 1, several tiles, ragged H
+    (32, 16, (2, 2, 2), (3, 5, 12), 1),       # N = 128, m = 2, partial tiles in H and W
+    (192, 96, (2, 2, 2), (2, 8, 8), 1),       # N = 768 -> 3 column chunks; dgrad K = 8 taps x 12 blocks
+    (320, 320, (2, 2, 2), (1, 5, 5), 1),      # N = 2560 -> 10 chunks; dgrad N = 320 -> 2 chunks
+    (16, 8, (1, 1, 1), (2, 3, 3), 2),         # pool [1,1,1] (config 1): stride-1 point GEMM
+])
+def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
+    """ConvTranspose3d(kernel == stride) forward / data gradient through the 1-tap tcgen05 kernel
+    (strided TMA boxes, per-column-block scatter) vs the mma.sync gather kernel and torch."""
+    from e2enet_medical_b200 import ops
+    from e2enet_medical_b200.plans import build_tconv_plan
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(7)
+    bf = lambda t: t.bfloat16().float()
+    D, H, W = spatial
+    fine = (D * k[0], H * k[1], W * k[2])
+    x = bf(torch.from_numpy(rs.standard_normal((B, cin) + spatial).astype(np.float32))).to(dev)
+    w = bf(torch.from_numpy((rs.standard_normal((cin, cout) + k) / np.sqrt(cin)).astype(np.float32))).to(dev)
+    g = bf(torch.from_numpy(rs.standard_normal((B, cout) + fine).astype(np.float32))).to(dev)
+    plan = build_tconv_plan(cin, cout, k)
+    x8, g8 = ops.nc_to_c8(x), ops.nc_to_c8(g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv_transpose3d(xr, wr, stride=k)
+    (yr * g).sum().backward()
+    res = {}
+    for impl in (0, 1):
+        y = torch.full((B, cout // 8) + fine + (8,), float("nan"), dtype=torch.bfloat16, device=dev)
+        for ch in plan.fwd:
+            ops.run_gemm(ch, ops.pack_weights(ch, w, None), [x8], spatial, spatial, B, [y], fine, [cout // 8], impl)
+        dx = torch.full_like(x8, float("nan"))
+        for ch in plan.dgrad:
+            ops.run_gemm(ch, ops.pack_weights(ch, w, None), [g8], fine, spatial, B, [dx], spatial, [cin // 8], impl)
+        gw = ops.run_wgrad(plan.wgrad, [g8], fine, spatial, B, x8, tuple(w.shape), impl)
+        torch.cuda.synchronize()
+        res[impl] = (ops.c8_to_nc(y, cout), ops.c8_to_nc(dx, cin), gw)
+    for impl in (0, 1):
+        y, dx, gw = res[impl]
+        assert not torch.isnan(y).any() and not torch.isnan(dx).any()
+        assert rel(y, yr) < ULP, (impl, rel(y, yr))
+        assert rel(dx, xr.grad) < ULP, (impl, rel(dx, xr.grad))
+        assert rel(gw, wr.grad) < 2e-4, (impl, rel(gw, wr.grad))

@@ -82,8 +82,7 @@ def test_shiftconv_plans_reproduce_oracle(src, cout, stride, spatial):
     outs = [np.full(pi.to_c8(a).shape, np.nan) for a in xs]
     sd, sh, sw = stride
     for var in plan.dgrad:
-        pd, ph, pw = (int(v) for v in var.cols[0][3:6])
-        it = ((D - pd + sd - 1) // sd, (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw)
+        it = plan.dgrad_iter_grid(var, D, H, W)
         if min(it) <= 0:
             continue
         pi.gemm(var, pi.pack(var, w), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W))
@@ -103,7 +102,8 @@ def test_shiftconv_plan_applies_mask_on_pack():
 
 
 @pytest.mark.parametrize("cin,cout,k,spatial", [(16, 8, (1, 2, 2), (3, 3, 4)), (8, 16, (2, 2, 2), (2, 3, 2)),
-                                               (8, 8, (1, 1, 1), (2, 2, 3))])
+                                               (8, 8, (1, 1, 1), (2, 2, 3)),
+                                               (8, 40, (2, 2, 2), (1, 2, 2))])   # N = 320 -> two column chunks
 def test_tconv_plans_reproduce_torch(cin, cout, k, spatial):
     from e2enet_medical_b200.plans import build_tconv_plan
     rs = np.random.RandomState(4)
@@ -116,14 +116,17 @@ def test_tconv_plans_reproduce_torch(cin, cout, k, spatial):
     plan = build_tconv_plan(cin, cout, k)
     fine = tuple(s * kk for s, kk in zip(spatial, k))
     y = np.full((B, cout // 8) + fine + (8,), np.nan)
-    pi.gemm(plan.fwd, pi.pack(plan.fwd, w), [pi.to_c8(x)], spatial, spatial, B, [y], fine)
+    for ch in plan.fwd:
+        assert ch.Npad <= 256
+        pi.gemm(ch, pi.pack(ch, w), [pi.to_c8(x)], spatial, spatial, B, [y], fine)
     np.testing.assert_allclose(pi.from_c8(y, cout), ref.detach().numpy(), atol=1e-9)
     gy = rs.standard_normal(tuple(ref.shape))
     (ref * torch.from_numpy(gy)).sum().backward()
     dx = np.full(pi.to_c8(x).shape, np.nan)
-    pi.gemm(plan.dgrad, pi.pack(plan.dgrad, w), [pi.to_c8(gy)], fine, spatial, B, [dx], spatial)
+    for ch in plan.dgrad:
+        pi.gemm(ch, pi.pack(ch, w), [pi.to_c8(gy)], fine, spatial, B, [dx], spatial)
     np.testing.assert_allclose(pi.from_c8(dx, cin), tx.grad.numpy(), atol=1e-9)
-    gw = pi.wgrad(plan.dgrad, [pi.to_c8(gy)], fine, spatial, B, pi.to_c8(x), w.shape)
+    gw = pi.wgrad(plan.wgrad, [pi.to_c8(gy)], fine, spatial, B, pi.to_c8(x), w.shape)
     np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
 
 
@@ -165,7 +168,7 @@ def test_real_layer_plans_are_consistent():
         nvar = stride[0] * stride[1] * stride[2]
         seen = {}
         for var in plan.dgrad:
-            par = tuple(int(v) for v in var.cols[0][3:6])
+            par = tuple(int(v) for v in var.iter_off)
             live = var.rowoff[var.rowoff >= 0] // 9
             # columns of a variant address distinct channels
             cols = []
