@@ -27,6 +27,7 @@
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -41,6 +42,8 @@ struct TcParams {
   int isd, ish, isw, ivh, ivw;     // point form: source voxel = o * is + iv + entry offset
   int osd, osh, osw;               // destination voxel = o * os + column-block offset
   int rows;                        // window rows per slab: 18 (halo) or 16 (point)
+  int need_bounds;                 // destination offsets / strides can leave the destination grid
+  int merged;                      // source maps are 4-D with the merged (W, channel) inner dimension
   int n_cent, Npad, m, stages, acc_stages;
   int ivd;
   int tiles_h, tiles_w, n_tiles;
@@ -95,6 +98,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// 4-D form for the stride-1 maps: (W, channel) is merged into one contiguous inner dimension of
+// 32-bit elements (one voxel = 16 B = 4 elements), so a window row is ONE contiguous TMA row
+// instead of 8m+2 separate 16-byte rows
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -117,6 +130,13 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -142,19 +162,45 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <bool HALO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// tcgen05.mma with the two 64-bit shared-memory descriptors given as (lo, hi) halves: all descriptor
+// arithmetic of the issue loop stays 32-bit
+__device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+struct ColInfo {            // one 8-column block of the result, decoded once per CTA
+  int32_t off;              // voxel offset of (blk, od, oh, ow) inside one sample of the destination
+  int32_t bstride;          // voxels per sample of that destination (dst_cb * Dd * Hd * Wd)
+  int16_t od, oh, ow;
+  int8_t dst;               // -1: dead block
+  uint8_t chmask;
+};
+
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS2 = 64 + 32 * EPI_WARPS;
+
+template <bool HALO, int MS>      // MS: 8-voxel-wide sub-tiles (accumulators) per tile
+__global__ void __launch_bounds__(TC_THREADS2, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
   constexpr int NT = HALO ? 9 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_s;
   __shared__ e2e_centry_t s_cents[MAX_CENT];
+  __shared__ ColInfo s_cols[32];
   __shared__ int s_tapoff[9];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = p.m, Npad = p.Npad, S = p.stages, AS = p.acc_stages;
-  const int rowpitch = (8 * m + (HALO ? 2 : 0)) * 16;   // bytes per window row
+  const int Npad = p.Npad, S = p.stages, AS = p.acc_stages;
+  constexpr int rowpitch = (8 * MS + (HALO ? 2 : 0)) * 16;   // bytes per window row
   const int npairs = p.n_cent >> 1;
   // barrier indices
   auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
@@ -162,7 +208,19 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   auto tfull_bar = [&](int a) { return smem_u32(&bars[16 + a]); };
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
 
-  for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS) s_cents[i] = p.cents[i];
+  for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS2) s_cents[i] = p.cents[i];
+  if (threadIdx.x < (Npad >> 3)) {
+    const e2e_colblk_t c = p.cols[threadIdx.x];
+    ColInfo ci;
+    const int dst = (c.dst >= 0 && c.chmask != 0) ? c.dst : -1;
+    const int plane = p.Ddst * p.Hd * p.Wd;
+    ci.dst = (int8_t)dst;
+    ci.chmask = (uint8_t)c.chmask;
+    ci.od = (int16_t)c.od; ci.oh = (int16_t)c.oh; ci.ow = (int16_t)c.ow;
+    ci.off = dst >= 0 ? c.blk * plane + (c.od * p.Hd + c.oh) * p.Wd + c.ow : 0;
+    ci.bstride = dst >= 0 ? p.dst_cb[dst] * plane : 0;
+    s_cols[threadIdx.x] = ci;
+  }
   if (threadIdx.x < 9) {
     int off = 0;
     if (HALO) {
@@ -173,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -198,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         const int ht = t % p.tiles_h; t /= p.tiles_h;
         const int d = t % p.D;
         const int b = t / p.D;
-        const int h0 = ht * TH, w0 = wt * 8 * m;
+        const int h0 = ht * TH, w0 = wt * 8 * MS;
         for (int pr = 0; pr < npairs; ++pr) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), tx);
@@ -207,8 +265,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
           for (int hf = 0; hf < 2; ++hf) {
             const e2e_centry_t ce = s_cents[2 * pr + hf];
             if (HALO)
-              tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
+              tma_load_4d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
                           d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+            else if (p.merged)
+              tma_load_4d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
+                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
             else
               tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
                           h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
@@ -221,52 +282,56 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer (warp-uniform loop, one elected lane issues)
-    {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=Npad, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
-      int stage = 0, phase = 0, as = 0, aphase = 0;
-      const uint64_t adesc_hi = make_desc(0, p.a_slab_bytes, rowpitch) & 0xffffffff00000000ull;
-      const uint32_t adesc_lo_hi = (uint32_t)(make_desc(0, p.a_slab_bytes, rowpitch) & 0xffff0000ull);
-      const uint64_t bdesc_hi = make_desc(0, Npad * 16, 128) & 0xffffffff00000000ull;
-      const uint32_t bdesc_lo_hi = (uint32_t)(make_desc(0, Npad * 16, 128) & 0xffff0000ull);
-      const int b_tap_units = (2 * Npad * 16) >> 4;
-      int tapoff_units[NT];
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=Npad, M=128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
+    int stage = 0, phase = 0, as = 0, aphase = 0;
+    // descriptors differ only in the 14-bit start-address field (units of 16 B) of the low word
+    const uint64_t adesc = make_desc(0, p.a_slab_bytes, rowpitch);
+    const uint64_t bdesc = make_desc(0, Npad * 16, 128);
+    const uint32_t a_hi = (uint32_t)(adesc >> 32), a_lo0 = (uint32_t)adesc;
+    const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
+    const uint32_t b_tap_units = (uint32_t)(2 * Npad * 16) >> 4;
+    uint32_t tapu[NT];
 #pragma unroll
-      for (int t = 0; t < NT; ++t) tapoff_units[t] = s_tapoff[t] >> 4;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1);
+    for (int t = 0; t < NT; ++t) tapu[t] = (uint32_t)s_tapoff[t] >> 4;
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t sa0 = smem_base >> 4;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1);
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(as * MS * Npad);
+      for (int pr = 0; pr < npairs; ++pr) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(as * m * Npad);
-        for (int pr = 0; pr < npairs; ++pr) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t sa = smem_base + stage * p.stage_bytes;
-            const uint32_t sb = sa + p.a_stage_bytes;
-            // descriptors differ only in the 14-bit start-address field (units of 16 B): add to the low word
-            const uint64_t a0 = adesc_hi | (uint64_t)(adesc_lo_hi | (sa >> 4));
-            const uint64_t b0 = bdesc_hi | (uint64_t)(bdesc_lo_hi | (sb >> 4));
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units;
+          const uint32_t b_lo = b_lo0 + sa0 + (uint32_t)stage * stage_units + a_stage_units;
+          const uint32_t first = pr ? 1u : 0u;
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-              const uint64_t bdesc = b0 + (uint64_t)(t * b_tap_units);
-              const uint64_t a_t = a0 + (uint64_t)tapoff_units[t];
-              for (int j = 0; j < m; ++j)
-                tc_mma_f16(acc0 + j * Npad, a_t + (uint64_t)(j * 8), bdesc, idesc, (pr | t) ? 1u : 0u);
-            }
-            tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
+          for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int j = 0; j < MS; ++j)
+              tc_mma_f16_lh(acc0 + (uint32_t)(j * Npad), a_lo + tapu[t] + (uint32_t)(j * 8), a_hi,
+                            b_lo + (uint32_t)t * b_tap_units, b_hi, idesc, t ? 1u : first);
           }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
         }
-        if (elect_one_sync()) tc_commit(tfull_bar(as));   // accumulators of this tile are complete
         __syncwarp();
-        if (++as == AS) { as = 0; aphase ^= 1; }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) tc_commit(tfull_bar(as));   // accumulators of this tile are complete
+      __syncwarp();
+      if (++as == AS) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ================================================= epilogue (warps 2..5 -> TMEM lane quadrants)
+    // ================================================= epilogue: 8 warps, 2 per TMEM lane quadrant;
+    // the two warps of a quadrant take alternate 32-column chunks
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;                  // accumulator row = voxel (r / 8, r % 8) of a sub-tile
+    const int nchunk = (Npad + 31) >> 5;
+    const bool need_bounds = p.need_bounds != 0;
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int t = tile;
@@ -275,57 +340,60 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       const int d = t % p.D;
       const int b = t / p.D;
       const int h = ht * TH + (r >> 3);
+      const int hs = h * p.osh, ds = d * p.osd;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
-      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * m * Npad);
-      for (int j = 0; j < m; ++j) {
-        const int w = wt * 8 * m + j * 8 + (r & 7);
+      const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MS * Npad);
+      for (int ci = grp; ci < MS * nchunk; ci += 2) {
+        const int j = ci / nchunk, c0 = (ci - j * nchunk) << 5;
+        const int w = (wt * MS + j) * 8 + (r & 7);
+        const int ws = w * p.osw;
         const bool inb = (h < p.H) && (w < p.W);
-        const int hs = h * p.osh, ws = w * p.osw, ds = d * p.osd;
-        for (int cq = 0; cq < Npad / 8; cq += 2) {
-          uint32_t v[16];
-          tc_ld8(acc0 + j * Npad + cq * 8, v);
-          tc_ld8(acc0 + j * Npad + cq * 8 + 8, v + 8);
-          tc_wait_ld();
+        const int tv = (ds * p.Hd + hs) * p.Wd + ws;
+        uint32_t v[32];
+        const bool two = c0 + 16 < Npad;
+        tc_ld16(acc0 + j * Npad + c0, v);
+        if (two) tc_ld16(acc0 + j * Npad + c0 + 16, v + 16);
+        tc_wait_ld();
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const e2e_colblk_t col = p.cols[cq + u];
-            if (!inb || col.dst < 0 || col.chmask == 0) continue;
-            // per-column-block destination offset: depth for the shift-folded dgrad, all three for tconv
+        for (int u = 0; u < 4; ++u) {
+          if (u >= 2 && !two) break;
+          const ColInfo col = s_cols[(c0 >> 3) + u];
+          if (!inb || col.dst < 0) continue;
+          if (need_bounds) {
             const int dd = ds + col.od, hh = hs + col.oh, ww = ws + col.ow;
             if ((unsigned)dd >= (unsigned)p.Ddst || (unsigned)hh >= (unsigned)p.Hd || (unsigned)ww >= (unsigned)p.Wd)
               continue;
-            bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) +
-                       (((((size_t)b * p.dst_cb[col.dst] + col.blk) * p.Ddst + dd) * p.Hd + hh) * (size_t)p.Wd + ww) * 8;
-            const uint32_t* vv = v + u * 8;
-            uint4 o = make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
-                                 pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
-                                 pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
-                                 pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
-            if (col.chmask == 0xff) {
-              *reinterpret_cast<uint4*>(dp) = o;
-            } else {
-              // shift groups are contiguous channel ranges: store the selected channels in the widest
-              // aligned pieces (8 / 4 / 2 bytes)
-              const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-              const int cm = col.chmask;
+          }
+          bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
+          const uint32_t* vv = v + u * 8;
+          uint4 o = make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
+                               pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
+                               pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
+                               pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
+          if (col.chmask == 0xff) {
+            *reinterpret_cast<uint4*>(dp) = o;
+          } else {
+            // shift groups are contiguous channel ranges: store the selected channels in the widest
+            // aligned pieces (8 / 4 / 2 bytes)
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            const int cm = col.chmask;
 #pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int m4 = (cm >> (4 * h2)) & 0xf;
-                if (m4 == 0xf) {
-                  *reinterpret_cast<uint2*>(dp + 4 * h2) = make_uint2(ow[2 * h2], ow[2 * h2 + 1]);
-                } else {
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int m4 = (cm >> (4 * h2)) & 0xf;
+              if (m4 == 0xf) {
+                *reinterpret_cast<uint2*>(dp + 4 * h2) = make_uint2(ow[2 * h2], ow[2 * h2 + 1]);
+              } else {
 #pragma unroll
-                  for (int q2 = 0; q2 < 2; ++q2) {
-                    const int m2 = (m4 >> (2 * q2)) & 3;
-                    const int e = 4 * h2 + 2 * q2;
-                    if (m2 == 3) {
-                      *reinterpret_cast<uint32_t*>(dp + e) = ow[2 * h2 + q2];
-                    } else if (m2) {
-                      const bf16* ov = reinterpret_cast<const bf16*>(&ow[2 * h2 + q2]);
-                      if (m2 & 1) dp[e] = ov[0];
-                      if (m2 & 2) dp[e + 1] = ov[1];
-                    }
+                for (int q2 = 0; q2 < 2; ++q2) {
+                  const int m2 = (m4 >> (2 * q2)) & 3;
+                  const int e = 4 * h2 + 2 * q2;
+                  if (m2 == 3) {
+                    *reinterpret_cast<uint32_t*>(dp + e) = ow[2 * h2 + q2];
+                  } else if (m2) {
+                    const bf16* ov = reinterpret_cast<const bf16*>(&ow[2 * h2 + q2]);
+                    if (m2 & 1) dp[e] = ov[0];
+                    if (m2 & 2) dp[e + 1] = ov[1];
                   }
                 }
               }
@@ -412,6 +480,9 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   p.m = m;
   p.acc_stages = (2 * m * g->Npad <= 512) ? 2 : 1;
   p.rows = halo ? 18 : 16;
+  // halo-form forward stores in place (no offsets); everything else checks the destination bounds
+  p.merged = (halo || g->isw == 1) ? 1 : 0;
+  p.need_bounds = !(halo && g->Do == g->Dd && g->ivd == 0) || g->osd != 1 || g->osh != 1 || g->osw != 1;
   const int rowpitch = (8 * m + (halo ? 2 : 0)) * 16;
   p.a_slab_bytes = (p.rows * rowpitch + 127) / 128 * 128;
   p.a_stage_bytes = 2 * p.a_slab_bytes;
@@ -434,19 +505,26 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
     const int si = i < g->n_src ? i : 0;
     p.src_cb[i] = g->src_cb[si];
-    cuuint64_t gdim[5] = {8, (cuuint64_t)g->Wi, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16,
-                          (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)(8 * m + 2), 18, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    if (!halo) {
+    CUresult r;
+    if (p.merged) {
+      cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+      cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+      cuuint32_t box[4] = {(cuuint32_t)((8 * m + (halo ? 2 : 0)) * 4), (cuuint32_t)(halo ? 18 : 16 * g->ish), 1, 1};
+      cuuint32_t estr[4] = {1, (cuuint32_t)(halo ? 1 : g->ish), 1, 1};
+      r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
       // traversal strides: ceil(box / stride) elements are loaded per dimension
-      box[1] = (cuuint32_t)(8 * m * g->isw); box[2] = (cuuint32_t)(16 * g->ish);
-      estr[1] = (cuuint32_t)g->isw; estr[2] = (cuuint32_t)g->ish;
+      cuuint64_t gdim[5] = {8, (cuuint64_t)g->Wi, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+      cuuint64_t gstr[4] = {16, (cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16,
+                            (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+      cuuint32_t box[5] = {8, (cuuint32_t)(8 * m * g->isw), (cuuint32_t)(16 * g->ish), 1, 1};
+      cuuint32_t estr[5] = {1, (cuuint32_t)g->isw, (cuuint32_t)g->ish, 1, 1};
+      r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
-    CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       e2e_set_error("conv_tc_fwd: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
       return E2E_ERR_CUDA;
@@ -457,18 +535,20 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
     p.dst_cb[i] = i < g->n_dst ? g->dst_cb[i] : 0;
   }
   const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  typedef void (*kern_t)(const TcParams, const TcMaps);
+  static const kern_t kerns[2][4] = {
+      {conv_tc_kernel<false, 1>, conv_tc_kernel<false, 2>, conv_tc_kernel<false, 3>, conv_tc_kernel<false, 4>},
+      {conv_tc_kernel<true, 1>, conv_tc_kernel<true, 2>, conv_tc_kernel<true, 3>, conv_tc_kernel<true, 4>}};
   static bool attr_done = false;
   if (!attr_done) {
-    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
-    E2E_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 4; ++b)
+        E2E_CUDA(cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
     attr_done = true;
   }
   int grid = e2e_num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  if (halo)
-    conv_tc_kernel<true><<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
-  else
-    conv_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, st>>>(p, maps);
+  kerns[halo ? 1 : 0][m - 1]<<<grid, TC_THREADS2, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
 }
@@ -573,10 +653,10 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
           const uint32_t sx = smem_base + stage * p.stage_bytes;
           for (int e = 0; e < ne; ++e) {
             const e2e_centry_t ce = s_cents[e];
-            tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 - 1, h0 - 1,
+            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
                         d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
           }
-          tma_load_5d(sx + p.x_bytes, &maps.g, full_bar(stage), 0, w0, h0, d, b * p.grad_cb);
+          tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -702,11 +782,11 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
     const int si = i < g->n_src ? i : 0;
     p.src_cb[i] = g->src_cb[si];
-    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
-    cuuint32_t box[5] = {8, 10, 18, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box,
+    cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[4] = {40, 18, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -715,11 +795,11 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
     }
   }
   {
-    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
-    cuuint32_t box[5] = {8, 8, 16, 1, (cuuint32_t)(g->Npad / 8)};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&maps.g, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->grad), gdim, gstr, box, estr,
+    cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[4] = {32, 16, 1, (cuuint32_t)(g->Npad / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps.g, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->grad), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
