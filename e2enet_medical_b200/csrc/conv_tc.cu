@@ -33,7 +33,7 @@ namespace {
 
 constexpr int TC_THREADS = 192;
 constexpr int TH = 16;                 // tile rows (H)
-constexpr int MAX_CENT = 320;
+constexpr int MAX_CENT = 384;
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct TcParams {
@@ -554,27 +554,34 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
 }
 
 // =====================================================================================
-// tcgen05 weight-gradient kernel (same halo form): K = voxels.
+// tcgen05 weight-gradient kernel: K = voxels.
 //
-//   dwp[(cent e, tap t)][n][j] += sum_v  x_e[v + tap_t][j] * g[v][n]
+//   dwp[(cent e, tap t)][n][j] += sum_v  x_e[v * is + off_e + tap_t][j] * g[v][n]
 //
-// GEMM view per tap: D[M = 16 channel entries x 8 ch = 128][N = Npad] += A^T B with K = the 128
-// voxels of a 16(H) x 8(W) tile, 16 voxels (2 rows) per tcgen05.mma.  Both operands are read
-// straight from C8 slabs as MN-major no-swizzle UMMA operands: a core matrix is 8 W-consecutive
-// voxels x 8 channels (128 contiguous bytes); LBO = one tile/window row (next 8 voxels),
-// SBO = one slab (next 8 channels).  The 9 taps read the same haloed x window through different
-// descriptor start addresses and accumulate into 9 (or fewer, when 9*Npad > 512) TMEM
-// accumulators that live across ALL voxel tiles of the CTA; one fp32 atomic flush at the end.
-// Jobs: (16-entry group mg) x (tap group tg) x (voxel split); one CTA per job.
+// GEMM view per (entry group, tap): D[M = 16 channel entries x 8 ch = 128][N = Nc] += A^T B with
+// K = the 128 voxels of a 16(H) x 8(W) tile, 16 voxels (2 rows) per tcgen05.mma.  Both operands
+// are read straight from C8 slabs as MN-major no-swizzle UMMA operands: a core matrix is 8
+// W-consecutive voxels x 8 channels (128 contiguous bytes); LBO = one tile/window row (next 8
+// voxels), SBO = one slab (next 8 channels).
+//   HALO form (stride-1 3x3 convs): the 9 taps read the same haloed x window through different
+//     descriptor start addresses; one CTA owns `nt` taps of one entry group.
+//   POINT form (1 tap: transposed convs, strided convs as (tap, block) entries): every entry is its
+//     own TMA box (elementStrides = input stride, per-entry start offset); one CTA owns `G`
+//     consecutive entry groups that share the gradient tile.
+// The G * nt accumulators (Nc columns each, G * nt * Nc <= 512) live in TMEM across ALL voxel
+// tiles of the CTA; one fp32 atomic flush at the end.  Jobs: (entry-group set) x (tap group) x
+// (column chunk of <= 256 gradient channels) x (voxel split); one CTA per job.
 // =====================================================================================
 namespace {
 
 struct WgParams {
-  int B, D, H, W;
-  int n_cent, Npad, ivd;
+  int B, D, H, W;                  // iteration grid = grid of the gradient operand
+  int n_cent, Npad, ivd, ivh, ivw;
+  int isd, ish, isw;
   int tiles_h, tiles_w, n_tiles;
-  int n_tg, taps_per_group, splits, tiles_per_split;
-  int x_slab_bytes, g_slab_bytes, x_bytes, stage_bytes, stages;
+  int n_mgj, G, n_tg, taps_per_group, n_taps, n_chunks, Nc, splits, tiles_per_split;
+  int x_slab_bytes, x_rowpitch, x_rows, g_slab_bytes, x_bytes, stage_bytes, stages;
+  int merged;
   int src_cb[E2E_MAX_SRC];
   int grad_cb;
   const e2e_centry_t* cents;
@@ -587,26 +594,31 @@ struct alignas(64) WgMaps {
   CUtensorMap g;
 };
 
-constexpr int WG_ROWPITCH = 10 * 16;       // haloed window row: (8 + 2) voxels x 16 B
+constexpr int WG_MAX_ENT = 64;             // entries per CTA (G <= 4 groups of 16)
 
+template <bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[20];
   __shared__ uint32_t tmem_base_s;
-  __shared__ e2e_centry_t s_cents[16];
+  __shared__ e2e_centry_t s_cents[WG_MAX_ENT];
   __shared__ int s_tapoff[9];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Npad = p.Npad, S = p.stages;
+  const int Nc = p.Nc, S = p.stages;
   int job = blockIdx.x;
   const int split = job % p.splits; job /= p.splits;
+  const int chunk = job % p.n_chunks; job /= p.n_chunks;
   const int tg = job % p.n_tg;
-  const int mg = job / p.n_tg;
-  const int e0 = mg * 16;
-  const int ne = min(16, p.n_cent - e0);                    // channel entries of this group
+  const int mgj = job / p.n_tg;
+  const int e0 = mgj * p.G * 16;
+  const int ne = min(p.G * 16, p.n_cent - e0);              // channel entries of this job
+  const int ng = (ne + 15) >> 4;                            // entry groups of this job
   const int t0 = tg * p.taps_per_group;
-  const int nt = min(p.taps_per_group, 9 - t0);             // taps of this group
+  const int nt = min(p.taps_per_group, p.n_taps - t0);      // taps of this job
+  const int n0 = chunk * Nc;                                // first gradient channel of this job
+  const int ncol = min(Nc, p.Npad - n0);                    // multiple of 16
   const int tile_lo = split * p.tiles_per_split;
   const int tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
   const int my_tiles = tile_hi - tile_lo;
@@ -617,8 +629,12 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
 
   if (threadIdx.x < ne) s_cents[threadIdx.x] = p.cents[e0 + threadIdx.x];
   if (threadIdx.x < 9) {
-    const e2e_tap_t t = p.taps[threadIdx.x];
-    s_tapoff[threadIdx.x] = (1 + t.dh) * WG_ROWPITCH + (1 + t.dw) * 16;
+    int off = 0;
+    if (HALO) {
+      const e2e_tap_t t = p.taps[threadIdx.x];
+      off = (1 + t.dh) * p.x_rowpitch + (1 + t.dw) * 16;
+    }
+    s_tapoff[threadIdx.x] = off;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -640,7 +656,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
     if (warp == 0) {
       if (lane == 0) {
         int stage = 0, phase = 0;
-        const uint32_t tx = (uint32_t)ne * 18u * WG_ROWPITCH + (uint32_t)Npad * 256u;
+        const uint32_t tx = (uint32_t)ne * (uint32_t)(p.x_rows * p.x_rowpitch) + (uint32_t)ncol * 256u;
         for (int tile = tile_lo; tile < tile_hi; ++tile) {
           int t = tile;
           const int wt = t % p.tiles_w; t /= p.tiles_w;
@@ -653,64 +669,86 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
           const uint32_t sx = smem_base + stage * p.stage_bytes;
           for (int e = 0; e < ne; ++e) {
             const e2e_centry_t ce = s_cents[e];
-            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
-                        d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+            const int cb = b * p.src_cb[ce.src] + ce.blk;
+            if (HALO)
+              tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
+                          d + p.ivd + ce.dd, cb);
+            else if (p.merged)
+              tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
+                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
+            else
+              tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
+                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
           }
-          tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb);
+          // gradient tile: ncol / 8 channel blocks starting at block n0 / 8 (4-D box is sized for Nc:
+          // the last chunk may be narrower, so it is loaded block by block when it is)
+          if (ncol == Nc) {
+            tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb + (n0 >> 3));
+          } else {
+            for (int q = 0; q < (ncol >> 3); ++q)
+              tma_load_4d(sx + p.x_bytes + q * p.g_slab_bytes, &maps.x[E2E_MAX_SRC - 1], full_bar(stage), w0 * 4, h0, d,
+                          b * p.grad_cb + (n0 >> 3) + q);
+          }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     } else if (warp == 1) {
-      {
-        // D=f32, A=B=bf16, A and B MN-major, N=Npad, M=128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                               ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
-        int stage = 0, phase = 0;
-        for (int it = 0; it < my_tiles; ++it) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t sx = smem_base + stage * p.stage_bytes;
-            const uint32_t sg = sx + p.x_bytes;
-            const uint64_t a0 = make_desc(sx, WG_ROWPITCH, p.x_slab_bytes);
-            const uint64_t b0 = make_desc(sg, 128, p.g_slab_bytes);
+      // D=f32, A=B=bf16, A and B MN-major, N=ncol, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(ncol >> 3) << 17) | (8u << 24);
+      int stage = 0, phase = 0;
+      const uint32_t krow_units = (uint32_t)(2 * p.x_rowpitch) >> 4;     // 16 voxels = 2 window rows
+      const uint32_t grp_units = (uint32_t)(16 * p.x_slab_bytes) >> 4;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sx = smem_base + stage * p.stage_bytes;
+          const uint32_t sg = sx + p.x_bytes;
+          const uint64_t a0 = make_desc(sx, p.x_rowpitch, p.x_slab_bytes);
+          const uint64_t b0 = make_desc(sg, 128, p.g_slab_bytes);
+          const uint32_t a_hi = (uint32_t)(a0 >> 32), b_hi = (uint32_t)(b0 >> 32);
+          const uint32_t a_lo0 = (uint32_t)a0, b_lo0 = (uint32_t)b0;
+          uint32_t acc = tmem_base;
+          for (int gi = 0; gi < ng; ++gi) {
             for (int tl = 0; tl < nt; ++tl) {
-              const uint64_t a_t = a0 + (uint64_t)(s_tapoff[t0 + tl] >> 4);
+              const uint32_t a_t = a_lo0 + (uint32_t)gi * grp_units + ((uint32_t)s_tapoff[t0 + tl] >> 4);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                // 16 voxels = tile rows 2k, 2k+1; start-address field is in units of 16 B
-                tc_mma_f16(tmem_base + tl * Npad, a_t + (uint64_t)(2 * k * (WG_ROWPITCH >> 4)), b0 + (uint64_t)(k * 16),
-                           idesc, (it | k) ? 1u : 0u);
-              }
+              for (int k = 0; k < 8; ++k)
+                tc_mma_f16_lh(acc, a_t + (uint32_t)k * krow_units, a_hi, b_lo0 + (uint32_t)(k * 16), b_hi, idesc,
+                              (it | k) ? 1u : 0u);
+              acc += (uint32_t)Nc;
             }
-            tc_commit(empty_bar(stage));
           }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          tc_commit(empty_bar(stage));
         }
-        if (elect_one_sync()) tc_commit(done_bar);
         __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
+      if (elect_one_sync()) tc_commit(done_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;             // accumulator row = (entry r/8, channel r%8)
       const int el = r >> 3, j = r & 7;
       mbar_wait(done_bar, 0);
       tc_fence_after();
-      const int e = e0 + el;
-      const bool valid = el < ne;
-      for (int tl = 0; tl < nt; ++tl) {
-        const int t = t0 + tl;
-        // dwp index of (entry e, tap t): slab = ((e/2)*9 + t)*2 + e%2
-        float* base = p.dwp + ((size_t)(((e >> 1) * 9 + t) * 2 + (e & 1)) * Npad) * 8 + j;
-        for (int c = 0; c < Npad; c += 16) {
-          uint32_t v[16];
-          tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + tl * Npad + c, v);
-          tc_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + tl * Npad + c + 8, v + 8);
-          tc_wait_ld();
-          if (valid) {
+      for (int gi = 0; gi < ng; ++gi) {
+        const int e = e0 + gi * 16 + el;
+        const bool valid = gi * 16 + el < ne;
+        for (int tl = 0; tl < nt; ++tl) {
+          const int t = t0 + tl;
+          // dwp index of (entry e, tap t): slab = ((e/2)*n_taps + t)*2 + e%2
+          float* base = p.dwp + ((size_t)(((e >> 1) * p.n_taps + t) * 2 + (e & 1)) * p.Npad + n0) * 8 + j;
+          const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((gi * nt + tl) * Nc);
+          for (int c = 0; c < ncol; c += 16) {
+            uint32_t v[16];
+            tc_ld16(acc + c, v);
+            tc_wait_ld();
+            if (valid) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
+              for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
+            }
           }
         }
       }
@@ -726,42 +764,72 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
 
 }  // namespace
 
+// 1: stride-1 3x3 halo form, 2: 1-tap point form, 0: not served
 int e2e_wgrad_tc_supported(const e2e_wgrad_t* p) {
-  if (p->n_taps != 9) return 0;
-  if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->ivh != 0 || p->ivw != 0) return 0;
-  if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
-  if (p->Npad > 256 || p->Npad % 16 != 0) return 0;
-  // two pipeline stages of (16 x-windows + Npad/8 gradient slabs) must fit in shared memory
-  const int x_slab = (18 * WG_ROWPITCH + 127) / 128 * 128;
-  if (2 * (16 * x_slab + (p->Npad / 8) * 2048) > SMEM_BUDGET) return 0;
-  return 1;
+  if (p->Npad % 16 != 0) return 0;
+  if (p->n_taps == 9) {
+    if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->ivh != 0 || p->ivw != 0) return 0;
+    if (p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
+    return 1;
+  }
+  if (p->n_taps == 1) {
+    if (p->isd < 1 || p->ish < 1 || p->isw < 1 || p->isd > 8 || p->ish > 8 || p->isw > 8) return 0;
+    return 2;
+  }
+  return 0;
 }
 
 int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
-  if (!e2e_wgrad_tc_supported(g)) {
-    e2e_set_error("wgrad_tc: call is not a stride-1 3x3 halo-form weight gradient with Npad <= 256");
+  const int form = e2e_wgrad_tc_supported(g);
+  if (!form) {
+    e2e_set_error("wgrad_tc: call is neither a stride-1 3x3 halo-form nor a 1-tap weight gradient");
     return E2E_ERR_UNSUPPORTED;
   }
+  const bool halo = form == 1;
   auto encode = get_encode_fn();
   if (!encode) {
     e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return E2E_ERR_CUDA;
   }
   WgParams p{};
-  p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
-  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  p.B = g->B; p.D = g->Do; p.H = g->Ho; p.W = g->Wo;
+  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd; p.ivh = g->ivh; p.ivw = g->ivw;
+  p.isd = g->isd; p.ish = g->ish; p.isw = g->isw;
+  p.n_taps = g->n_taps;
+  p.merged = (halo || g->isw == 1) ? 1 : 0;
   p.tiles_h = (p.H + TH - 1) / TH;
   p.tiles_w = (p.W + 7) / 8;
   p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
-  p.taps_per_group = 512 / g->Npad;
-  if (p.taps_per_group > 9) p.taps_per_group = 9;
-  p.n_tg = (9 + p.taps_per_group - 1) / p.taps_per_group;
-  p.taps_per_group = (9 + p.n_tg - 1) / p.n_tg;            // balance the groups
-  const int n_mg = (g->n_cent + 15) / 16;
-  p.x_slab_bytes = (18 * WG_ROWPITCH + 127) / 128 * 128;
+  // column chunks: balanced, <= 256 (halo: <= 96 when more than one accumulator tap has to share
+  // the 512 TMEM columns -- x windows are re-read per tap group, gradient tiles per entry group)
+  int maxc = 256;
+  if (halo && g->Npad > 96) maxc = (g->Npad % 96 == 0) ? 96 : ((g->Npad % 80 == 0) ? 160 : 128);
+  p.n_chunks = (g->Npad + maxc - 1) / maxc;
+  p.Nc = ((g->Npad / 16 + p.n_chunks - 1) / p.n_chunks) * 16;
+  p.n_chunks = (g->Npad + p.Nc - 1) / p.Nc;
+  const int n_groups = (g->n_cent + 15) / 16;
+  p.x_rowpitch = halo ? 10 * 16 : 8 * 16;
+  p.x_rows = halo ? 18 : 16;
+  p.x_slab_bytes = (p.x_rows * p.x_rowpitch + 127) / 128 * 128;
   p.g_slab_bytes = 128 * 16;
-  p.x_bytes = 16 * p.x_slab_bytes;
-  p.stage_bytes = (p.x_bytes + (g->Npad / 8) * p.g_slab_bytes + 127) / 128 * 128;
+  if (halo) {
+    p.G = 1;
+    p.taps_per_group = 512 / p.Nc;
+    if (p.taps_per_group > 9) p.taps_per_group = 9;
+    p.n_tg = (9 + p.taps_per_group - 1) / p.taps_per_group;
+    p.taps_per_group = (9 + p.n_tg - 1) / p.n_tg;            // balance the groups
+  } else {
+    p.taps_per_group = 1; p.n_tg = 1;
+    int G = 512 / p.Nc;
+    if (G > WG_MAX_ENT / 16) G = WG_MAX_ENT / 16;
+    if (G > n_groups) G = n_groups;
+    // two stages of (G * 16 windows + gradient tile) must fit
+    while (G > 1 && 2 * (G * 16 * p.x_slab_bytes + (p.Nc / 8) * p.g_slab_bytes) > SMEM_BUDGET) --G;
+    p.G = G;
+  }
+  p.n_mgj = (n_groups + p.G - 1) / p.G;
+  p.x_bytes = p.G * 16 * p.x_slab_bytes;
+  p.stage_bytes = (p.x_bytes + (p.Nc / 8) * p.g_slab_bytes + 127) / 128 * 128;
   int stages = SMEM_BUDGET / p.stage_bytes;
   if (stages > 4) stages = 4;
   if (stages < 2) {
@@ -769,7 +837,7 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
     return E2E_ERR_UNSUPPORTED;
   }
   p.stages = stages;
-  const int jobs = n_mg * p.n_tg;
+  const int jobs = p.n_mgj * p.n_tg * p.n_chunks;
   int splits = (e2e_num_sms() + jobs - 1) / jobs;
   if (splits > p.n_tiles) splits = p.n_tiles;
   if (splits < 1) splits = 1;
@@ -779,29 +847,48 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   p.cents = g->cents; p.taps = g->taps; p.dwp = g->dwp; p.grad_cb = g->grad_cb;
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
-  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+  const int n_xmaps = g->n_src < E2E_MAX_SRC - 1 ? E2E_MAX_SRC - 1 : E2E_MAX_SRC;
+  if (g->n_src > E2E_MAX_SRC - 1 && p.Npad % p.Nc != 0) {
+    e2e_set_error("wgrad_tc: ragged column chunks need a free tensor-map slot (n_src <= %d)", E2E_MAX_SRC - 1);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < n_xmaps; ++i) {
     const int si = i < g->n_src ? i : 0;
     p.src_cb[i] = g->src_cb[si];
-    cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->src_cb[si]};
-    cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
-    cuuint32_t box[4] = {40, 18, 1, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (p.merged) {
+      cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+      cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+      cuuint32_t box[4] = {(cuuint32_t)(halo ? 40 : 32), (cuuint32_t)(halo ? 18 : 16 * g->ish), 1, 1};
+      cuuint32_t estr[4] = {1, (cuuint32_t)(halo ? 1 : g->ish), 1, 1};
+      r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[5] = {8, (cuuint64_t)g->Wi, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+      cuuint64_t gstr[4] = {16, (cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16,
+                            (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+      cuuint32_t box[5] = {8, (cuuint32_t)(8 * g->isw), (cuuint32_t)(16 * g->ish), 1, 1};
+      cuuint32_t estr[5] = {1, (cuuint32_t)g->isw, (cuuint32_t)g->ish, 1, 1};
+      r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) {
       e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
       return E2E_ERR_CUDA;
     }
   }
-  {
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0: box of Nc / 8 channel blocks; pass 1: single-block box for a ragged last chunk
+    if (pass == 1 && p.Npad % p.Nc == 0) break;
     cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};
     cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
-    cuuint32_t box[4] = {32, 16, 1, (cuuint32_t)(g->Npad / 8)};
+    cuuint32_t box[4] = {32, 16, 1, (cuuint32_t)(pass == 0 ? p.Nc / 8 : 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&maps.g, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->grad), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = encode(pass == 0 ? &maps.g : &maps.x[E2E_MAX_SRC - 1], CU_TENSOR_MAP_DATA_TYPE_INT32, 4,
+                        const_cast<void*>(g->grad), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled failed with %d (grad)", (int)r);
       return E2E_ERR_CUDA;
@@ -810,10 +897,14 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   const int smem_bytes = p.stages * p.stage_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4 * 1024));
+    E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
+    E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
     attr_done = true;
   }
-  wgrad_tc_kernel<<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+  if (halo)
+    wgrad_tc_kernel<true><<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+  else
+    wgrad_tc_kernel<false><<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("wgrad_tc");
   return E2E_OK;
 }

@@ -224,9 +224,10 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dev = srcs[0].device
         Cb = plan.cout // 8
         impl = CONFIG["impl"]
-        wp = pack_weights(plan.fwd, weight, mask)
         raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
-        run_gemm(plan.fwd, wp, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], impl)
+        for chunk in plan.fwd_chunks:
+            run_gemm(chunk, pack_weights(chunk, weight, mask), srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                     [Cb], impl)
         V = Do * Ho * Wo
         nch = _nchunk(V, B * Cb)
         partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
@@ -273,7 +274,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         need = [ctx.needs_input_grad[7 + i] for i in range(len(srcs))]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(need):
-            outs = [torch.empty_like(s) for s in srcs]
+            outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.empty_like(s)) for s in srcs]
             for var in plan.dgrad:
                 it = plan.dgrad_iter_grid(var, D, H, W)
                 if min(it) <= 0:

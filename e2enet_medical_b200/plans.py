@@ -94,14 +94,24 @@ def _finish(cents, centoff, taps, tapoff, cols, rowoff, **kw) -> GemmPlan:
 # ----------------------------------------------------------------------------------------
 # depth-shifted (1,3,3) conv over a virtual concat of sources
 # ----------------------------------------------------------------------------------------
+def _col_chunks(n_blocks: int, max_blocks: int = 32) -> List[Tuple[int, int]]:
+    """balanced split of n_blocks 8-column blocks into chunks of <= max_blocks (even sizes: Npad % 16 == 0)"""
+    n_chunks = -(-n_blocks // max_blocks)
+    per = -(-n_blocks // n_chunks)
+    per += per % 2
+    return [(c0, min(n_blocks, c0 + per)) for c0 in range(0, n_blocks, per)]
+
+
 @dataclass
 class ShiftConvPlan:
     src_channels: List[int]
     cin: int
     cout: int
     stride: Tuple[int, int, int]
-    fwd: GemmPlan
-    dgrad: List[GemmPlan]        # variants; every element of every source gradient is written exactly once
+    fwd: GemmPlan                # all Cout columns: gather plan of the weight gradient (and of the forward if Cout <= 256)
+    fwd_chunks: List[GemmPlan]   # forward GEMMs: column chunks of <= 256
+    dgrad: List[GemmPlan]        # variants; every element of every source gradient is written at most once
+    dgrad_needs_zero: bool       # strided convs: the variants write only the voxels that receive a contribution
 
     def out_grid(self, D, H, W):
         sd, sh, sw = self.stride
@@ -117,11 +127,13 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
     src_channels = [int(c) for c in src_channels]
     cin = sum(src_channels)
     stride = tuple(int(s) for s in stride)
+    unit = stride == (1, 1, 1)
     assert cout % 8 == 0, "Cout must be a multiple of 8 (C8 layout)"
     sh_c = channel_shifts(cin) if shift else np.zeros(cin, np.int64)
     src_off = np.concatenate([[0], np.cumsum(src_channels)]).astype(int)
+    sd, shh, sww = stride
 
-    # ---- forward: K = (source block, shift) entries x 9 taps
+    # ---- K entries of the forward: (source block, shift)
     cents, centoff = [], []
     for i, ci in enumerate(src_channels):
         for blk in range((ci + 7) // 8):
@@ -129,98 +141,94 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
             for s in sorted({int(sh_c[c]) for c in chans if c >= 0}):
                 cents.append([i, blk, -s, 0, 0])                  # x~[d] = x[d - s]
                 centoff.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
-    _pad_even(cents, centoff)
-    taps = [[0, kh - 1, kw - 1] for kh in range(3) for kw in range(3)]
-    tapoff = [kh * 3 + kw for kh in range(3) for kw in range(3)]
     cols = [[0, q, 0xff, 0, 0, 0] for q in range(cout // 8)]
     rowoff = [n * cin * 9 for n in range(cout)]
-    fwd = _finish(cents, centoff, taps, tapoff, cols, rowoff, istride=stride, halo=(stride == (1, 1, 1)))
+    if unit:
+        # halo form: 9 taps over every entry (one haloed window serves all taps)
+        _pad_even(cents, centoff)
+        taps = [[0, kh - 1, kw - 1] for kh in range(3) for kw in range(3)]
+        tapoff = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+    else:
+        # point form: every (tap, entry) is its own K entry fetched at o*stride + (kh-1, kw-1); conv
+        # padding and the shift's zero fill are out-of-range reads
+        pc, po = [], []
+        for kh in range(3):
+            for kw in range(3):
+                for ce, co in zip(cents, centoff):
+                    pc.append([ce[0], ce[1], ce[2], kh - 1, kw - 1])
+                    po.append([v + kh * 3 + kw if v >= 0 else -1 for v in co])
+        cents, centoff = pc, po
+        _pad_even(cents, centoff)
+        taps, tapoff = [[0, 0, 0]], [0]
+    mk = lambda cc, rr: _finish([list(c) for c in cents], [list(c) for c in centoff], taps, tapoff, cc, rr,
+                                istride=stride, halo=unit)
+    fwd = mk(cols, rowoff)
+    chunks = _col_chunks(len(cols))
+    fwd_chunks = [fwd] if len(chunks) == 1 else [mk(cols[a:b], rowoff[8 * a:8 * b]) for a, b in chunks]
 
-    # ---- dgrad: source of the GEMM is d(raw) on the conv's output grid, K = Cout x taps
+    # ---- dgrad: source of the GEMM is d(raw) on the conv's output grid, K = Cout x taps.
+    # Columns = (source block, shift group); the columns of a group shifted by s are stored at depth
+    # o*sd + (smin_or_0 - s):  dx[c, d] = dx~[c, d + s_c], dx~ on depths that are multiples of sd.
     g_cents = [[0, e, 0, 0, 0] for e in range(cout // 8)]
     g_centoff = [[(e * 8 + j) * cin * 9 for j in range(8)] for e in range(cout // 8)]
-    _pad_even(g_cents, g_centoff)
-    sd, shh, sww = stride
-    variants: List[GemmPlan] = []
-    if stride == (1, 1, 1):
-        # One GEMM over the depth range of d(raw) that any shift group needs: iteration depth o reads
-        # d(raw) at depth o + smin and stores the columns of a group shifted by s at depth o + smin - s
-        # (dx[c, d] = dx~[c, d + s_c]); depths outside d(raw) read zeros, which also writes the zero
-        # slices of dx the shift leaves uncovered.  Columns are chunked to <= 256 per GEMM.
-        shifts = sorted({int(v) for v in sh_c})
-        smin, smax = shifts[0], shifts[-1]
-        ucols, urow = [], []
-        for i, ci in enumerate(src_channels):
-            for blk in range((ci + 7) // 8):
-                chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
-                for s in sorted({int(sh_c[c]) for c in chans if c >= 0}):
-                    m = 0
-                    for j, c in enumerate(chans):
-                        if c >= 0 and sh_c[c] == s:
-                            m |= 1 << j
-                    ucols.append([i, blk, m, smin - s, 0, 0])
-                    urow.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
-        taps_d = [[0, 1 - kh, 1 - kw] for kh in range(3) for kw in range(3)]
-        tapoff_d = [kh * 3 + kw for kh in range(3) for kw in range(3)]
-        n_chunks = -(-len(ucols) // 32)
-        per = -(-len(ucols) // n_chunks)
-        per += per % 2
-        for c0 in range(0, len(ucols), per):
-            cc, rr = ucols[c0:c0 + per], [v for r in urow[c0:c0 + per] for v in r]
-            variants.append(_finish([list(c) for c in g_cents], [list(c) for c in g_centoff], taps_d, tapoff_d,
-                                    cc, rr, istride=(1, 1, 1), ivoff=(smin, 0, 0), ostride=(1, 1, 1),
-                                    iter_extra=(smax - smin, 0, 0), halo=True))
-        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, variants)
-    for s in sorted({int(v) for v in sh_c}):
-        vcols, vrow = [], []
-        for i, ci in enumerate(src_channels):
-            for blk in range((ci + 7) // 8):
-                chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
+    shifts = sorted({int(v) for v in sh_c})
+    smin, smax = shifts[0], shifts[-1]
+    ucols, urow = [], []
+    for i, ci in enumerate(src_channels):
+        for blk in range((ci + 7) // 8):
+            chans = [src_off[i] + blk * 8 + j if blk * 8 + j < ci else -1 for j in range(8)]
+            for s in sorted({int(sh_c[c]) for c in chans if c >= 0}):
                 m = 0
                 for j, c in enumerate(chans):
                     if c >= 0 and sh_c[c] == s:
                         m |= 1 << j
-                if m:
-                    vcols.append((i, blk, m))
-                    vrow.extend([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
-        for pd in range(sd):
-            for ph in range(shh):
-                for pw in range(sww):
-                    # dx[c, d'] = dx~[c, d'+s];  dx~ lives on depths that are multiples of sd
-                    ok_d = (pd + s) % sd == 0
-                    vt, vto = [], []
-                    if ok_d:
-                        for kh in range(3):
-                            if (ph - kh + 1) % shh:
-                                continue
-                            for kw in range(3):
-                                if (pw - kw + 1) % sww:
-                                    continue
-                                vt.append([0, (ph - kh + 1) // shh, (pw - kw + 1) // sww])
-                                vto.append(kh * 3 + kw)
-                    live = bool(vt)
-                    if not live:
-                        vt, vto = [[0, 0, 0]], [0]
-                    cols_v = [[i, blk, m, pd, ph, pw] for (i, blk, m) in vcols]
-                    row_v = list(vrow) if live else [-1] * len(vrow)
-                    variants.append(_finish([list(c) for c in g_cents], [list(c) for c in g_centoff], vt, vto, cols_v,
-                                            row_v, istride=(1, 1, 1),
-                                            ivoff=((pd + s) // sd if ok_d else 0, 0, 0), ostride=stride,
-                                            iter_off=(pd, ph, pw)))
-    return ShiftConvPlan(src_channels, cin, cout, stride, fwd, variants)
+                ucols.append((i, blk, m, s))
+                urow.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
+    variants: List[GemmPlan] = []
+    if unit:
+        # One halo-form GEMM over the depth range of d(raw) that any shift group needs: iteration
+        # depth o reads d(raw) at depth o + smin; depths outside d(raw) read zeros, which also writes
+        # the zero slices of dx the shift leaves uncovered.
+        gc, go = [list(c) for c in g_cents], [list(c) for c in g_centoff]
+        _pad_even(gc, go)
+        taps_d = [[0, 1 - kh, 1 - kw] for kh in range(3) for kw in range(3)]
+        tapoff_d = [kh * 3 + kw for kh in range(3) for kw in range(3)]
+        for a, b in _col_chunks(len(ucols)):
+            cc = [[i, blk, m, smin - s, 0, 0] for (i, blk, m, s) in ucols[a:b]]
+            rr = [v for r in urow[a:b] for v in r]
+            variants.append(_finish([list(c) for c in gc], [list(c) for c in go], taps_d, tapoff_d, cc, rr,
+                                    istride=(1, 1, 1), ivoff=(smin, 0, 0), ostride=(1, 1, 1),
+                                    iter_extra=(smax - smin, 0, 0), halo=True))
+        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, variants, False)
+    # strided: one point-form GEMM per (H, W) output parity; its K entries are the taps that reach
+    # that parity, each fetched from d(raw) at o + (p - k + 1) / stride.  dx is zeroed by the caller
+    # (depths / voxels that no tap reaches stay zero).
+    for ph in range(shh):
+        for pw in range(sww):
+            vc, vo = [], []
+            for kh in range(3):
+                if (ph - kh + 1) % shh:
+                    continue
+                for kw in range(3):
+                    if (pw - kw + 1) % sww:
+                        continue
+                    for ce, co in zip(g_cents, g_centoff):
+                        vc.append([0, ce[1], 0, (ph - kh + 1) // shh, (pw - kw + 1) // sww])
+                        vo.append([v + kh * 3 + kw for v in co])
+            if not vc:
+                continue
+            _pad_even(vc, vo)
+            for a, b in _col_chunks(len(ucols)):
+                cc = [[i, blk, m, -s, ph, pw] for (i, blk, m, s) in ucols[a:b]]
+                rr = [v for r in urow[a:b] for v in r]
+                variants.append(_finish([list(c) for c in vc], [list(c) for c in vo], [[0, 0, 0]], [0], cc, rr,
+                                        istride=(1, 1, 1), ivoff=(0, 0, 0), ostride=stride, iter_off=(0, ph, pw)))
+    return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, variants, True)
 
 
 # ----------------------------------------------------------------------------------------
 # ConvTranspose3d with kernel == stride (the up* modules), weight (Cin, Cout, kd, kh, kw)
 # ----------------------------------------------------------------------------------------
-def _col_chunks(n_blocks: int, max_blocks: int = 32) -> List[Tuple[int, int]]:
-    """balanced split of n_blocks 8-column blocks into chunks of <= max_blocks (even sizes: Npad % 16 == 0)"""
-    n_chunks = -(-n_blocks // max_blocks)
-    per = -(-n_blocks // n_chunks)
-    per += per % 2
-    return [(c0, min(n_blocks, c0 + per)) for c0 in range(0, n_blocks, per)]
-
-
 @dataclass
 class TConvPlan:
     cin: int

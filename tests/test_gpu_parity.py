@@ -327,8 +327,11 @@ def _bf(x):
     ([8], 8, (2, 2, 2), (5, 5, 3)),
     ([320, 320, 192], 320, (1, 1, 1), (4, 5, 5)),
     ([320, 320, 320], 320, (1, 1, 1), (2, 3, 3)),
+    ([192], 320, (2, 2, 2), (4, 10, 12)),       # ctx3.0-style: Cout 320 -> two column chunks, 252 point entries
+    ([96], 192, (2, 2, 2), (6, 21, 19)),        # odd sizes under stride
 ])
-def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial):
+@pytest.mark.parametrize("impl", [0, 1])
+def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial, impl):
     """conv fwd / wgrad / dgrad and InstanceNorm+LeakyReLU fwd/bwd, each against torch fp32 math on the
     same bf16-rounded operands: only accumulation order and the final bf16 rounding may differ."""
     import torch.nn.functional as F
@@ -345,8 +348,9 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial):
     w = _bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
     xs8 = [ops.nc_to_c8(x) for x in xs]
     raw = torch.empty((B, cout // 8, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
-    ops.run_gemm(plan.fwd, ops.pack_weights(plan.fwd, w, None), xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
-                 [cout // 8], 0)
+    for ch in plan.fwd_chunks:
+        ops.run_gemm(ch, ops.pack_weights(ch, w, None), xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                     [cout // 8], impl)
     xc = torch.cat(xs, 1).clone().requires_grad_(True)
     wc = w.clone().requires_grad_(True)
     ref_raw = F.conv3d(onet.shift_depth(xc), wc, None, stride=stride, padding=(0, 1, 1))
@@ -354,16 +358,16 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial):
     g = _bf(torch.from_numpy(rs.standard_normal((B, cout, Do, Ho, Wo)).astype(np.float32))).to(dev)
     (ref_raw * g).sum().backward()
     g8 = ops.nc_to_c8(g)
-    gw = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (Do, Ho, Wo), B, g8, tuple(w.shape), 0)
+    gw = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (Do, Ho, Wo), B, g8, tuple(w.shape), impl)
     assert rel(gw, wc.grad) < 2e-4                                   # fp32 out; fp32 atomics order only
-    outs = [torch.full_like(s, float("nan")) for s in xs8]
+    outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.full_like(s, float("nan"))) for s in xs8]
     sd, sh, sw = stride
     for var in plan.dgrad:
         it = plan.dgrad_iter_grid(var, D, H, W)
         if min(it) <= 0:
             continue
         ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W),
-                     [s.shape[1] for s in xs8], 0)
+                     [s.shape[1] for s in xs8], impl)
     off = 0
     for o, c in zip(outs, src):
         got = ops.c8_to_nc(o, c)

@@ -71,7 +71,8 @@ def test_shiftconv_plans_reproduce_oracle(src, cout, stride, spatial):
     ref = F.conv3d(onet.shift_depth(torch.cat(tx, 1)), tw, None, stride=stride, padding=(0, 1, 1))
     assert tuple(ref.shape[2:]) == (Do, Ho, Wo)
     raw = np.zeros((B, cout // 8, Do, Ho, Wo, 8))
-    pi.gemm(plan.fwd, pi.pack(plan.fwd, w), [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo))
+    for ch in plan.fwd_chunks:
+        pi.gemm(ch, pi.pack(ch, w), [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo))
     np.testing.assert_allclose(pi.from_c8(raw, cout), ref.detach().numpy(), atol=1e-9)
     # backward
     gy = rs.standard_normal(tuple(ref.shape))
@@ -79,7 +80,8 @@ def test_shiftconv_plans_reproduce_oracle(src, cout, stride, spatial):
     g8 = pi.to_c8(gy)
     gw = pi.wgrad(plan.fwd, [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, g8, w.shape)
     np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
-    outs = [np.full(pi.to_c8(a).shape, np.nan) for a in xs]
+    # strided convs: the variants write only voxels that receive a contribution; the caller zeroes dx
+    outs = [np.full(pi.to_c8(a).shape, 0.0 if plan.dgrad_needs_zero else np.nan) for a in xs]
     sd, sh, sw = stride
     for var in plan.dgrad:
         it = plan.dgrad_iter_grid(var, D, H, W)
@@ -163,9 +165,13 @@ def test_real_layer_plans_are_consistent():
         cin = sum(src)
         f = plan.fwd
         co = f.centoff[f.centoff >= 0]
-        assert sorted(co.tolist()) == [c * 9 for c in range(cin)], (src, cout)
+        # halo form: one entry per channel (x 9 taps in the kernel); point form: one entry per (tap, channel)
+        want = [c * 9 for c in range(cin)] if f.n_taps == 9 else list(range(cin * 9))
+        assert sorted(co.tolist()) == want, (src, cout)
+        assert all(ch.Npad <= 256 for ch in plan.fwd_chunks) and sum(
+            int((ch.rowoff >= 0).sum()) for ch in plan.fwd_chunks) == cout
         assert f.n_cent % 2 == 0 and f.Npad % 16 == 0
-        nvar = stride[0] * stride[1] * stride[2]
+        nvar = stride[1] * stride[2] if plan.dgrad_needs_zero else 1
         seen = {}
         for var in plan.dgrad:
             par = tuple(int(v) for v in var.iter_off)

@@ -74,13 +74,17 @@ def main():
         raw = torch.randn((B, cout // 8, Do, Ho, Wo, 8), device=dev).bfloat16()
         dxs = [torch.empty_like(x) for x in xs8]
         flops = 2.0 * B * Do * Ho * Wo * cout * cin * 9
-        wp = ops.pack_weights(plan.fwd, w, None)
+        wpf = [ops.pack_weights(c, w, None) for c in plan.fwd_chunks]
         wpd = [ops.pack_weights(v, w, None) for v in plan.dgrad]
 
         def fwd():
-            ops.run_gemm(plan.fwd, wp, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [cout // 8], impl)
+            for c, wc in zip(plan.fwd_chunks, wpf):
+                ops.run_gemm(c, wc, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [cout // 8], impl)
 
         def dgrad():
+            if plan.dgrad_needs_zero:
+                for t in dxs:
+                    t.zero_()
             for v, wv in zip(plan.dgrad, wpd):
                 it = plan.dgrad_iter_grid(v, D, H, W)
                 if min(it) > 0:
