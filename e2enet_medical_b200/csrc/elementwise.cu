@@ -7,6 +7,7 @@
 namespace {
 
 constexpr int EW_THREADS = 256;
+constexpr int UNR = 4;            // independent 16-byte vectors in flight per thread and operand
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
@@ -84,13 +85,23 @@ __global__ void __launch_bounds__(EW_THREADS) in_stats_partial_kernel(const uint
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
-    float f[8];
-    unpack8(ld_nc_16(base + v), f);
+  // UNR independent 16-byte loads in flight per thread (the loop is latency-bound otherwise)
+  for (long long v0 = lo + threadIdx.x; v0 < hi; v0 += UNR * EW_THREADS) {
+    uint4 r[UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] += f[j];
-      acc[8 + j] += f[j] * f[j];
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      r[u] = v < hi ? ld_nc_16(base + v) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float f[8];
+      unpack8(r[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += f[j];
+        acc[8 + j] += f[j] * f[j];
+      }
     }
   }
   block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
@@ -133,15 +144,26 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_kernel(const uint4* __res
   const long long lo = chunk * per, hi = min(V, lo + per);
   const uint4* ib = raw + (long long)plane * V;
   uint4* ob = out + (long long)plane * V;
-  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
-    float f[8];
-    unpack8(ld_nc_16(ib + v), f);
+  for (long long v0 = lo + threadIdx.x; v0 < hi; v0 += UNR * EW_THREADS) {
+    uint4 r[UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float z = f[j] * sc[j] + sh[j];
-      f[j] = z > 0.f ? z : z * slope;
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      if (v < hi) r[u] = ld_nc_16(ib + v);
     }
-    ob[v] = pack8(f);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      if (v >= hi) break;
+      float f[8];
+      unpack8(r[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = f[j] * sc[j] + sh[j];
+        f[j] = z > 0.f ? z : z * slope;
+      }
+      ob[v] = pack8(f);
+    }
   }
 }
 
@@ -167,17 +189,27 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_reduce_kernel(const uint4* 
   float acc[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
-    float x[8], g[8];
-    unpack8(ld_nc_16(xb + v), x);
-    unpack8(ld_nc_16(gb + v), g);
+  for (long long v0 = lo + threadIdx.x; v0 < hi; v0 += UNR * EW_THREADS) {
+    uint4 xr[UNR], gr[UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (x[j] - mu[j]) * rs[j];
-      const float z = xh * ga[j] + be[j];
-      const float dz = z > 0.f ? g[j] : g[j] * slope;
-      acc[j] += dz;
-      acc[8 + j] += dz * xh;
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      if (v < hi) { xr[u] = ld_nc_16(xb + v); gr[u] = ld_nc_16(gb + v); }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (v0 + u * EW_THREADS >= hi) break;
+      float x[8], g[8];
+      unpack8(xr[u], x);
+      unpack8(gr[u], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mu[j]) * rs[j];
+        const float z = xh * ga[j] + be[j];
+        const float dz = z > 0.f ? g[j] : g[j] * slope;
+        acc[j] += dz;
+        acc[8 + j] += dz * xh;
+      }
     }
   }
   block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
@@ -221,23 +253,34 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_apply_kernel(const uint4* _
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (long long v = lo + threadIdx.x; v < hi; v += EW_THREADS) {
-    float x[8], g[8], o[8];
-    unpack8(ld_nc_16(xb + v), x);
-    unpack8(ld_nc_16(gb + v), g);
+  for (long long v0 = lo + threadIdx.x; v0 < hi; v0 += UNR * EW_THREADS) {
+    uint4 xr[UNR], gr[UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (x[j] - mu[j]) * rs[j];
-      const float z = xh * ga[j] + be[j];
-      const float dz = z > 0.f ? g[j] : g[j] * slope;
-      o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      if (v < hi) { xr[u] = ld_nc_16(xb + v); gr[u] = ld_nc_16(gb + v); }
     }
-    const uint4 pk = pack8(o);
-    ob[v] = pk;
-    float ro[8];
-    unpack8(pk, ro);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+    for (int u = 0; u < UNR; ++u) {
+      const long long v = v0 + u * EW_THREADS;
+      if (v >= hi) break;
+      float x[8], g[8], o[8];
+      unpack8(xr[u], x);
+      unpack8(gr[u], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mu[j]) * rs[j];
+        const float z = xh * ga[j] + be[j];
+        const float dz = z > 0.f ? g[j] : g[j] * slope;
+        o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+      }
+      const uint4 pk = pack8(o);
+      ob[v] = pk;
+      float ro[8];
+      unpack8(pk, ro);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+    }
   }
   block_reduce_store<8>(acc, partial2 + ((long long)plane * nchunk + chunk) * 8);
 }
@@ -298,35 +341,43 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const uint4* __
   }
 }
 
+// one thread per POOLED voxel: reads dy + argmax once, writes the whole kd x kh x kw window of dx
+// (zeros except at the arg-max position); trailing voxels of dx that no window covers are zeroed
+// by the threads of the last window along each axis
 __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ amax,
                                                                  uint4* __restrict__ dx, int BCb, int D, int H, int W,
                                                                  int kd, int kh, int kw) {
   const int Do = D / kd, Ho = H / kh, Wo = W / kw;
-  const long long total = (long long)BCb * D * H * W;
+  const long long total = (long long)BCb * Do * Ho * Wo;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i % W);
-    long long t = i / W;
-    const int h = (int)(t % H);
-    t /= H;
-    const int d = (int)(t % D);
-    const long long plane = t / D;
-    const int od = d / kd, oh = h / kh, ow = w / kw;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (od < Do && oh < Ho && ow < Wo) {
-      const int widx = ((d - od * kd) * kh + (h - oh * kh)) * kw + (w - ow * kw);
-      const long long oi = ((plane * Do + od) * Ho + oh) * (long long)Wo + ow;
-      const uint2 am = amax[oi];
-      float g[8], r[8];
-      unpack8(dy[oi], g);
+    const int ow = (int)(i % Wo);
+    long long t = i / Wo;
+    const int oh = (int)(t % Ho);
+    t /= Ho;
+    const int od = (int)(t % Do);
+    const long long plane = t / Do;
+    const uint2 am = amax[i];
+    const uint4 gv = ld_nc_16(dy + i);
+    const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    // extents of this thread's window (the last window along an axis also covers the remainder)
+    const int d1 = (od == Do - 1) ? D : (od + 1) * kd;
+    const int h1 = (oh == Ho - 1) ? H : (oh + 1) * kh;
+    const int w1 = (ow == Wo - 1) ? W : (ow + 1) * kw;
+    for (int d = od * kd; d < d1; ++d)
+      for (int h = oh * kh; h < h1; ++h)
+        for (int w = ow * kw; w < w1; ++w) {
+          const int a = d - od * kd, b = h - oh * kh, c = w - ow * kw;
+          const uint32_t widx = (a < kd && b < kh && c < kw) ? (uint32_t)((a * kh + b) * kw + c) : 0xffffu;
+          uint32_t o[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t a = ((j < 4 ? am.x : am.y) >> ((j & 3) * 8)) & 0xffu;
-        r[j] = (a == (uint32_t)widx) ? g[j] : 0.f;
-      }
-      o = pack8(r);
-    }
-    dx[i] = o;
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t a0 = ((q < 2 ? am.x : am.y) >> ((2 * q & 3) * 8)) & 0xffu;
+            const uint32_t a1 = ((q < 2 ? am.x : am.y) >> (((2 * q + 1) & 3) * 8)) & 0xffu;
+            o[q] = (a0 == widx ? (gw[q] & 0xffffu) : 0u) | (a1 == widx ? (gw[q] & 0xffff0000u) : 0u);
+          }
+          dx[((plane * D + d) * H + h) * (long long)W + w] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
   }
 }
 
@@ -433,7 +484,7 @@ extern "C" int e2e_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t 
 extern "C" int e2e_maxpool_bwd(const void* dy, const uint8_t* argmax, void* dx, int32_t BCb, int32_t D, int32_t H,
                                int32_t W, int32_t kd, int32_t kh, int32_t kw, void* stream) {
   E2E_ARG(dy && argmax && dx, "maxpool_bwd: null pointer");
-  const long long total = (long long)BCb * D * H * W;
+  const long long total = (long long)BCb * (D / kd) * (H / kh) * (W / kw);
   if (total <= 0) return E2E_OK;
   maxpool_bwd_kernel<<<ew_blocks(total), EW_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)argmax,
                                                                                 (uint4*)dx, BCb, D, H, W, kd, kh, kw);

@@ -194,7 +194,7 @@ def test_tconv_pool_seghead_vs_torch(dev):
         (y * gy.to(dev)).sum().backward()
         assert rel(y, yr) < TOL and rel(dx.grad, tx.grad) < TOL and rel(dw.grad, tw.grad) < TOL
     # max pool
-    for k, sp in (((1, 2, 2), (3, 6, 8)), ((2, 2, 2), (4, 6, 6))):
+    for k, sp in (((1, 2, 2), (3, 6, 8)), ((2, 2, 2), (4, 6, 6)), ((2, 2, 2), (5, 7, 6)), ((1, 1, 1), (2, 3, 5))):
         x = torch.from_numpy(rs.standard_normal((2, 16) + sp).astype(np.float32)).bfloat16().float()
         tx = x.clone().requires_grad_(True)
         yr = torch.nn.functional.max_pool3d(tx, k)
