@@ -82,6 +82,7 @@ SIGNATURES = {
     "e2e_version": (C.c_int, []),
     "e2e_launch_count": (C.c_longlong, []),
     "e2e_gather_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
+    "e2e_gather_gemm_multi": (C.c_int, [C.POINTER(GemmParams), _I32, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
     "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),

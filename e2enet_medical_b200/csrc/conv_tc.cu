@@ -34,7 +34,8 @@ namespace {
 constexpr int TC_THREADS = 192;
 constexpr int TH = 16;                 // tile rows (H)
 constexpr int MAX_CENT = 384;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int TC_MAX_CHUNKS = 12;
+constexpr int SMEM_BUDGET = 196 * 1024;    // dynamic pipeline stages; static tables take up to ~15 KB more
 
 struct TcParams {
   int B, D, H, W;        // iteration grid (D, H, W); sources have Dsrc slices, destinations (Ddst, Hd, Wd)
@@ -52,8 +53,12 @@ struct TcParams {
   int src_cb[E2E_MAX_SRC];
   const e2e_centry_t* cents;
   const e2e_tap_t* taps;
-  const bf16* wpacked;
-  const e2e_colblk_t* cols;
+  // column chunks of one GEMM batched into one launch: work item = (tile, chunk); chunks differ in
+  // packed weights, column table and width only (Npad above is the widest: it fixes the geometry)
+  int n_chunks;
+  const bf16* wpacked[TC_MAX_CHUNKS];
+  const e2e_colblk_t* cols[TC_MAX_CHUNKS];
+  int npad[TC_MAX_CHUNKS];
   void* dst[E2E_MAX_SRC];
   int dst_cb[E2E_MAX_SRC];
 };
@@ -195,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_s;
   __shared__ e2e_centry_t s_cents[MAX_CENT];
-  __shared__ ColInfo s_cols[32];
+  __shared__ ColInfo s_cols[TC_MAX_CHUNKS * 32];
   __shared__ int s_tapoff[9];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -209,8 +214,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
 
   for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS2) s_cents[i] = p.cents[i];
-  if (threadIdx.x < (Npad >> 3)) {
-    const e2e_colblk_t c = p.cols[threadIdx.x];
+  for (int i = threadIdx.x; i < p.n_chunks * 32; i += TC_THREADS2) {
+    const int ch = i >> 5, q = i & 31;
+    if (q >= (p.npad[ch] >> 3)) continue;
+    const e2e_colblk_t c = p.cols[ch][q];
     ColInfo ci;
     const int dst = (c.dst >= 0 && c.chmask != 0) ? c.dst : -1;
     const int plane = p.Ddst * p.Hd * p.Wd;
@@ -219,7 +226,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     ci.od = (int16_t)c.od; ci.oh = (int16_t)c.oh; ci.ow = (int16_t)c.ow;
     ci.off = dst >= 0 ? c.blk * plane + (c.od * p.Hd + c.oh) * p.Wd + c.ow : 0;
     ci.bstride = dst >= 0 ? p.dst_cb[dst] * plane : 0;
-    s_cols[threadIdx.x] = ci;
+    s_cols[i] = ci;
   }
   if (threadIdx.x < 9) {
     int off = 0;
@@ -249,9 +256,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     // ================================================= TMA producer
     if (lane == 0) {
       int stage = 0, phase = 0;
-      const uint32_t tx = 2u * (uint32_t)p.rows * (uint32_t)rowpitch + (uint32_t)p.b_stage_bytes;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        int t = tile;
+      const uint32_t txa = 2u * (uint32_t)p.rows * (uint32_t)rowpitch;
+      const int nwork = p.n_tiles * p.n_chunks;
+      for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+        int t = work / p.n_chunks;
+        const int ch = work - t * p.n_chunks;
+        const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
+        const bf16* wsrc = p.wpacked[ch];
         const int wt = t % p.tiles_w; t /= p.tiles_w;
         const int ht = t % p.tiles_h; t /= p.tiles_h;
         const int d = t % p.D;
@@ -259,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         const int h0 = ht * TH, w0 = wt * 8 * MS;
         for (int pr = 0; pr < npairs; ++pr) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), tx);
+          mbar_expect_tx(full_bar(stage), txa + bbytes);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
@@ -274,30 +285,31 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
               tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
                           h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
           }
-          bulk_copy_g2s(sa + p.a_stage_bytes, p.wpacked + (size_t)pr * (p.b_stage_bytes / 2), p.b_stage_bytes,
-                        full_bar(stage));
+          bulk_copy_g2s(sa + p.a_stage_bytes, wsrc + (size_t)pr * (bbytes / 2), bbytes, full_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer (warp-uniform loop, one elected lane issues)
-    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=Npad, M=128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
     int stage = 0, phase = 0, as = 0, aphase = 0;
     // descriptors differ only in the 14-bit start-address field (units of 16 B) of the low word
     const uint64_t adesc = make_desc(0, p.a_slab_bytes, rowpitch);
-    const uint64_t bdesc = make_desc(0, Npad * 16, 128);
     const uint32_t a_hi = (uint32_t)(adesc >> 32), a_lo0 = (uint32_t)adesc;
-    const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
-    const uint32_t b_tap_units = (uint32_t)(2 * Npad * 16) >> 4;
     uint32_t tapu[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) tapu[t] = (uint32_t)s_tapoff[t] >> 4;
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     const uint32_t a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
     const uint32_t sa0 = smem_base >> 4;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int nwork = p.n_tiles * p.n_chunks;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      const int npc = p.npad[work % p.n_chunks];           // width of this column chunk
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=npc, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npc >> 3) << 17) | (8u << 24);
+      const uint64_t bdesc = make_desc(0, npc * 16, 128);
+      const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
+      const uint32_t b_tap_units = (uint32_t)(2 * npc * 16) >> 4;
       mbar_wait(tempty_bar(as), aphase ^ 1);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + (uint32_t)(as * MS * Npad);
@@ -330,11 +342,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;                  // accumulator row = voxel (r / 8, r % 8) of a sub-tile
-    const int nchunk = (Npad + 31) >> 5;
     const bool need_bounds = p.need_bounds != 0;
     int as = 0, aphase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      int t = tile;
+    const int nwork = p.n_tiles * p.n_chunks;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      int t = work / p.n_chunks;
+      const int ch = work - t * p.n_chunks;
+      const int npc = p.npad[ch];
+      const int nchunk = (npc + 31) >> 5;
+      const ColInfo* ccols = s_cols + ch * 32;
       const int wt = t % p.tiles_w; t /= p.tiles_w;
       const int ht = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
@@ -351,14 +367,14 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         const bool inb = (h < p.H) && (w < p.W);
         const int tv = (ds * p.Hd + hs) * p.Wd + ws;
         uint32_t v[32];
-        const bool two = c0 + 16 < Npad;
+        const bool two = c0 + 16 < npc;
         tc_ld16(acc0 + j * Npad + c0, v);
         if (two) tc_ld16(acc0 + j * Npad + c0 + 16, v + 16);
         tc_wait_ld();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (u >= 2 && !two) break;
-          const ColInfo col = s_cols[(c0 >> 3) + u];
+          const ColInfo col = ccols[(c0 >> 3) + u];
           if (!inb || col.dst < 0) continue;
           if (need_bounds) {
             const int dd = ds + col.od, hh = hs + col.oh, ww = ws + col.ow;
@@ -452,8 +468,17 @@ int e2e_conv_tc_supported(const e2e_gemm_t* p) {
   return 0;
 }
 
-int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
-  const int form = e2e_conv_tc_supported(g);
+// gs[0..n): column chunks of ONE GEMM (same sources, grids, channel entries, taps and destinations;
+// different packed weights / column tables / widths), executed by one launch
+int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
+  const e2e_gemm_t* g = gs;
+  int form = e2e_conv_tc_supported(g);
+  if (n < 1 || n > TC_MAX_CHUNKS) form = 0;
+  int npmax = 0;
+  for (int i = 0; i < n && form; ++i) {
+    if (e2e_conv_tc_supported(gs + i) != form) form = 0;
+    if (gs[i].Npad > npmax) npmax = gs[i].Npad;
+  }
   if (!form) {
     e2e_set_error("conv_tc_fwd: call is neither a stride-1 3x3 halo-form nor a 1-tap GEMM with Npad <= 256");
     return E2E_ERR_UNSUPPORTED;
@@ -471,14 +496,20 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   p.Dsrc = g->Di; p.Ddst = g->Dd; p.Hd = g->Hd; p.Wd = g->Wd;
   p.isd = g->isd; p.ish = g->ish; p.isw = g->isw; p.ivh = g->ivh; p.ivw = g->ivw;
   p.osd = g->osd; p.osh = g->osh; p.osw = g->osw;
-  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  p.n_cent = g->n_cent; p.Npad = npmax; p.ivd = g->ivd;
+  p.n_chunks = n;
+  for (int i = 0; i < n; ++i) {
+    p.wpacked[i] = reinterpret_cast<const bf16*>(gs[i].wpacked);
+    p.cols[i] = gs[i].cols;
+    p.npad[i] = gs[i].Npad;
+  }
   const int n_taps = halo ? 9 : 1;
-  int m = 256 / g->Npad;
+  int m = 256 / npmax;
   if (m > 4) m = 4;
   if (m < 1) m = 1;
   while (m > 1 && 8 * (m - 1) >= g->Wo) --m;          // do not tile wider than the row
   p.m = m;
-  p.acc_stages = (2 * m * g->Npad <= 512) ? 2 : 1;
+  p.acc_stages = (2 * m * npmax <= 512) ? 2 : 1;
   p.rows = halo ? 18 : 16;
   // halo-form forward stores in place (no offsets); everything else checks the destination bounds
   p.merged = (halo || g->isw == 1) ? 1 : 0;
@@ -486,7 +517,7 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   const int rowpitch = (8 * m + (halo ? 2 : 0)) * 16;
   p.a_slab_bytes = (p.rows * rowpitch + 127) / 128 * 128;
   p.a_stage_bytes = 2 * p.a_slab_bytes;
-  p.b_stage_bytes = n_taps * 2 * g->Npad * 16;
+  p.b_stage_bytes = n_taps * 2 * npmax * 16;
   p.stage_bytes = (p.a_stage_bytes + p.b_stage_bytes + 127) / 128 * 128;
   int stages = SMEM_BUDGET / p.stage_bytes;
   if (stages > 8) stages = 8;
@@ -498,8 +529,7 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   p.tiles_h = (p.H + TH - 1) / TH;
   p.tiles_w = (p.W + 8 * m - 1) / (8 * m);
   p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
-  p.cents = g->cents; p.taps = g->taps; p.cols = g->cols;
-  p.wpacked = reinterpret_cast<const bf16*>(g->wpacked);
+  p.cents = g->cents; p.taps = g->taps;
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
@@ -542,12 +572,16 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* g, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 4; ++b)
-        E2E_CUDA(cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 10 * 1024));
+      for (int b = 0; b < 4; ++b) {
+        cudaFuncAttributes fa;
+        E2E_CUDA(cudaFuncGetAttributes(&fa, kerns[a][b]));
+        E2E_CUDA(cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024 - (int)fa.sharedSizeBytes));
+      }
     attr_done = true;
   }
   int grid = e2e_num_sms();
-  if (grid > p.n_tiles) grid = p.n_tiles;
+  if (grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
   kerns[halo ? 1 : 0][m - 1]<<<grid, TC_THREADS2, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;

@@ -449,12 +449,35 @@ int launch_wgrad(const e2e_wgrad_t* p, cudaStream_t st) {
 
 }  // namespace
 
-int e2e_conv_tc_fwd(const e2e_gemm_t* p, cudaStream_t st);   // conv_tc.cu
+int e2e_conv_tc_fwd(const e2e_gemm_t* p, int n, cudaStream_t st);   // conv_tc.cu
 int e2e_conv_tc_supported(const e2e_gemm_t* p);
 int e2e_wgrad_tc(const e2e_wgrad_t* p, cudaStream_t st);
 int e2e_wgrad_tc_supported(const e2e_wgrad_t* p);
 
-extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) {
+static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc);
+
+extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) { return gather_gemm_one(p, stream, true); }
+
+// n column chunks of one GEMM (identical except wpacked / cols / Npad): one launch on the tcgen05
+// path, n launches otherwise
+extern "C" int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* stream) {
+  E2E_ARG(p != nullptr && n >= 1, "gather_gemm_multi: bad arguments");
+  if (n == 1) return gather_gemm_one(p, stream, true);
+  bool tc = p[0].impl == 1 && n <= 12;
+  for (int i = 0; i < n && tc; ++i) tc = p[i].impl == 1 && e2e_conv_tc_supported(p + i) == e2e_conv_tc_supported(p);
+  if (tc && e2e_conv_tc_supported(p)) {
+    const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
+    if (M <= 0) return E2E_OK;
+    return e2e_conv_tc_fwd(p, n, reinterpret_cast<cudaStream_t>(stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    const int rc = gather_gemm_one(p + i, stream, true);
+    if (rc != E2E_OK) return rc;
+  }
+  return E2E_OK;
+}
+
+static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   E2E_ARG(p != nullptr, "gather_gemm: null params");
   E2E_ARG(p->n_cent > 0 && (p->n_cent & 1) == 0, "gather_gemm: n_cent must be even and > 0 (got %d)", p->n_cent);
   E2E_ARG(p->n_taps > 0, "gather_gemm: n_taps must be > 0");
@@ -464,7 +487,7 @@ extern "C" int e2e_gather_gemm(const e2e_gemm_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
-  if (p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, st);
+  if (allow_tc && p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, 1, st);
   const int N = p->Npad;
   if (N % 128 == 0) return launch_gemm<8>(p, st);
   if (N % 96 == 0) return launch_gemm<6>(p, st);

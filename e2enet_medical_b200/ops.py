@@ -95,8 +95,30 @@ def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tens
 def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int,
              dsts: Sequence[torch.Tensor], dst_grid, dst_cb: Sequence[int], impl: int = 0):
     lib = _lib.load()
+    p = _fill_gemm(_lib.GemmParams(), plan, wpacked, srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl)
+    with _Timed("gemm", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
+        _lib.check(lib.e2e_gather_gemm(C.byref(p), _lib.stream_ptr()), "gather_gemm")
+
+
+def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optional[torch.Tensor],
+                    srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, dsts: Sequence[torch.Tensor], dst_grid,
+                    dst_cb: Sequence[int], impl: int = 0):
+    """the column chunks of one GEMM (plans differ in columns / packed weights only): one launch."""
+    lib = _lib.load()
+    if len(plans) == 1:
+        return run_gemm(plans[0], pack_weights(plans[0], weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid,
+                        dst_cb, impl)
+    arr = (_lib.GemmParams * len(plans))()
+    flops = 0.0
+    for i, pl in enumerate(plans):
+        _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl)
+        flops += _plan_flops(pl, B * iter_grid[0] * iter_grid[1] * iter_grid[2])
+    with _Timed("gemm", flops):
+        _lib.check(lib.e2e_gather_gemm_multi(arr, len(plans), _lib.stream_ptr()), "gather_gemm_multi")
+
+
+def _fill_gemm(p, plan: GemmPlan, wpacked: torch.Tensor, srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl):
     dev = plan.dev(srcs[0].device)
-    p = _lib.GemmParams()
     p.B = B
     p.Di, p.Hi, p.Wi = src_grid
     p.Do, p.Ho, p.Wo = iter_grid
@@ -121,8 +143,7 @@ def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor]
         p.dst_cb[i] = dst_cb[i]
     p.out_mode = plan.out_mode
     p.impl = impl
-    with _Timed("gemm", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
-        _lib.check(lib.e2e_gather_gemm(C.byref(p), _lib.stream_ptr()), "gather_gemm")
+    return p
 
 
 def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, grad: torch.Tensor,
@@ -225,9 +246,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         Cb = plan.cout // 8
         impl = CONFIG["impl"]
         raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
-        for chunk in plan.fwd_chunks:
-            run_gemm(chunk, pack_weights(chunk, weight, mask), srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
-                     [Cb], impl)
+        run_gemm_chunks(plan.fwd_chunks, weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], impl)
         V = Do * Ho * Wo
         nch = _nchunk(V, B * Cb)
         partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
@@ -275,12 +294,12 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(need):
             outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.empty_like(s)) for s in srcs]
-            for var in plan.dgrad:
-                it = plan.dgrad_iter_grid(var, D, H, W)
+            for group in plan.dgrad_groups:          # column chunks of one GEMM go out as one launch
+                it = plan.dgrad_iter_grid(group[0], D, H, W)
                 if min(it) <= 0:
                     continue
-                wpd = pack_weights(var, weight, ctx.mask)
-                run_gemm(var, wpd, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W), [s.shape[1] for s in srcs], impl)
+                run_gemm_chunks(group, weight, ctx.mask, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W),
+                                [s.shape[1] for s in srcs], impl)
             dsrcs = [o if n else None for o, n in zip(outs, need)]
         return (None, None, gw, dbias.to(weight.dtype) if ctx.needs_input_grad[3] else None,
                 dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, *dsrcs)
@@ -296,9 +315,8 @@ class TConv(torch.autograd.Function):
         kd, kh, kw = plan.k
         impl = CONFIG["impl"]
         y = torch.empty((B, plan.cout // 8, D * kd, H * kh, W * kw, 8), dtype=torch.bfloat16, device=x.device)
-        for chunk in plan.fwd:
-            run_gemm(chunk, pack_weights(chunk, weight, mask), [x], (D, H, W), (D, H, W), B, [y],
-                     (D * kd, H * kh, W * kw), [plan.cout // 8], impl)
+        run_gemm_chunks(plan.fwd, weight, mask, [x], (D, H, W), (D, H, W), B, [y], (D * kd, H * kh, W * kw),
+                        [plan.cout // 8], impl)
         ctx.plan, ctx.mask = plan, mask
         ctx.save_for_backward(weight, x)
         return y
@@ -317,9 +335,7 @@ class TConv(torch.autograd.Function):
             gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl)
         if ctx.needs_input_grad[3]:
             dx = torch.empty_like(x)
-            for chunk in plan.dgrad:
-                run_gemm(chunk, pack_weights(chunk, weight, ctx.mask), [dy], fine, (D, H, W), B, [dx], (D, H, W),
-                         [Cb], impl)
+            run_gemm_chunks(plan.dgrad, weight, ctx.mask, [dy], fine, (D, H, W), B, [dx], (D, H, W), [Cb], impl)
         return None, gw, None, dx
 
 

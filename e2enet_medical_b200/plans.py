@@ -117,6 +117,14 @@ class ShiftConvPlan:
         sd, sh, sw = self.stride
         return (D - 1) // sd + 1, (H + 2 - 3) // sh + 1, (W + 2 - 3) // sw + 1
 
+    @property
+    def dgrad_groups(self) -> List[List[GemmPlan]]:
+        """variants grouped into GEMMs: the column chunks of one GEMM share the output parity"""
+        groups: Dict[Tuple[int, int, int], List[GemmPlan]] = {}
+        for v in self.dgrad:
+            groups.setdefault(tuple(v.iter_off), []).append(v)
+        return list(groups.values())
+
     def dgrad_iter_grid(self, var: GemmPlan, D, H, W):
         """iteration grid of data-gradient variant `var` for a source grid (D, H, W)."""
         return tuple((n - o + s - 1) // s + e

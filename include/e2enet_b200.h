@@ -88,6 +88,9 @@ typedef struct {
 } e2e_gemm_t;
 
 int e2e_gather_gemm(const e2e_gemm_t* p, void* stream);
+/* p[0..n): column chunks of one GEMM -- identical except wpacked / cols / Npad (a result wider than
+ * 256 columns is split by the host plan); one kernel launch on the tcgen05 path */
+int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* stream);
 
 /*
  * dwp[e/2][t][e%2][n][j] += sum_o grad[b, n/8, o, n%8] * src[...][(o*is + iv + cent[e].off + tap[t].off), j]

@@ -348,9 +348,7 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial, impl):
     w = _bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
     xs8 = [ops.nc_to_c8(x) for x in xs]
     raw = torch.empty((B, cout // 8, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
-    for ch in plan.fwd_chunks:
-        ops.run_gemm(ch, ops.pack_weights(ch, w, None), xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
-                     [cout // 8], impl)
+    ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [cout // 8], impl)
     xc = torch.cat(xs, 1).clone().requires_grad_(True)
     wc = w.clone().requires_grad_(True)
     ref_raw = F.conv3d(onet.shift_depth(xc), wc, None, stride=stride, padding=(0, 1, 1))
@@ -362,12 +360,11 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial, impl):
     assert rel(gw, wc.grad) < 2e-4                                   # fp32 out; fp32 atomics order only
     outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.full_like(s, float("nan"))) for s in xs8]
     sd, sh, sw = stride
-    for var in plan.dgrad:
-        it = plan.dgrad_iter_grid(var, D, H, W)
+    for group in plan.dgrad_groups:
+        it = plan.dgrad_iter_grid(group[0], D, H, W)
         if min(it) <= 0:
             continue
-        ops.run_gemm(var, ops.pack_weights(var, w, None), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W),
-                     [s.shape[1] for s in xs8], impl)
+        ops.run_gemm_chunks(group, w, None, [g8], (Do, Ho, Wo), it, B, outs, (D, H, W), [s.shape[1] for s in xs8], impl)
     off = 0
     for o, c in zip(outs, src):
         got = ops.c8_to_nc(o, c)

@@ -104,11 +104,9 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
     res = {}
     for impl in (0, 1):
         y = torch.full((B, cout // 8) + fine + (8,), float("nan"), dtype=torch.bfloat16, device=dev)
-        for ch in plan.fwd:
-            ops.run_gemm(ch, ops.pack_weights(ch, w, None), [x8], spatial, spatial, B, [y], fine, [cout // 8], impl)
+        ops.run_gemm_chunks(plan.fwd, w, None, [x8], spatial, spatial, B, [y], fine, [cout // 8], impl)   # one launch
         dx = torch.full_like(x8, float("nan"))
-        for ch in plan.dgrad:
-            ops.run_gemm(ch, ops.pack_weights(ch, w, None), [g8], fine, spatial, B, [dx], spatial, [cin // 8], impl)
+        ops.run_gemm_chunks(plan.dgrad, w, None, [g8], fine, spatial, B, [dx], spatial, [cin // 8], impl)
         gw = ops.run_wgrad(plan.wgrad, [g8], fine, spatial, B, x8, tuple(w.shape), impl)
         torch.cuda.synchronize()
         res[impl] = (ops.c8_to_nc(y, cout), ops.c8_to_nc(dx, cin), gw)

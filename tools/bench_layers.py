@@ -78,17 +78,18 @@ def main():
         wpd = [ops.pack_weights(v, w, None) for v in plan.dgrad]
 
         def fwd():
-            for c, wc in zip(plan.fwd_chunks, wpf):
-                ops.run_gemm(c, wc, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [cout // 8], impl)
+            ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                                [cout // 8], impl)
 
         def dgrad():
             if plan.dgrad_needs_zero:
                 for t in dxs:
                     t.zero_()
-            for v, wv in zip(plan.dgrad, wpd):
-                it = plan.dgrad_iter_grid(v, D, H, W)
+            for grp in plan.dgrad_groups:
+                it = plan.dgrad_iter_grid(grp[0], D, H, W)
                 if min(it) > 0:
-                    ops.run_gemm(v, wv, [raw], (Do, Ho, Wo), it, B, dxs, (D, H, W), [x.shape[1] for x in xs8], impl)
+                    ops.run_gemm_chunks(grp, w, None, [raw], (Do, Ho, Wo), it, B, dxs, (D, H, W),
+                                        [x.shape[1] for x in xs8], impl)
 
         def wgrad():
             ops.run_wgrad(plan.fwd, xs8, (D, H, W), (Do, Ho, Wo), B, raw, tuple(w.shape), impl)
@@ -116,12 +117,10 @@ def main():
         wpd = [ops.pack_weights(c, w, None) for c in plan.dgrad]
 
         def fwd():
-            for c, wc in zip(plan.fwd, wpf):
-                ops.run_gemm(c, wc, [x8], (D, H, W), (D, H, W), B, [y8], fine, [cout // 8], impl)
+            ops.run_gemm_chunks(plan.fwd, w, None, [x8], (D, H, W), (D, H, W), B, [y8], fine, [cout // 8], impl)
 
         def dgrad():
-            for c, wc in zip(plan.dgrad, wpd):
-                ops.run_gemm(c, wc, [y8], fine, (D, H, W), B, [dx8], (D, H, W), [cin // 8], impl)
+            ops.run_gemm_chunks(plan.dgrad, w, None, [y8], fine, (D, H, W), B, [dx8], (D, H, W), [cin // 8], impl)
 
         def wgrad():
             ops.run_wgrad(plan.wgrad, [y8], fine, (D, H, W), B, x8, tuple(w.shape), impl)
