@@ -75,6 +75,12 @@ class WgradParams(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("mask", C.c_void_p), ("rowoff", C.c_void_p), ("centoff", C.c_void_p),
+                ("tapoff", C.c_void_p), ("n_cent", C.c_int32), ("n_taps", C.c_int32), ("Npad", C.c_int32),
+                ("pad_", C.c_int32), ("out", C.c_void_p), ("item_begin", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/e2enet_b200.h
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -85,6 +91,7 @@ SIGNATURES = {
     "e2e_gather_gemm_multi": (C.c_int, [C.POINTER(GemmParams), _I32, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
     "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_pack_weights_multi": (C.c_int, [_VP, _I32, _I64, _VP]),
     "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_nc_to_c8": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),
     "e2e_c8_to_nc": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),

@@ -382,6 +382,45 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
   }
 }
 
+// all packed operands of a network in one launch: job j owns items [item_begin[j], item_begin[j+1])
+__global__ void pack_weights_multi_kernel(const e2e_pack_job_t* __restrict__ jobs, int n_jobs, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_jobs - 1;                 // last job with item_begin <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].item_begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const e2e_pack_job_t jb = jobs[lo];
+    const long long li = i - jb.item_begin;
+    const int n = (int)(li % jb.Npad);
+    const long long sl = li / jb.Npad;             // slab = ks*2 + half
+    const int hf = (int)(sl & 1);
+    const int ks = (int)(sl >> 1);
+    const int pr = ks / jb.n_taps, t = ks - pr * jb.n_taps;
+    const int e = 2 * pr + hf;
+    const int ro = jb.rowoff[n], to = jb.tapoff[t];
+    uint32_t o[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int co = jb.centoff[e * 8 + jj * 2 + u];
+        float x = 0.f;
+        if (ro >= 0 && co >= 0) {
+          const int idx = ro + co + to;
+          x = jb.w[idx];
+          if (jb.mask) x *= jb.mask[idx];
+        }
+        v[u] = x;
+      }
+      o[jj] = pack_bf16x2(v[0], v[1]);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(jb.out) + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int32_t* __restrict__ rowoff,
                                     const int32_t* __restrict__ centoff, const int32_t* __restrict__ tapoff,
                                     int n_cent, int n_taps, int Npad, float* __restrict__ grad) {
@@ -526,6 +565,16 @@ extern "C" int e2e_pack_weights(const float* w, const float* mask, const int32_t
   pack_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       w, mask, rowoff, centoff, tapoff, n_cent, n_taps, Npad, reinterpret_cast<bf16*>(wpacked));
   E2E_LAUNCHED("pack_weights");
+  return E2E_OK;
+}
+
+extern "C" int e2e_pack_weights_multi(const e2e_pack_job_t* jobs, int32_t n_jobs, int64_t total_items, void* stream) {
+  E2E_ARG(jobs && n_jobs > 0 && total_items >= 0, "pack_weights_multi: bad arguments");
+  if (total_items == 0) return E2E_OK;
+  long long blocks = (total_items + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_weights_multi_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs, n_jobs, total_items);
+  E2E_LAUNCHED("pack_weights_multi");
   return E2E_OK;
 }
 

@@ -73,22 +73,82 @@ def bump_weight_epoch():
     _WEIGHT_EPOCH[0] += 1
 
 
+class _PackEntry(object):
+    """one (plan, weight, mask) -> persistent packed bf16 operand"""
+    __slots__ = ("tables", "plan", "wref", "mask", "out", "key", "dead")
+
+    def current_key(self, w):
+        m = self.mask
+        return (w.data_ptr(), w._version, None if m is None else (m.data_ptr(), m._version), _WEIGHT_EPOCH[0])
+
+
+_PACK_REG = {}          # device -> {"entries": [...], "sig": tuple, "table": device tensor, "total": int}
+
+
+def _pack_key(weight, mask):
+    return (weight.data_ptr(), weight._version, None if mask is None else (mask.data_ptr(), mask._version),
+            _WEIGHT_EPOCH[0])
+
+
+def _repack_all(device):
+    """after an optimizer / Masking step every packed operand is stale: repack all of them in ONE launch"""
+    import weakref  # noqa: F401
+    reg = _PACK_REG[str(device)]
+    live = []
+    for e in reg["entries"]:
+        w = e.wref()
+        if w is not None and not e.dead:
+            live.append((e, w))
+    reg["entries"] = [e for e, _ in live]
+    if not live:
+        return
+    sig = tuple((w.data_ptr(), 0 if e.mask is None else e.mask.data_ptr(), e.out.data_ptr()) for e, w in live)
+    if reg.get("sig") != sig:
+        arr = (_lib.PackJob * len(live))()
+        total = 0
+        for i, (e, w) in enumerate(live):
+            j = arr[i]
+            j.w, j.mask = w.data_ptr(), (0 if e.mask is None else e.mask.data_ptr())
+            j.rowoff, j.centoff, j.tapoff = (e.tables[k].data_ptr() for k in ("rowoff", "centoff", "tapoff"))
+            j.n_cent, j.n_taps, j.Npad = e.plan.n_cent, e.plan.n_taps, e.plan.Npad
+            j.out, j.item_begin = e.out.data_ptr(), total
+            total += e.plan.n_cent * e.plan.n_taps * e.plan.Npad
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        reg["table"], reg["sig"], reg["total"] = host.to(device), sig, total
+    _lib.check(_lib.load().e2e_pack_weights_multi(_p(reg["table"]), len(live), reg["total"], _lib.stream_ptr()),
+               "pack_weights_multi")
+    for e, w in live:
+        e.key = e.current_key(w)
+
+
 def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """bf16 packed operand of `plan` for the current value of weight * mask.  Cached until the weight or
+    its mask changes; when it does, every registered operand of the device is repacked by one kernel."""
+    import weakref
     lib = _lib.load()
     dev = plan.dev(weight.device)
-    key = (weight.data_ptr(), weight._version, None if mask is None else (mask.data_ptr(), mask._version),
-           _WEIGHT_EPOCH[0], torch.is_grad_enabled() and weight.requires_grad)
-    hit = dev.get("_wp")
-    if hit is not None and hit[0] == key:
-        return hit[1]
-    out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
+    key = _pack_key(weight, mask)
+    e = dev.get("_wpe")
+    w0 = e.wref() if e is not None else None
+    same = w0 is weight or (w0 is not None and w0.data_ptr() == weight.data_ptr() and w0.shape == weight.shape)
+    if e is not None and same and e.mask is mask and not e.dead:
+        if e.key != key:
+            _repack_all(weight.device)
+        return e.out
+    # first use of this (plan, weight): allocate the persistent operand, pack it alone, register it
+    if e is not None:
+        e.dead = True
     w = weight.detach()
     assert w.dtype == torch.float32 and w.is_contiguous()
     if mask is not None:
         assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == w.shape
+    out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
     _lib.check(lib.e2e_pack_weights(_p(w), _p(mask), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]),
                                     plan.n_cent, plan.n_taps, plan.Npad, _p(out), _lib.stream_ptr()), "pack_weights")
-    dev["_wp"] = (key, out)
+    e = _PackEntry()
+    e.tables, e.plan, e.wref, e.mask, e.out, e.key, e.dead = dev, plan, weakref.ref(weight), mask, out, key, False
+    dev["_wpe"] = e
+    _PACK_REG.setdefault(str(weight.device), {"entries": []})["entries"].append(e)
     return out
 
 

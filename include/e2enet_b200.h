@@ -124,6 +124,19 @@ int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream);
 int e2e_pack_weights(const float* w, const float* mask, const int32_t* rowoff, const int32_t* centoff,
                      const int32_t* tapoff, int32_t n_cent, int32_t n_taps, int32_t Npad,
                      void* wpacked, void* stream);
+/* the same for many (plan, weight) pairs in one launch: jobs is a DEVICE array; job j packs items
+ * [item_begin, item_begin + n_cent*n_taps*Npad) (one item = 8 bf16 = 16 bytes of `out`) */
+typedef struct {
+  const float* w;
+  const float* mask;              /* may be null */
+  const int32_t* rowoff;
+  const int32_t* centoff;
+  const int32_t* tapoff;
+  int32_t n_cent, n_taps, Npad, pad_;
+  void* out;
+  int64_t item_begin;
+} e2e_pack_job_t;
+int e2e_pack_weights_multi(const e2e_pack_job_t* jobs, int32_t n_jobs, int64_t total_items, void* stream);
 /* grad[rowoff[n] + centoff[e*8+j] + tapoff[t]] = dwp[...]  (inverse scatter; every weight appears once) */
 int e2e_unpack_wgrad(const float* dwp, const int32_t* rowoff, const int32_t* centoff, const int32_t* tapoff,
                      int32_t n_cent, int32_t n_taps, int32_t Npad, float* grad, void* stream);
