@@ -51,6 +51,7 @@ class GemmParams(C.Structure):
         ("dst_cb", C.c_int32 * E2E_MAX_SRC),
         ("out_mode", C.c_int32),
         ("impl", C.c_int32),
+        ("col_bounds", C.c_int32),
     ]
 
 

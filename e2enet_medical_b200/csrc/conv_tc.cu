@@ -45,6 +45,8 @@ struct TcParams {
   int rows;                        // window rows per slab: 18 (halo) or 16 (point)
   int need_bounds;                 // destination offsets / strides can leave the destination grid
   int merged;                      // source maps are 4-D with the merged (W, channel) inner dimension
+  int b_res;                       // packed weights of the CTA's (fixed) column chunk stay resident in smem
+  int b_region_bytes;              // size of that region (then the A stages follow)
   int n_cent, Npad, m, stages, acc_stages;
   int ivd;
   int tiles_h, tiles_w, n_tiles;
@@ -189,7 +191,7 @@ struct ColInfo {            // one 8-column block of the result, decoded once pe
   uint8_t chmask;
 };
 
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;            // 4 per TMEM lane quadrant: the epilogue is instruction-bound
 constexpr int TC_THREADS2 = 64 + 32 * EPI_WARPS;
 
 template <bool HALO, int MS>      // MS: 8-voxel-wide sub-tiles (accumulators) per tile
@@ -212,6 +214,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   auto empty_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
   auto tfull_bar = [&](int a) { return smem_u32(&bars[16 + a]); };
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
+  const uint32_t bfull_bar = smem_u32(&bars[24]);
 
   for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS2) s_cents[i] = p.cents[i];
   for (int i = threadIdx.x; i < p.n_chunks * 32; i += TC_THREADS2) {
@@ -239,6 +242,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    mbar_init(bfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -258,6 +262,15 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       int stage = 0, phase = 0;
       const uint32_t txa = 2u * (uint32_t)p.rows * (uint32_t)rowpitch;
       const int nwork = p.n_tiles * p.n_chunks;
+      if (p.b_res && (int)blockIdx.x < nwork) {
+        // resident mode: gridDim.x is a multiple of n_chunks, so this CTA only ever sees one chunk;
+        // its whole packed operand [pair][tap][2][npad][8] is fetched once
+        const int ch = blockIdx.x % p.n_chunks;
+        const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
+        mbar_expect_tx(bfull_bar, bbytes * (uint32_t)npairs);
+        for (int pr = 0; pr < npairs; ++pr)
+          bulk_copy_g2s(smem_base + pr * bbytes, p.wpacked[ch] + (size_t)pr * (bbytes / 2), bbytes, bfull_bar);
+      }
       for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
         int t = work / p.n_chunks;
         const int ch = work - t * p.n_chunks;
@@ -270,8 +283,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         const int h0 = ht * TH, w0 = wt * 8 * MS;
         for (int pr = 0; pr < npairs; ++pr) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), txa + bbytes);
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          mbar_expect_tx(full_bar(stage), p.b_res ? txa : txa + bbytes);
+          const uint32_t sa = smem_base + p.b_region_bytes + stage * p.stage_bytes;
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const e2e_centry_t ce = s_cents[2 * pr + hf];
@@ -285,7 +298,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
               tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
                           h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
           }
-          bulk_copy_g2s(sa + p.a_stage_bytes, wsrc + (size_t)pr * (bbytes / 2), bbytes, full_bar(stage));
+          if (!p.b_res)
+            bulk_copy_g2s(sa + p.a_stage_bytes, wsrc + (size_t)pr * (bbytes / 2), bbytes, full_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -301,8 +315,13 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     for (int t = 0; t < NT; ++t) tapu[t] = (uint32_t)s_tapoff[t] >> 4;
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     const uint32_t a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
-    const uint32_t sa0 = smem_base >> 4;
+    const uint32_t sa0 = (smem_base + (uint32_t)p.b_region_bytes) >> 4;
+    const uint32_t sb0 = smem_base >> 4;
     const int nwork = p.n_tiles * p.n_chunks;
+    if (p.b_res && (int)blockIdx.x < nwork) {
+      mbar_wait(bfull_bar, 0);
+      tc_fence_after();
+    }
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
       const int npc = p.npad[work % p.n_chunks];           // width of this column chunk
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=npc, M=128
@@ -318,7 +337,8 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units;
-          const uint32_t b_lo = b_lo0 + sa0 + (uint32_t)stage * stage_units + a_stage_units;
+          const uint32_t b_lo = p.b_res ? b_lo0 + sb0 + (uint32_t)pr * (uint32_t)(NT * 2) * (uint32_t)npc
+                                        : b_lo0 + sa0 + (uint32_t)stage * stage_units + a_stage_units;
           const uint32_t first = pr ? 1u : 0u;
 #pragma unroll
           for (int t = 0; t < NT; ++t) {
@@ -337,12 +357,12 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       if (++as == AS) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ================================================= epilogue: 8 warps, 2 per TMEM lane quadrant;
-    // the two warps of a quadrant take alternate 32-column chunks
+    // ================================================= epilogue: EPI_WARPS / 4 warps per TMEM lane
+    // quadrant; the warps of a quadrant take the 32-column chunks round-robin
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;                  // accumulator row = voxel (r / 8, r % 8) of a sub-tile
-    const bool need_bounds = p.need_bounds != 0;
+    const int need_bounds = p.need_bounds;      // bit 0: depth, 1: H, 2: W may leave the destination grid
     int as = 0, aphase = 0;
     const int nwork = p.n_tiles * p.n_chunks;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
@@ -360,7 +380,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MS * Npad);
-      for (int ci = grp; ci < MS * nchunk; ci += 2) {
+      for (int ci = grp; ci < MS * nchunk; ci += EPI_WARPS / 4) {
         const int j = ci / nchunk, c0 = (ci - j * nchunk) << 5;
         const int w = (wt * MS + j) * 8 + (r & 7);
         const int ws = w * p.osw;
@@ -377,9 +397,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
           const ColInfo col = ccols[(c0 >> 3) + u];
           if (!inb || col.dst < 0) continue;
           if (need_bounds) {
-            const int dd = ds + col.od, hh = hs + col.oh, ww = ws + col.ow;
-            if ((unsigned)dd >= (unsigned)p.Ddst || (unsigned)hh >= (unsigned)p.Hd || (unsigned)ww >= (unsigned)p.Wd)
-              continue;
+            if ((need_bounds & 1) && (unsigned)(ds + col.od) >= (unsigned)p.Ddst) continue;
+            if ((need_bounds & 2) && (unsigned)(hs + col.oh) >= (unsigned)p.Hd) continue;
+            if ((need_bounds & 4) && (unsigned)(ws + col.ow) >= (unsigned)p.Wd) continue;
           }
           bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
           const uint32_t* vv = v + u * 8;
@@ -511,15 +531,27 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
   p.m = m;
   p.acc_stages = (2 * m * npmax <= 512) ? 2 : 1;
   p.rows = halo ? 18 : 16;
-  // halo-form forward stores in place (no offsets); everything else checks the destination bounds
   p.merged = (halo || g->isw == 1) ? 1 : 0;
-  p.need_bounds = !(halo && g->Do == g->Dd && g->ivd == 0) || g->osd != 1 || g->osh != 1 || g->osw != 1;
+  p.need_bounds = g->col_bounds & 7;
   const int rowpitch = (8 * m + (halo ? 2 : 0)) * 16;
   p.a_slab_bytes = (p.rows * rowpitch + 127) / 128 * 128;
   p.a_stage_bytes = 2 * p.a_slab_bytes;
   p.b_stage_bytes = n_taps * 2 * npmax * 16;
   p.stage_bytes = (p.a_stage_bytes + p.b_stage_bytes + 127) / 128 * 128;
-  int stages = SMEM_BUDGET / p.stage_bytes;
+  int grid = e2e_num_sms();
+  // resident weights: the whole packed operand of a chunk (all K pairs) fits beside >= 3 A stages
+  const int npairs = g->n_cent / 2;
+  p.b_res = 0; p.b_region_bytes = 0;
+  {
+    const int region = (npairs * p.b_stage_bytes + 1023) / 1024 * 1024;
+    const int gres = (grid / n) * n;
+    static int allow = -1;
+    if (allow < 0) { const char* e = getenv("E2E_TC_BRES"); allow = e ? atoi(e) : 1; }
+    if (allow && region <= 112 * 1024 && gres >= n && region + 3 * p.a_stage_bytes <= SMEM_BUDGET) {
+      p.b_res = 1; p.b_region_bytes = region; p.stage_bytes = p.a_stage_bytes; grid = gres;
+    }
+  }
+  int stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) {
     e2e_set_error("conv_tc_fwd: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
@@ -564,7 +596,7 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     p.dst[i] = i < g->n_dst ? g->dst[i] : nullptr;
     p.dst_cb[i] = i < g->n_dst ? g->dst_cb[i] : 0;
   }
-  const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + 1024;
   typedef void (*kern_t)(const TcParams, const TcMaps);
   static const kern_t kerns[2][4] = {
       {conv_tc_kernel<false, 1>, conv_tc_kernel<false, 2>, conv_tc_kernel<false, 3>, conv_tc_kernel<false, 4>},
@@ -580,8 +612,7 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
       }
     attr_done = true;
   }
-  int grid = e2e_num_sms();
-  if (grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
+  if (!p.b_res && grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
   kerns[halo ? 1 : 0][m - 1]<<<grid, TC_THREADS2, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
@@ -872,7 +903,7 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   }
   p.stages = stages;
   const int jobs = p.n_mgj * p.n_tg * p.n_chunks;
-  int splits = (e2e_num_sms() + jobs - 1) / jobs;
+  int splits = e2e_num_sms() / jobs;            // one wave: jobs * splits <= SMs (one CTA per SM)
   if (splits > p.n_tiles) splits = p.n_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.n_tiles + splits - 1) / splits;

@@ -203,6 +203,7 @@ def _fill_gemm(p, plan: GemmPlan, wpacked: torch.Tensor, srcs, src_grid, iter_gr
         p.dst_cb[i] = dst_cb[i]
     p.out_mode = plan.out_mode
     p.impl = impl
+    p.col_bounds = plan.col_bounds
     return p
 
 
@@ -348,7 +349,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         # weight gradient (dense, also at masked positions: SURVEY H3)
         gw = None
         if ctx.needs_input_grad[2]:
-            gw = run_wgrad(plan.fwd, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl)
+            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl)
         # data gradients of every source
         need = [ctx.needs_input_grad[7 + i] for i in range(len(srcs))]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)

@@ -48,6 +48,7 @@ class GemmPlan:
     iter_off: Tuple[int, int, int] = (0, 0, 0)
     iter_extra: Tuple[int, int, int] = (0, 0, 0)
     halo: bool = False          # stride-1 3x3 halo form (tcgen05 kernel eligible)
+    col_bounds: int = 7         # bit 0/1/2: destination depth / row / column of a column block may leave the grid
     _dev: Dict = field(default_factory=dict, repr=False)
 
     @property
@@ -108,8 +109,9 @@ class ShiftConvPlan:
     cin: int
     cout: int
     stride: Tuple[int, int, int]
-    fwd: GemmPlan                # all Cout columns: gather plan of the weight gradient (and of the forward if Cout <= 256)
+    fwd: GemmPlan                # all Cout columns
     fwd_chunks: List[GemmPlan]   # forward GEMMs: column chunks of <= 256
+    wgrad: GemmPlan              # gather plan of the weight gradient (fwd, or its point form for tiny Cin)
     dgrad: List[GemmPlan]        # variants; every element of every source gradient is written at most once
     dgrad_needs_zero: bool       # strided convs: the variants write only the voxels that receive a contribution
 
@@ -151,6 +153,18 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
                 centoff.append([c * 9 if (c >= 0 and sh_c[c] == s) else -1 for c in chans])
     cols = [[0, q, 0xff, 0, 0, 0] for q in range(cout // 8)]
     rowoff = [n * cin * 9 for n in range(cout)]
+    base_cents, base_centoff = [list(c) for c in cents], [list(c) for c in centoff]
+
+    def point_form():
+        pc, po = [], []
+        for kh in range(3):
+            for kw in range(3):
+                for ce, co in zip(base_cents, base_centoff):
+                    pc.append([ce[0], ce[1], ce[2], kh - 1, kw - 1])
+                    po.append([v + kh * 3 + kw if v >= 0 else -1 for v in co])
+        _pad_even(pc, po)
+        return pc, po
+
     if unit:
         # halo form: 9 taps over every entry (one haloed window serves all taps)
         _pad_even(cents, centoff)
@@ -159,18 +173,17 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
     else:
         # point form: every (tap, entry) is its own K entry fetched at o*stride + (kh-1, kw-1); conv
         # padding and the shift's zero fill are out-of-range reads
-        pc, po = [], []
-        for kh in range(3):
-            for kw in range(3):
-                for ce, co in zip(cents, centoff):
-                    pc.append([ce[0], ce[1], ce[2], kh - 1, kw - 1])
-                    po.append([v + kh * 3 + kw if v >= 0 else -1 for v in co])
-        cents, centoff = pc, po
-        _pad_even(cents, centoff)
+        cents, centoff = point_form()
         taps, tapoff = [[0, 0, 0]], [0]
     mk = lambda cc, rr: _finish([list(c) for c in cents], [list(c) for c in centoff], taps, tapoff, cc, rr,
-                                istride=stride, halo=unit)
+                                istride=stride, halo=unit, col_bounds=0)
     fwd = mk(cols, rowoff)
+    wgrad = fwd
+    if unit and 9 * len(base_cents) <= 16:
+        # tiny Cin (the network input): the 9 taps of the few entries fill ONE 16-entry group of the
+        # weight-gradient kernel as point entries instead of 9 mostly empty tap accumulators
+        pc, po = point_form()
+        wgrad = _finish(pc, po, [[0, 0, 0]], [0], cols, rowoff, istride=stride)
     chunks = _col_chunks(len(cols))
     fwd_chunks = [fwd] if len(chunks) == 1 else [mk(cols[a:b], rowoff[8 * a:8 * b]) for a, b in chunks]
 
@@ -206,8 +219,8 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
             rr = [v for r in urow[a:b] for v in r]
             variants.append(_finish([list(c) for c in gc], [list(c) for c in go], taps_d, tapoff_d, cc, rr,
                                     istride=(1, 1, 1), ivoff=(smin, 0, 0), ostride=(1, 1, 1),
-                                    iter_extra=(smax - smin, 0, 0), halo=True))
-        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, variants, False)
+                                    iter_extra=(smax - smin, 0, 0), halo=True, col_bounds=1))
+        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, wgrad, variants, False)
     # strided: one point-form GEMM per (H, W) output parity; its K entries are the taps that reach
     # that parity, each fetched from d(raw) at o + (p - k + 1) / stride.  dx is zeroed by the caller
     # (depths / voxels that no tap reaches stay zero).
@@ -230,8 +243,9 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
                 cc = [[i, blk, m, -s, ph, pw] for (i, blk, m, s) in ucols[a:b]]
                 rr = [v for r in urow[a:b] for v in r]
                 variants.append(_finish([list(c) for c in vc], [list(c) for c in vo], [[0, 0, 0]], [0], cc, rr,
-                                        istride=(1, 1, 1), ivoff=(0, 0, 0), ostride=stride, iter_off=(0, ph, pw)))
-    return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, variants, True)
+                                        istride=(1, 1, 1), ivoff=(0, 0, 0), ostride=stride, iter_off=(0, ph, pw),
+                                        col_bounds=1))
+    return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, wgrad, variants, True)
 
 
 # ----------------------------------------------------------------------------------------
@@ -257,13 +271,18 @@ def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
     cents = [[0, e, 0, 0, 0] for e in range(cin // 8)]
     centoff = [[(e * 8 + j) * cout * kv for j in range(8)] for e in range(cin // 8)]
     _pad_even(cents, centoff)
+    # column order (a, b) -> channel block -> c: the kw column blocks that land in adjacent 16-byte
+    # halves of the same 32-byte sectors sit next to each other and are stored back to back
     cols, rowoff = [], []
-    for t, (a, b, c) in enumerate(tl):
-        for q in range(cout // 8):
-            cols.append([0, q, 0xff, a, b, c])
-            rowoff.extend([(q * 8 + j) * kv + t for j in range(8)])
+    for a in range(kd):
+        for b in range(kh):
+            for q in range(cout // 8):
+                for c in range(kw):
+                    t = (a * kh + b) * kw + c
+                    cols.append([0, q, 0xff, a, b, c])
+                    rowoff.extend([(q * 8 + j) * kv + t for j in range(8)])
     fwd = [_finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols[a:b],
-                   rowoff[8 * a:8 * b], ostride=k) for a, b in _col_chunks(len(cols))]
+                   rowoff[8 * a:8 * b], ostride=k, col_bounds=0) for a, b in _col_chunks(len(cols))]
     # dgrad: K = (tap, Cout block) gathered from dy at u*k + tap, N = Cin
     cents, centoff = [], []
     for t, (a, b, c) in enumerate(tl):
@@ -275,7 +294,7 @@ def build_tconv_plan(cin: int, cout: int, k) -> TConvPlan:
     rowoff = [n * cout * kv for n in range(cin)]
     wgrad = _finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols, rowoff, istride=k)
     dgrad = [_finish([list(c) for c in cents], [list(c) for c in centoff], [[0, 0, 0]], [0], cols[a:b],
-                     rowoff[8 * a:8 * b], istride=k) for a, b in _col_chunks(len(cols))]
+                     rowoff[8 * a:8 * b], istride=k, col_bounds=0) for a, b in _col_chunks(len(cols))]
     return TConvPlan(cin, cout, k, fwd, dgrad, wgrad)
 
 

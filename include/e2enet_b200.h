@@ -84,7 +84,9 @@ typedef struct {
   void* dst[E2E_MAX_SRC];
   int32_t dst_cb[E2E_MAX_SRC];       /* channel blocks (out_mode 0) or channel count (out_mode 1) */
   int32_t out_mode;                  /* 0: bf16 C8   1: fp32 NCDHW (dst[0], column n -> channel n) */
-  int32_t impl;                      /* 0: mma.sync gather kernel   1: tcgen05/TMA kernel (stride-1 halo form) */
+  int32_t impl;                      /* 0: mma.sync gather kernel   1: tcgen05/TMA kernel (halo / 1-tap forms) */
+  int32_t col_bounds;                /* bit 0 / 1 / 2: a column block's destination depth / row / column can fall
+                                        outside the destination grid and must be checked (7 is always safe) */
 } e2e_gemm_t;
 
 int e2e_gather_gemm(const e2e_gemm_t* p, void* stream);

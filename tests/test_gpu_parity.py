@@ -356,7 +356,7 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial, impl):
     g = _bf(torch.from_numpy(rs.standard_normal((B, cout, Do, Ho, Wo)).astype(np.float32))).to(dev)
     (ref_raw * g).sum().backward()
     g8 = ops.nc_to_c8(g)
-    gw = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (Do, Ho, Wo), B, g8, tuple(w.shape), impl)
+    gw = ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (Do, Ho, Wo), B, g8, tuple(w.shape), impl)
     assert rel(gw, wc.grad) < 2e-4                                   # fp32 out; fp32 atomics order only
     outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.full_like(s, float("nan"))) for s in xs8]
     sd, sh, sw = stride

@@ -53,8 +53,8 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     # weight gradient: tcgen05 kernel (K = voxels, MN-major operands) vs mma.sync kernel vs torch
     g = bf(torch.from_numpy(rs.standard_normal((B, cout, D, H, W)).astype(np.float32))).to(dev)
     g8 = ops.nc_to_c8(g)
-    gw0 = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 0)
-    gw1 = ops.run_wgrad(plan.fwd, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 1)
+    gw0 = ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 0)
+    gw1 = ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 1)
     torch.cuda.synchronize()
     wc = w.clone().requires_grad_(True)
     (F.conv3d(onet.shift_depth(torch.cat(xs, 1)), wc, None, padding=(0, 1, 1)) * g).sum().backward()

@@ -78,7 +78,7 @@ def test_shiftconv_plans_reproduce_oracle(src, cout, stride, spatial):
     gy = rs.standard_normal(tuple(ref.shape))
     (ref * torch.from_numpy(gy)).sum().backward()
     g8 = pi.to_c8(gy)
-    gw = pi.wgrad(plan.fwd, [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, g8, w.shape)
+    gw = pi.wgrad(plan.wgrad, [pi.to_c8(a) for a in xs], (D, H, W), (Do, Ho, Wo), B, g8, w.shape)
     np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9)
     # strided convs: the variants write only voxels that receive a contribution; the caller zeroes dx
     outs = [np.full(pi.to_c8(a).shape, 0.0 if plan.dgrad_needs_zero else np.nan) for a in xs]

@@ -92,7 +92,7 @@ def main():
                                         [x.shape[1] for x in xs8], impl)
 
         def wgrad():
-            ops.run_wgrad(plan.fwd, xs8, (D, H, W), (Do, Ho, Wo), B, raw, tuple(w.shape), impl)
+            ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (Do, Ho, Wo), B, raw, tuple(w.shape), impl)
 
         line = "%-40s %9.1f |" % ("%s x%d" % (name, cnt), flops / 1e9)
         for o in which:
