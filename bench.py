@@ -222,6 +222,8 @@ def run_ours(args):
     sampler.stop_flag = True
 
     if rank != 0:
+        if not args.no_inference:
+            inference_leg(dev, world, rank, args)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -247,6 +249,8 @@ def run_ours(args):
                      "share_of_step": gemm_ms / ms if ms > 0 else None, "peak_source": peaks["src"] + ", sustained bf16"},
         "step_tflops": STEP_GFLOP_B2 / 1e3 * args.steps / (ms / 1e3),
     }
+    if not args.no_inference:
+        line["inference"] = inference_leg(dev, world, rank, args)
     if not args.no_cpu_baseline and world == 1:
         v, dt, n = cpu_baseline_patches_per_s()
         line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
@@ -257,6 +261,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def inference_leg(dev, world, rank, args):
+    """BASELINE.json configs[2]: AMOS-CT-shaped sliding-window inference, 300x512x512 volume, 16 classes,
+    patch 64x160x160, step 0.5 (324 tiles), Gaussian weighting, no mirroring; tiles sharded over the
+    ranks with one NCCL all-reduce of the accumulators.  Timed through predict_3D (NumPy in, NumPy
+    out: H2D of the volume and D2H of labels + softmax are inside the timed region)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from e2enet_medical_b200.training import POOLS, build_network
+    from e2enet_medical_b200.network_architecture.unetpp_d import softmax_helper
+    vol_shape = tuple(args.infer_volume)
+    torch.manual_seed(0)
+    net = build_network(1, 16, POOLS["btcv"], PATCH, 48, deep_supervision=True).to(dev)
+    net.eval()
+    net.do_ds = False
+    net.inference_apply_nonlin = softmax_helper
+    net.set_tile_sharding(rank, world)
+    vol = np.random.RandomState(0).randn(1, *vol_shape).astype(np.float32)
+    small = vol[:, :64, :160, :320].copy()                       # warm-up: 3 tiles
+    net.predict_3D(small, False, (0, 1, 2), True, 0.5, PATCH, None, True, "constant", None, True, False, True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    seg, probs = net.predict_3D(vol, False, (0, 1, 2), True, 0.5, PATCH, None, True, "constant", None, True, False,
+                                True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # device-only time of the tile loop (volume resident, results left on the device)
+    dev_ms = net._last_tile_loop_ms
+    n_tiles = net._last_num_tiles
+    if world > 1:
+        t = torch.tensor([dt, dev_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dev_ms = float(t[0]), float(t[1])
+    nvox = float(np.prod(vol_shape))
+    return {"metric": "inference voxels/s", "value": nvox / (dev_ms / 1e3), "unit": "voxels/s",
+            "e2e": {"value": nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(vol.nbytes),
+                    "d2h_bytes_per_step": int(seg.nbytes + probs.nbytes)},
+            "ms_per_volume": dev_ms, "e2e_ms_per_volume": dt * 1e3, "tiles": n_tiles,
+            "tiles_per_s": n_tiles / (dev_ms / 1e3),
+            "config": {"workload": "E2ENet AMOS-CT-shaped sliding-window inference: %dx%dx%d volume, 16 classes, patch "
+                                   "64x160x160, step 0.5, gaussian, no mirroring (BASELINE.json configs[2]); value = "
+                                   "tile loop + reduce + finalise on resident data, e2e = predict_3D NumPy->NumPy"
+                                   % vol_shape, "tiles_sharded_over": world}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,6 +316,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel-impl", type=int, default=1, help="0: mma.sync gather kernels, 1: tcgen05 where available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true", help="skip the sliding-window inference leg")
+    ap.add_argument("--infer-volume", type=int, nargs=3, default=[300, 512, 512])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -45,6 +45,7 @@ struct TcParams {
   int rows;                        // window rows per slab: 18 (halo) or 16 (point)
   int need_bounds;                 // destination offsets / strides can leave the destination grid
   int merged;                      // source maps are 4-D with the merged (W, channel) inner dimension
+  int poll;                        // E2E_TC_POLL: 0 all lanes poll, 1 one lane, 2 one lane + backoff
   int b_res;                       // packed weights of the CTA's (fixed) column chunk stay resident in smem
   int b_region_bytes;              // size of that region (then the A stages follow)
   int n_cent, Npad, m, stages, acc_stages;
@@ -105,6 +106,25 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// Warp-level waits: ONE lane polls the mbarrier (a 32-lane try_wait on one address is a 32-way
+// serialised shared-memory access, and ncu showed the polling taking 5-20 % of the shared-memory
+// pipe that the tensor core needs for its operands), the rest of the warp joins at __syncwarp().
+// `backoff` > 0 adds a nanosleep between polls for waits that are expected to be long.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int backoff = 0, int mode = 1) {
+  if (mode == 0) { mbar_wait(bar, parity); return; }
+  if (mode == 1) backoff = 0;
+  if ((threadIdx.x & 31) == 0) {
+    if (!mbar_try_wait(bar, parity)) {
+      const long long t0 = clock64();
+      while (!mbar_try_wait(bar, parity)) {
+        if (backoff) __nanosleep(backoff);
+        if (clock64() - t0 > 8000000000LL) __trap();
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // 4-D form for the stride-1 maps: (W, channel) is merged into one contiguous inner dimension of
 // 32-bit elements (one voxel = 16 B = 4 elements), so a window row is ONE contiguous TMA row
 // instead of 8m+2 separate 16-byte rows
@@ -191,7 +211,7 @@ struct ColInfo {            // one 8-column block of the result, decoded once pe
   uint8_t chmask;
 };
 
-constexpr int EPI_WARPS = 16;            // 4 per TMEM lane quadrant: the epilogue is instruction-bound
+constexpr int EPI_WARPS = 16;            // upper bound; the launch picks 8 or 16 (blockDim.x = 64 + 32 * warps)
 constexpr int TC_THREADS2 = 64 + 32 * EPI_WARPS;
 
 template <bool HALO, int MS>      // MS: 8-voxel-wide sub-tiles (accumulators) per tile
@@ -216,8 +236,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
   const uint32_t bfull_bar = smem_u32(&bars[24]);
 
-  for (int i = threadIdx.x; i < p.n_cent; i += TC_THREADS2) s_cents[i] = p.cents[i];
-  for (int i = threadIdx.x; i < p.n_chunks * 32; i += TC_THREADS2) {
+  const int epi_warps = ((int)blockDim.x >> 5) - 2;
+  for (int i = threadIdx.x; i < p.n_cent; i += blockDim.x) s_cents[i] = p.cents[i];
+  for (int i = threadIdx.x; i < p.n_chunks * 32; i += blockDim.x) {
     const int ch = i >> 5, q = i & 31;
     if (q >= (p.npad[ch] >> 3)) continue;
     const e2e_colblk_t c = p.cols[ch][q];
@@ -241,7 +262,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), epi_warps); }
     mbar_init(bfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -319,7 +340,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     const uint32_t sb0 = smem_base >> 4;
     const int nwork = p.n_tiles * p.n_chunks;
     if (p.b_res && (int)blockIdx.x < nwork) {
-      mbar_wait(bfull_bar, 0);
+      mbar_wait_warp(bfull_bar, 0);
       tc_fence_after();
     }
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
@@ -329,11 +350,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       const uint64_t bdesc = make_desc(0, npc * 16, 128);
       const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
       const uint32_t b_tap_units = (uint32_t)(2 * npc * 16) >> 4;
-      mbar_wait(tempty_bar(as), aphase ^ 1);
+      mbar_wait_warp(tempty_bar(as), aphase ^ 1, 0, p.poll);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + (uint32_t)(as * MS * Npad);
       for (int pr = 0; pr < npairs; ++pr) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_warp(full_bar(stage), phase, 0, p.poll);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units;
@@ -377,10 +398,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       const int b = t / p.D;
       const int h = ht * TH + (r >> 3);
       const int hs = h * p.osh, ds = d * p.osd;
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait_warp(tfull_bar(as), aphase, 64, p.poll);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MS * Npad);
-      for (int ci = grp; ci < MS * nchunk; ci += EPI_WARPS / 4) {
+      for (int ci = grp; ci < MS * nchunk; ci += (epi_warps >> 2)) {
         const int j = ci / nchunk, c0 = (ci - j * nchunk) << 5;
         const int w = (wt * MS + j) * 8 + (r & 7);
         const int ws = w * p.osw;
@@ -531,6 +552,11 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
   p.m = m;
   p.acc_stages = (2 * m * npmax <= 512) ? 2 : 1;
   p.rows = halo ? 18 : 16;
+  {
+    static int poll = -1;
+    if (poll < 0) { const char* e = getenv("E2E_TC_POLL"); poll = e ? atoi(e) : 0; }
+    p.poll = poll;
+  }
   p.merged = (halo || g->isw == 1) ? 1 : 0;
   p.need_bounds = g->col_bounds & 7;
   const int rowpitch = (8 * m + (halo ? 2 : 0)) * 16;
@@ -613,7 +639,16 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     attr_done = true;
   }
   if (!p.b_res && grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
-  kerns[halo ? 1 : 0][m - 1]<<<grid, TC_THREADS2, smem_bytes, st>>>(p, maps);
+  // 16 epilogue warps when a tile has many accumulator columns per MMA (short K loops: data gradients
+  // of narrow layers); 8 otherwise (measured: more warps slow the MMA-bound and the store-bound cases)
+  int epi = 8;
+  if (halo && m * npmax > 6 * npairs * n_taps) epi = 16;
+  {
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("E2E_TC_EPI"); force = e ? atoi(e) : 0; }
+    if (force == 8 || force == 16) epi = force;
+  }
+  kerns[halo ? 1 : 0][m - 1]<<<grid, 64 + 32 * epi, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
 }
@@ -765,7 +800,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
       const uint32_t krow_units = (uint32_t)(2 * p.x_rowpitch) >> 4;     // 16 voxels = 2 window rows
       const uint32_t grp_units = (uint32_t)(16 * p.x_slab_bytes) >> 4;
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_warp(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t sx = smem_base + stage * p.stage_bytes;
@@ -796,7 +831,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
       const int q = warp & 3;
       const int r = q * 32 + lane;             // accumulator row = (entry r/8, channel r%8)
       const int el = r >> 3, j = r & 7;
-      mbar_wait(done_bar, 0);
+      mbar_wait_warp(done_bar, 0, 1000);      // the whole K loop runs before this fires: poll rarely
       tc_fence_after();
       for (int gi = 0; gi < ng; ++gi) {
         const int e = e0 + gi * 16 + el;

@@ -110,6 +110,18 @@ class SegmentationNetwork(NeuralNetwork):
         NCCL all-reduce before normalisation (option A)."""
         self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group)
 
+    @staticmethod
+    def _shard_tiles(tiles, rank: int, world_size: int):
+        """round-robin partition of the sliding-window tiles over ranks (every tile exactly once)"""
+        return list(tiles)[int(rank)::int(world_size)]
+
+    @staticmethod
+    def _reduce_accumulators(agg, wsum, group=None):
+        """the one exchange step of sharded sliding-window inference: sum the per-rank accumulators"""
+        import torch.distributed as dist
+        dist.all_reduce(agg, group=group)
+        dist.all_reduce(wsum, group=group)
+
     # ------------------------------------------------------------------ public API
     def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
                    use_sliding_window: bool = False, step_size: float = 0.5, patch_size: Tuple[int, ...] = None,
@@ -244,16 +256,18 @@ class SegmentationNetwork(NeuralNetwork):
         tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
         shard = self._tile_shard
         if shard is not None:
-            tiles = tiles[shard[0]::shard[1]]
+            tiles = self._shard_tiles(tiles, shard[0], shard[1])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         for (a, b, c) in tiles:
             tile = vol[None, :, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]].contiguous()
             self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, (a, b, c))
         if shard is not None:
-            import torch.distributed as dist
-            dist.all_reduce(agg, group=shard[2])
-            dist.all_reduce(wsum, group=shard[2])
+            self._reduce_accumulators(agg, wsum, shard[2])
 
         seg = self._finalize(agg, wsum)                       # agg now holds agg / wsum
+        ev1.record()
+        self._last_tile_events, self._last_num_tiles = (ev0, ev1), num_tiles
         sp = tuple(slicer[1:])
         probs = agg[(slice(None),) + sp]
         seg = seg[sp]
@@ -267,6 +281,8 @@ class SegmentationNetwork(NeuralNetwork):
                 predicted_segmentation[class_probabilities[i] > 0.5] = c
         if verbose:
             print("prediction done")
+        # device time of tile loop + reduce + finalise of the last call (events are complete: the D2H copies synchronised)
+        self._last_tile_loop_ms = ev0.elapsed_time(ev1)
         return predicted_segmentation, class_probabilities
 
     def _internal_predict_3D_3Dconv(self, x: np.ndarray, min_size: Tuple[int, ...], do_mirroring: bool,

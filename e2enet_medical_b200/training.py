@@ -78,6 +78,20 @@ def synthetic_batch(batch: int, in_ch: int, num_classes: int, patch, pools, seed
     return data, targets
 
 
+def allreduce_mean_grads(params, world_size: int, group=None):
+    """data-parallel gradient mean: ONE flat all-reduce over all gradients (the E2ENet gradients are
+    ~95 MB fp32; NCCL over NVLink/NVSwitch on the GPU box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or world_size <= 1:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, group=group)
+    flat.div_(world_size)
+    for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(s)
+
+
 class SparseArgs(argparse.Namespace):
     adv = False
     fix = False
@@ -111,13 +125,7 @@ class TrainStep(object):
 
     def _allreduce_grads(self):
         """data-parallel gradient mean over NCCL (one flat bucket; grads are ~95 MB fp32)."""
-        import torch.distributed as dist
-        grads = [p.grad for p in self.network.parameters() if p.grad is not None]
-        flat = torch._utils._flatten_dense_tensors(grads)
-        dist.all_reduce(flat)
-        flat.div_(self.world_size)
-        for g, s in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-            g.copy_(s)
+        allreduce_mean_grads(list(self.network.parameters()), self.world_size)
 
     def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
         self.optimizer.zero_grad()
