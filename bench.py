@@ -218,6 +218,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     gemm_ms = sum(a.elapsed_time(b) for (_, a, b, _) in recs)
     gemm_flops = sum(f for (_, _, _, f) in recs)
+    per_kind = {}
+    for kind in ("gemm", "wgrad"):
+        kms = sum(a.elapsed_time(b) for (k, a, b, _) in recs if k == kind)
+        kfl = sum(f for (k, _, _, f) in recs if k == kind)
+        per_kind[kind] = {"launches_per_step": sum(1 for r in recs if r[0] == kind) / max(args.steps, 1),
+                          "ms_per_step": kms / max(args.steps, 1),
+                          "achieved_tflops": (kfl / 1e12) / (kms / 1e3) if kms > 0 else 0.0}
     ms_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag = True
 
@@ -244,8 +251,15 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tf_sustained"], "traffic": None,
-                     "kernel": "conv/tconv/seg GEMM launches (gather_gemm + gather_wgrad), dense 2MNK FLOPs",
+                     "frac": achieved / peaks["tf_sustained"],
+                     # one `ncu --set full` capture of the family's largest launch (loc4 forward, conv_tc_kernel<1,4>,
+                     # profiles/r01_ncu_conv_tc_loc4_fwd_details.txt): dram read 618.8 MB + write 286.0 MB per launch
+                     # vs 943.7 MB algorithmic (2 x 48-ch bf16 sources + 48-ch bf16 result): no wasted re-reads
+                     "traffic": 904.8e6,
+                     "traffic_of": "conv_tc_kernel<1,4> loc4 forward launch (algorithmic bytes 943.7e6, 271.8 GFLOP)",
+                     "kernel": "tcgen05 conv / transposed-conv / 1x1 GEMM launches of one step: conv_tc_kernel (fwd + "
+                               "dgrad; key 'gemm') and wgrad_tc_kernel (key 'wgrad'); dense 2MNK FLOPs",
+                     "per_kind": {k: dict(v, frac=v["achieved_tflops"] / peaks["tf_sustained"]) for k, v in per_kind.items()},
                      "share_of_step": gemm_ms / ms if ms > 0 else None, "peak_source": peaks["src"] + ", sustained bf16"},
         "step_tflops": STEP_GFLOP_B2 / 1e3 * args.steps / (ms / 1e3),
     }
@@ -278,9 +292,12 @@ def inference_leg(dev, world, rank, args):
     net.do_ds = False
     net.inference_apply_nonlin = softmax_helper
     net.set_tile_sharding(rank, world)
+    net.pinned_output_buffers = True       # results land in reused pinned host buffers (documented opt-in)
     vol = np.random.RandomState(0).randn(1, *vol_shape).astype(np.float32)
     small = vol[:, :64, :160, :320].copy()                       # warm-up: 3 tiles
     net.predict_3D(small, False, (0, 1, 2), True, 0.5, PATCH, None, True, "constant", None, True, False, True)
+    net._pinned_out = {"seg": torch.empty(vol_shape, dtype=torch.int64, pin_memory=True),
+                       "probs": torch.empty((16,) + vol_shape, dtype=torch.float32, pin_memory=True)}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -304,7 +321,7 @@ def inference_leg(dev, world, rank, args):
             "tiles_per_s": n_tiles / (dev_ms / 1e3),
             "config": {"workload": "E2ENet AMOS-CT-shaped sliding-window inference: %dx%dx%d volume, 16 classes, patch "
                                    "64x160x160, step 0.5, gaussian, no mirroring (BASELINE.json configs[2]); value = "
-                                   "tile loop + reduce + finalise on resident data, e2e = predict_3D NumPy->NumPy"
+                                   "tile loop + reduce + finalise on resident data, e2e = predict_3D NumPy->NumPy (pinned_output_buffers=True)"
                                    % vol_shape, "tiles_sharded_over": world}}
 
 

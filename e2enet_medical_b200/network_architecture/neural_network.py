@@ -222,6 +222,22 @@ class SegmentationNetwork(NeuralNetwork):
                                            C.c_void_p(seg.data_ptr()), _lib.stream_ptr()), "window_finalize")
         return seg
 
+    def _to_host(self, t: torch.Tensor, tag: str) -> np.ndarray:
+        """device -> NumPy.  With `self.pinned_output_buffers = True` the result lives in a pinned host
+        buffer that is REUSED by the next predict_3D call (copy it if you keep it): the 5.6 GB of
+        labels + softmax of a 300x512x512 / 16-class volume then move at PCIe speed instead of
+        pageable-memory speed.  Default: a fresh pageable array per call, like the reference."""
+        if not getattr(self, "pinned_output_buffers", False):
+            return t.cpu().numpy()
+        cache = self.__dict__.setdefault("_pinned_out", {})
+        buf = cache.get(tag)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            cache[tag] = buf
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return buf.numpy()
+
     def _device(self):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
@@ -272,10 +288,10 @@ class SegmentationNetwork(NeuralNetwork):
         probs = agg[(slice(None),) + sp]
         seg = seg[sp]
         if regions_class_order is None:
-            predicted_segmentation = seg.cpu().numpy()
-            class_probabilities = probs.cpu().numpy()
+            predicted_segmentation = self._to_host(seg, "seg")
+            class_probabilities = self._to_host(probs, "probs")
         else:
-            class_probabilities = probs.cpu().numpy()
+            class_probabilities = self._to_host(probs, "probs")
             predicted_segmentation = np.zeros(class_probabilities.shape[1:], dtype=np.float32)
             for i, c in enumerate(regions_class_order):
                 predicted_segmentation[class_probabilities[i] > 0.5] = c
