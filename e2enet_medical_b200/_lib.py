@@ -110,6 +110,8 @@ SIGNATURES = {
     "e2e_mask_dead_list": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "e2e_mask_grow": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "e2e_mask_counts": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP]),
+    "e2e_softmax_stats_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I64, _VP, _VP]),
     "e2e_window_accumulate": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                         _I32, _I32, _F, _I32, _I32, _VP]),
     "e2e_window_finalize": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),

@@ -1,0 +1,164 @@
+// Fused softmax statistics for the deep-supervision loss.
+//
+// The reference's DC_and_CE_loss (e2enet/training/loss_functions/dice_loss.py:302-359) runs, per
+// deep-supervision output, softmax + one-hot scatter + tp/fp/fn reductions (SoftDiceLoss,
+// dice_loss.py:155-190) and a second log-softmax + nll pass (crossentropy.py:4-11): ~10 passes
+// over the fp32 logits.  Everything voxel-sized they compute is a function of three per-(b, c)
+// sums and one scalar:
+//     S_p[b,c] = sum_v p[b,c,v]      tp[b,c] = sum_v p[b,c,v] * [y[b,v] == c]
+//     S_y[b,c] = #{v : y[b,v] == c}  ce_sum  = sum_{b,v} -log p[b, y[b,v], v]
+// (fp = S_p - tp, fn = S_y - tp).  One pass produces them; the dice / CE formulas stay in torch on
+// the tiny (B, C) tensors, and one more pass applies their gradients through the softmax:
+//     dz[b,k,v] = p_k * (g_k - sum_j p_j g_j) + g_ce * (p_k - [y == k]),   g_j = gS_p[b,j] + gtp[b,j] * [y == j]
+// HBM-bound: forward reads logits + target once, backward reads them once and writes dlogits once.
+#include "common.cuh"
+
+namespace {
+
+template <int NC>
+__global__ void __launch_bounds__(256) softmax_stats_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                                int C, long long V, int chunks_per_b,
+                                                                float* __restrict__ stats /* [B][C][3] */,
+                                                                float* __restrict__ ce_sum) {
+  // grid: (chunks_per_b, B); block-level partial sums in shared memory, then one atomic per value
+  __shared__ float s_acc[3 * NC + 1];
+  for (int i = threadIdx.x; i < 3 * NC + 1; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const int b = blockIdx.y;
+  const long long per = (V + chunks_per_b - 1) / chunks_per_b;
+  const long long lo = (long long)blockIdx.x * per, hi = min(V, lo + per);
+  const float* lb = logits + (long long)b * C * V;
+  const float* tb = target + (long long)b * V;
+  float sp[NC], tpv[NC], sy[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) { sp[c] = 0.f; tpv[c] = 0.f; sy[c] = 0.f; }
+  float ce = 0.f;
+  for (long long v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+    float z[NC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      z[c] = (c < C) ? lb[(long long)c * V + v] : -INFINITY;
+      mx = fmaxf(mx, z[c]);
+    }
+    const int y = (int)tb[v];
+    float sum = 0.f, zy = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float e = (c < C) ? expf(z[c] - mx) : 0.f;
+      if (c == y) zy = z[c];
+      z[c] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float p = z[c] * inv;
+      sp[c] += p;
+      if (c == y) { tpv[c] += p; sy[c] += 1.f; }
+    }
+    ce += logf(sum) + mx - zy;                     // -log softmax(z)[y]
+  }
+  // warp reduce, then shared-memory atomics (few per warp), then one global atomic per value
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c >= C) break;
+    const float a = warp_sum(sp[c]), t = warp_sum(tpv[c]), s = warp_sum(sy[c]);
+    if (lane == 0) {
+      atomicAdd(&s_acc[3 * c + 0], a);
+      atomicAdd(&s_acc[3 * c + 1], t);
+      atomicAdd(&s_acc[3 * c + 2], s);
+    }
+  }
+  ce = warp_sum(ce);
+  if (lane == 0) atomicAdd(&s_acc[3 * NC], ce);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(&stats[(long long)b * C * 3 + i], s_acc[i]);
+  if (threadIdx.x == 0) atomicAdd(ce_sum, s_acc[3 * NC]);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256) softmax_stats_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                                const float* __restrict__ gsp, const float* __restrict__ gtp,
+                                                                const float* __restrict__ gce, int C, long long V,
+                                                                int chunks_per_b, float* __restrict__ dlogits) {
+  const int b = blockIdx.y;
+  const long long per = (V + chunks_per_b - 1) / chunks_per_b;
+  const long long lo = (long long)blockIdx.x * per, hi = min(V, lo + per);
+  const float* lb = logits + (long long)b * C * V;
+  const float* tb = target + (long long)b * V;
+  float* db = dlogits + (long long)b * C * V;
+  float a[NC], t[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    a[c] = (c < C) ? gsp[b * C + c] : 0.f;
+    t[c] = (c < C) ? gtp[b * C + c] : 0.f;
+  }
+  const float gc = gce[0];
+  for (long long v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+    float z[NC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      z[c] = (c < C) ? lb[(long long)c * V + v] : -INFINITY;
+      mx = fmaxf(mx, z[c]);
+    }
+    const int y = (int)tb[v];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      z[c] = (c < C) ? expf(z[c] - mx) : 0.f;
+      sum += z[c];
+    }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      z[c] *= inv;                                           // p_c
+      dot += z[c] * (a[c] + (c == y ? t[c] : 0.f));
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c >= C) break;
+      const float g = a[c] + (c == y ? t[c] : 0.f);
+      db[(long long)c * V + v] = z[c] * (g - dot) + gc * (z[c] - (c == y ? 1.f : 0.f));
+    }
+  }
+}
+
+inline int chunks_for(long long V, int B) {
+  long long want = ((long long)e2e_num_sms() * 8 + B - 1) / B;
+  long long mx = (V + 1023) / 1024;
+  if (want > mx) want = mx;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace
+
+extern "C" int e2e_softmax_stats_fwd(const float* logits, const float* target, int32_t B, int32_t C, int64_t V,
+                                     float* stats, float* ce_sum, void* stream) {
+  E2E_ARG(logits && target && stats && ce_sum && B > 0 && C > 0 && V > 0, "softmax_stats_fwd: bad arguments");
+  E2E_ARG(C <= 32, "softmax_stats_fwd: at most 32 classes (got %d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(chunks_for(V, B), B);
+  if (C <= 4) softmax_stats_fwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
+  else if (C <= 16) softmax_stats_fwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
+  else softmax_stats_fwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
+  E2E_LAUNCHED("softmax_stats_fwd");
+  return E2E_OK;
+}
+
+extern "C" int e2e_softmax_stats_bwd(const float* logits, const float* target, const float* gsp, const float* gtp,
+                                     const float* gce, int32_t B, int32_t C, int64_t V, float* dlogits, void* stream) {
+  E2E_ARG(logits && target && gsp && gtp && gce && dlogits && B > 0 && C > 0 && V > 0, "softmax_stats_bwd: bad arguments");
+  E2E_ARG(C <= 32, "softmax_stats_bwd: at most 32 classes (got %d)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(chunks_for(V, B), B);
+  if (C <= 4) softmax_stats_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
+  else if (C <= 16) softmax_stats_bwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
+  else softmax_stats_bwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
+  E2E_LAUNCHED("softmax_stats_bwd");
+  return E2E_OK;
+}

@@ -447,11 +447,53 @@ class SegHead(torch.autograd.Function):
         weight, x = ctx.saved_tensors
         B, Cb, D, H, W = c8_shape(x)
         g = nc_to_c8(dy)
+        impl = CONFIG["impl"]
         gw = dx = None
         if ctx.needs_input_grad[1]:
-            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), 0)
+            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl)
         if ctx.needs_input_grad[2]:
             wp = pack_weights(plan.dgrad, weight, None)
             dx = torch.empty_like(x)
-            run_gemm(plan.dgrad, wp, [g], (D, H, W), (D, H, W), B, [dx], (D, H, W), [Cb], 0)
+            run_gemm(plan.dgrad, wp, [g], (D, H, W), (D, H, W), B, [dx], (D, H, W), [Cb], impl)
         return None, gw, dx
+
+
+class SoftmaxStats(torch.autograd.Function):
+    """(logits fp32 (B,C,*sp), target (B,1,*sp) or (B,*sp) with class indices) ->
+    S_p (B,C) = sum_v softmax, tp (B,C) = sum_v softmax * onehot, S_y (B,C) = class counts,
+    ce_sum () = sum over all voxels of -log softmax[target].  One fused pass forward, one backward
+    (csrc/loss.cu); everything else of DC_and_CE_loss is arithmetic on these tiny tensors."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        _need_cuda(logits, "softmax_stats")
+        lib = _lib.load()
+        x = logits.contiguous().float()
+        t = target.detach().contiguous().float()
+        B, Cc = x.shape[:2]
+        V = x[0, 0].numel()
+        if t.numel() != B * V:
+            raise ValueError("softmax_stats: target must hold one class index per voxel (got %s for logits %s)"
+                             % (tuple(target.shape), tuple(logits.shape)))
+        stats = torch.zeros((B, Cc, 3), dtype=torch.float32, device=x.device)
+        ce = torch.zeros((), dtype=torch.float32, device=x.device)
+        _lib.check(lib.e2e_softmax_stats_fwd(_p(x), _p(t), B, Cc, V, _p(stats), _p(ce), _lib.stream_ptr()),
+                   "softmax_stats_fwd")
+        ctx.save_for_backward(x, t)
+        sp, tp, sy = stats[..., 0].clone(), stats[..., 1].clone(), stats[..., 2].clone()
+        ctx.mark_non_differentiable(sy)
+        return sp, tp, sy, ce
+
+    @staticmethod
+    def backward(ctx, gsp, gtp, _gsy, gce):
+        x, t = ctx.saved_tensors
+        lib = _lib.load()
+        B, Cc = x.shape[:2]
+        V = x[0, 0].numel()
+        z = lambda g, shape: (torch.zeros(shape, dtype=torch.float32, device=x.device) if g is None
+                              else g.contiguous().float())
+        gsp, gtp, gce = z(gsp, (B, Cc)), z(gtp, (B, Cc)), z(gce, ())
+        dx = torch.empty_like(x)
+        _lib.check(lib.e2e_softmax_stats_bwd(_p(x), _p(t), _p(gsp), _p(gtp), _p(gce), B, Cc, V, _p(dx),
+                                             _lib.stream_ptr()), "softmax_stats_bwd")
+        return dx, None

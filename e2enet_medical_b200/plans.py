@@ -321,5 +321,5 @@ def build_seghead_plan(cin: int, ncls: int) -> SegHeadPlan:
     centoff = [[(e * 8 + j) * cin if e * 8 + j < ncls else -1 for j in range(8)] for e in range(ncb)]
     _pad_even(cents, centoff)
     cols = [[0, q, 0xff, 0, 0, 0] for q in range(cin // 8)]
-    dgrad = _finish(cents, centoff, [[0, 0, 0]], [0], cols, list(range(cin)))
+    dgrad = _finish(cents, centoff, [[0, 0, 0]], [0], cols, list(range(cin)), col_bounds=0)
     return SegHeadPlan(cin, ncls, fwd, dgrad)

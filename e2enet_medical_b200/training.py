@@ -103,7 +103,8 @@ class TrainStep(object):
     """one data-parallel replica of the reference's training iteration on synthetic data."""
 
     def __init__(self, in_ch=1, num_classes=14, pools=None, patch=(64, 160, 160), density=0.2, death_rate=0.5,
-                 update_frequency=1200, device="cuda", world_size=1, seed=0, base=48, total_steps=250000):
+                 update_frequency=1200, device="cuda", world_size=1, seed=0, base=48, total_steps=250000,
+                 fused_loss=True):
         from .sparselearning.core_channel import CosineDecay, Masking
         import random
         pools = POOLS["btcv"] if pools is None else pools
@@ -122,6 +123,13 @@ class TrainStep(object):
         self.mask.add_module(self.network, sparse_init='uniform', density=density)
         self.world_size = world_size
         self._flat = None
+        # the trainer's loss (nnUNetTrainer_simple.py:100,200-215): fused statistics kernels, or plain torch
+        if fused_loss:
+            from .loss_functions import DC_and_CE_loss, MultipleOutputLoss2
+            self.loss = MultipleOutputLoss2(DC_and_CE_loss({'batch_dice': False, 'smooth': 1e-5, 'do_bg': False}, {}),
+                                            ds_loss_weights(4, len(pools)))
+        else:
+            self.loss = multiple_output_loss
 
     def _allreduce_grads(self):
         """data-parallel gradient mean over NCCL (one flat bucket; grads are ~95 MB fp32)."""
@@ -130,7 +138,7 @@ class TrainStep(object):
     def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
         self.optimizer.zero_grad()
         output = self.network(data)
-        l = multiple_output_loss(output, targets)
+        l = self.loss(output, targets)
         l.backward()
         if self.world_size > 1:
             self._allreduce_grads()

@@ -185,6 +185,19 @@ int e2e_mask_grow(float* mask, const int32_t* dead, const int32_t* pick, int32_t
 /* nnz[0] = #(mask != 0); fired |= mask; nnz[1] = #(fired != 0) */
 int e2e_mask_counts(const float* mask, uint8_t* fired, int64_t numel, int32_t* nnz, void* stream);
 
+/* ---------------------------------------------------------------- deep-supervision loss statistics */
+/*
+ * logits fp32 [B][C][V], target fp32 [B][V] (class index as float, like the reference's target[:, 0]):
+ * stats[b][c] = {sum_v p, sum_v p*[y==c], #{y==c}} and *ce_sum = sum -log p[y] are ACCUMULATED (caller
+ * zeroes them).  Replaces the softmax / one-hot / tp-fp-fn / log-softmax / nll passes of
+ * e2enet/training/loss_functions/dice_loss.py:100-190,302-359 and crossentropy.py:4-11.
+ */
+int e2e_softmax_stats_fwd(const float* logits, const float* target, int32_t B, int32_t C, int64_t V,
+                          float* stats, float* ce_sum, void* stream);
+/* dlogits = p_k (g_k - sum_j p_j g_j) + gce (p_k - [y==k]),  g_j = gsp[b][j] + gtp[b][j] [y==j]; gce: device scalar */
+int e2e_softmax_stats_bwd(const float* logits, const float* target, const float* gsp, const float* gtp,
+                          const float* gce, int32_t B, int32_t C, int64_t V, float* dlogits, void* stream);
+
 /* ---------------------------------------------------------------- sliding-window accumulate */
 /*
  * logits fp32 [ncls][px][py][pz] of one tile (possibly predicted on a flipped input: flip bit0=x,

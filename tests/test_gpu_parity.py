@@ -543,3 +543,39 @@ def test_window_steps_known_answers(dev):
                                                         [0, 55, 109, 164, 219, 273, 328],
                                                         [0, 55, 109, 164, 219, 273, 328]]
     assert np.array_equal(S._get_gaussian((16, 24, 20)), owin.gaussian_map((16, 24, 20)))
+
+
+# ------------------------------------------------------------------------------ fused deep-supervision loss
+@pytest.mark.parametrize("batch_dice", [False, True])
+def test_fused_ds_loss_vs_oracle(dev, batch_dice):
+    """DC_and_CE_loss / MultipleOutputLoss2 mirrors (one fused statistics pass + one backward pass)
+    vs the fp32 oracle restatement of the reference loss: value and d(loss)/d(logits)."""
+    from e2enet_medical_b200.loss_functions import DC_and_CE_loss, MultipleOutputLoss2
+    rs = np.random.RandomState(11)
+    ncls, B = 14, 2
+    shapes = [(6, 20, 24), (6, 10, 12), (3, 5, 6), (2, 3, 3)]
+    outs_h = [torch.from_numpy((2.0 * rs.standard_normal((B, ncls) + s)).astype(np.float32)) for s in shapes]
+    tg_h = [torch.from_numpy(np.round(rs.rand(B, 1, *s) * (ncls - 1)).astype(np.float32)) for s in shapes]
+    w = onet.ds_weights(4)
+    # oracle (CPU fp32); batch_dice=True variant restated inline from SoftDiceLoss (dice_loss.py:168-190)
+    ref_in = [o.clone().requires_grad_(True) for o in outs_h]
+    if not batch_dice:
+        ref = onet.ds_loss(ref_in, tg_h)
+    else:
+        def one(lg, tg):
+            ce = torch.nn.functional.cross_entropy(lg, tg[:, 0].long())
+            p = torch.softmax(lg, 1)
+            oh = torch.zeros_like(p).scatter_(1, tg.long(), 1.0)
+            ax = (0, 2, 3, 4)
+            tp, fp, fn = (p * oh).sum(ax), (p * (1 - oh)).sum(ax), ((1 - p) * oh).sum(ax)
+            dc = (2 * tp + 1e-5) / (2 * tp + fp + fn + 1e-5 + 1e-8)
+            return ce - dc[1:].mean()
+        ref = sum(w[k] * one(ref_in[k], tg_h[k]) for k in range(4))
+    ref.backward()
+    loss_mod = MultipleOutputLoss2(DC_and_CE_loss({'batch_dice': batch_dice, 'smooth': 1e-5, 'do_bg': False}, {}), w)
+    dev_in = [o.clone().to(dev).requires_grad_(True) for o in outs_h]
+    got = loss_mod(dev_in, [t.to(dev) for t in tg_h])
+    got.backward()
+    assert abs(got.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+    for a, r in zip(dev_in, ref_in):
+        assert rel(a.grad, r.grad) < 2e-4, rel(a.grad, r.grad)
