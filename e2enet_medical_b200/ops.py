@@ -235,7 +235,7 @@ def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid,
     p.impl = impl
     with _Timed("wgrad", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
         _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
-    gw = torch.zeros(weight_shape, dtype=torch.float32, device=device)
+    gw = torch.empty(weight_shape, dtype=torch.float32, device=device)      # unpack writes every weight once
     _lib.check(lib.e2e_unpack_wgrad(_p(dwp), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]), plan.n_cent,
                                     plan.n_taps, plan.Npad, _p(gw), _lib.stream_ptr()), "unpack_wgrad")
     return gw
