@@ -187,9 +187,12 @@ class SegmentationNetwork(NeuralNetwork):
         return getattr(self.inference_apply_nonlin, "__name__", "") == "softmax_helper"
 
     def _accumulate_tile(self, tile: torch.Tensor, mirror_axes, do_mirroring, gauss, agg, wsum, origin):
-        """tile: (1,c,px,py,pz) CUDA fp32.  Fuses softmax, un-mirroring, 1/num_mirrors, Gaussian and
-        the += into agg / wsum (reference :529-563 and :392-393)."""
+        """tile: (n,c,px,py,pz) CUDA fp32, n tiles batched through one forward (InstanceNorm is per
+        sample, so batching tiles is exact); origin: one (x0,y0,z0) or a list of n.  Fuses softmax,
+        un-mirroring, 1/num_mirrors, Gaussian and the += into agg / wsum (reference :529-563, :392-393)."""
         lib = _lib.load()
+        origins = [origin] if isinstance(origin[0], (int, np.integer)) else list(origin)
+        assert len(origins) == tile.shape[0]
         ncls = self.num_classes
         X, Y, Z = wsum.shape
         px, py, pz = tile.shape[2:]
@@ -207,11 +210,13 @@ class SegmentationNetwork(NeuralNetwork):
             out = out.float().contiguous()
             assert out.shape[1] == ncls
             flip = sum(1 << a for a in m)
-            _lib.check(lib.e2e_window_accumulate(
-                C.c_void_p(out.data_ptr()), C.c_void_p(gauss.data_ptr() if gauss is not None else 0),
-                C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z,
-                origin[0], origin[1], origin[2], flip, scale, 1 if n == 0 else 0, 1 if fused else 0,
-                _lib.stream_ptr()), "window_accumulate")
+            per = out[0].numel() * 4
+            for i, org in enumerate(origins):
+                _lib.check(lib.e2e_window_accumulate(
+                    C.c_void_p(out.data_ptr() + i * per), C.c_void_p(gauss.data_ptr() if gauss is not None else 0),
+                    C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z,
+                    int(org[0]), int(org[1]), int(org[2]), flip, scale, 1 if n == 0 else 0, 1 if fused else 0,
+                    _lib.stream_ptr()), "window_accumulate")
 
     def _finalize(self, agg, wsum):
         lib = _lib.load()
@@ -275,9 +280,12 @@ class SegmentationNetwork(NeuralNetwork):
             tiles = self._shard_tiles(tiles, shard[0], shard[1])
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for (a, b, c) in tiles:
-            tile = vol[None, :, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]].contiguous()
-            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, (a, b, c))
+        nb = max(1, int(getattr(self, "tile_batch", 4)))      # tiles per forward (exact: per-sample norm)
+        for i0 in range(0, len(tiles), nb):
+            grp = tiles[i0:i0 + nb]
+            tile = torch.stack([vol[:, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]]
+                                for (a, b, c) in grp])
+            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, grp)
         if shard is not None:
             self._reduce_accumulators(agg, wsum, shard[2])
 

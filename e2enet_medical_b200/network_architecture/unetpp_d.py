@@ -381,12 +381,14 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
                 if i > 0:
                     parts.append(self._pool(getattr(self, "down%d" % z)[idx], node[(i - 1, j - 1)]))
                 node[(i, j)] = getattr(self, "loc%d" % z)[idx](C8.cat(parts))
+        if not (self._deep_supervision and self.do_ds):
+            # the reference computes all four heads and returns the last (:480-488); the other three
+            # have no effect on the result, so inference skips them
+            return self.final_nonlin(self._seg(0, node[(0, 5)]))
         seg_outputs = [self.final_nonlin(self._seg(3, node[(3, 2)])), self.final_nonlin(self._seg(2, node[(2, 3)])),
                        self.final_nonlin(self._seg(1, node[(1, 4)])), self.final_nonlin(self._seg(0, node[(0, 5)]))]
-        if self._deep_supervision and self.do_ds:
-            return list([seg_outputs[-1]] + [i(j) for i, j in zip(list(self.upscale_logits_ops)[::-1],
-                                                                   seg_outputs[:-1][::-1])])
-        return seg_outputs[-1]
+        return list([seg_outputs[-1]] + [i(j) for i, j in zip(list(self.upscale_logits_ops)[::-1],
+                                                               seg_outputs[:-1][::-1])])
 
     @staticmethod
     def compute_approx_vram_consumption(patch_size, num_pool_per_axis, base_num_features, max_num_features,
