@@ -107,17 +107,26 @@ __global__ void __launch_bounds__(EW_THREADS) in_stats_partial_kernel(const uint
   block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
 }
 
-// one thread per (plane, j)
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// one WARP per (plane, j): lanes stride over the chunk partials (fixed order -> deterministic)
 __global__ void in_stats_final_kernel(const float* __restrict__ partial, int planes, int nchunk, long long V, float eps,
                                       float* __restrict__ mean, float* __restrict__ rstd) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= planes * 8) return;
   const int plane = i >> 3, j = i & 7;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < nchunk; ++c) {
+  for (int c = lane; c < nchunk; c += 32) {
     s += partial[((long long)plane * nchunk + c) * 16 + j];
     q += partial[((long long)plane * nchunk + c) * 16 + 8 + j];
   }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane) return;
   const double m = s / (double)V;
   double var = q / (double)V - m * m;
   if (var < 0.0) var = 0.0;
@@ -217,12 +226,13 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_reduce_kernel(const uint4* 
 
 // sums[plane*16 + k] (fp32) = total over chunks
 __global__ void in_bwd_final_kernel(const float* __restrict__ partial, int planes, int nchunk, float* __restrict__ sums) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;     // one warp per value
   if (i >= planes * 16) return;
   const int plane = i >> 4, k = i & 15;
   double s = 0.0;
-  for (int c = 0; c < nchunk; ++c) s += partial[((long long)plane * nchunk + c) * 16 + k];
-  sums[i] = (float)s;
+  for (int c = lane; c < nchunk; c += 32) s += partial[((long long)plane * nchunk + c) * 16 + k];
+  s = warp_sum_d(s);
+  if (lane == 0) sums[i] = (float)s;
 }
 
 // backward pass 2: draw = rstd*gamma*(dz - mean(dz) - xhat*mean(dz*xhat)); partial2[plane][chunk][0..7] = sum draw
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_apply_kernel(const uint4* _
 __global__ void in_bwd_param_kernel(const float* __restrict__ sums, const float* __restrict__ partial2, int B, int Cb,
                                     int nchunk, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                     float* __restrict__ dbias) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;     // one warp per channel
   if (c >= Cb * 8) return;
   const int cb = c >> 3, j = c & 7;
   double g = 0.0, bt = 0.0, bi = 0.0;
@@ -297,8 +307,10 @@ __global__ void in_bwd_param_kernel(const float* __restrict__ sums, const float*
     const int plane = b * Cb + cb;
     bt += sums[plane * 16 + j];
     g += sums[plane * 16 + 8 + j];
-    for (int k = 0; k < nchunk; ++k) bi += partial2[((long long)plane * nchunk + k) * 8 + j];
+    for (int k = lane; k < nchunk; k += 32) bi += partial2[((long long)plane * nchunk + k) * 8 + j];
   }
+  bi = warp_sum_d(bi);
+  if (lane) return;
   dgamma[c] = (float)g;
   dbeta[c] = (float)bt;
   if (dbias) dbias[c] = (float)bi;
@@ -426,7 +438,7 @@ extern "C" int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, f
   cudaStream_t st = (cudaStream_t)stream;
   in_stats_partial_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, st>>>((const uint4*)raw, V, nchunk, partial);
   E2E_LAUNCHED("in_stats_partial");
-  const int n = B * Cb * 8;
+  const int n = B * Cb * 8 * 32;
   in_stats_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, V, eps, mean, rstd);
   E2E_LAUNCHED("in_stats_final");
   return E2E_OK;
@@ -458,13 +470,13 @@ extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, co
   in_bwd_reduce_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta,
                                                     slope, Cb, V, nchunk, partial);
   E2E_LAUNCHED("in_bwd_reduce");
-  const int n = B * Cb * 16;
+  const int n = B * Cb * 16 * 32;
   in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
   E2E_LAUNCHED("in_bwd_final");
   in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, sums,
                                                    slope, Cb, V, nchunk, (uint4*)draw, partial);
   E2E_LAUNCHED("in_bwd_apply");
-  in_bwd_param_kernel<<<(Cb * 8 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;
 }

@@ -46,25 +46,34 @@ __global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __r
     }
     const float g = gauss ? gauss[i] : 1.f;
     const long long dst = ((long long)(x0 + ii) * Y + (y0 + j)) * Z + (z0 + k);
+    // all accumulator loads first, then all stores: `agg[c*V + dst] += ...` in one loop makes every
+    // load wait for the previous store (the compiler cannot prove the class planes distinct)
+    float a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = (c < ncls) ? agg[c * V + dst] : 0.f;
+    const float w0 = add_weight ? wsum[dst] : 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c)
-      if (c < ncls) {
-        const float pr = (v[c] * inv) * scale;
-        agg[c * V + dst] += pr * g;
-      }
-    if (add_weight) wsum[dst] += g;
+      if (c < ncls) agg[c * V + dst] = a[c] + ((v[c] * inv) * scale) * g;
+    if (add_weight) wsum[dst] = w0 + g;
   }
 }
 
+template <int NC>
 __global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict__ agg, const float* __restrict__ wsum, int ncls,
                                                               long long V, long long* __restrict__ seg) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V;
        i += (long long)gridDim.x * blockDim.x) {
     const float w = wsum[i];
+    float a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = (c < ncls) ? agg[c * V + i] : 0.f;     // independent loads in flight
     float best = -INFINITY;
     int bi = 0;
-    for (int c = 0; c < ncls; ++c) {
-      const float p = agg[c * V + i] / w;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c >= ncls) break;
+      const float p = a[c] / w;
       agg[c * V + i] = p;
       if (p > best) { best = p; bi = c; }
     }
@@ -104,7 +113,11 @@ extern "C" int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, 
   long long blocks = (V + 255) / 256;
   const long long cap = (long long)e2e_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  window_finalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(agg, wsum, ncls, V, (long long*)seg);
+  E2E_ARG(ncls <= MAXC, "window_finalize: ncls %d outside [1,%d]", ncls, MAXC);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ncls <= 4) window_finalize_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
+  else if (ncls <= 16) window_finalize_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
+  else window_finalize_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
   E2E_LAUNCHED("window_finalize");
   return E2E_OK;
 }

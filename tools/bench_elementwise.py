@@ -90,8 +90,12 @@ def main():
         prm.grad = torch.zeros_like(prm)
     ts.optimizer.step()
     n = sum(m.numel() for m in ts.mask.masks.values())
-    report("mask.apply_mask() 35 tensors (w, momentum RMW + mask read)", n * 4 * 6,
-           timeit(ts.mask.apply_mask, a.iters))
+    ts.mask.apply_mask()                                   # builds the device pointer tables
+    _, wt, bt, mt, nt, mx = ts.mask._scratch[("apply", True)]
+    n_t = int(nt.numel())
+    report("mask_apply_multi kernel, 35 tensors (w, momentum RMW + mask read)", n * 4 * 6,
+           timeit(lambda: _lib.check(lib.e2e_mask_apply_multi(p(wt), p(bt), p(mt), p(nt), n_t, mx, st())), a.iters))
+    report("Masking.apply_mask() incl. Python host side", n * 4 * 6, timeit(ts.mask.apply_mask, a.iters))
     del ts
     # sliding window: one (16, 64, 160, 160) tile into a (16, 128, 320, 320) accumulator
     ncls, px, py, pz, X, Y, Z = 16, 64, 160, 160, 128, 320, 320
