@@ -754,43 +754,47 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
 
   if (my_tiles > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0, phase = 0;
-        const uint32_t tx = (uint32_t)ne * (uint32_t)(p.x_rows * p.x_rowpitch) + (uint32_t)ncol * 256u;
-        for (int tile = tile_lo; tile < tile_hi; ++tile) {
-          int t = tile;
-          const int wt = t % p.tiles_w; t /= p.tiles_w;
-          const int ht = t % p.tiles_h; t /= p.tiles_h;
-          const int d = t % p.D;
-          const int b = t / p.D;
-          const int h0 = ht * TH, w0 = wt * 8;
+      // producer WARP: lane 0 waits for the stage and arms the barrier; then every lane issues the boxes
+      // of its entries (lane, lane + 32) and lane 31 the gradient tile, in parallel
+      int stage = 0, phase = 0;
+      const uint32_t tx = (uint32_t)ne * (uint32_t)(p.x_rows * p.x_rowpitch) + (uint32_t)ncol * 256u;
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        int t = tile;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int d = t % p.D;
+        const int b = t / p.D;
+        const int h0 = ht * TH, w0 = wt * 8;
+        if (lane == 0) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), tx);
-          const uint32_t sx = smem_base + stage * p.stage_bytes;
-          for (int e = 0; e < ne; ++e) {
-            const e2e_centry_t ce = s_cents[e];
-            const int cb = b * p.src_cb[ce.src] + ce.blk;
-            if (HALO)
-              tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
-                          d + p.ivd + ce.dd, cb);
-            else if (p.merged)
-              tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
-                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
-            else
-              tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
-                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
-          }
-          // gradient tile: ncol / 8 channel blocks starting at block n0 / 8 (4-D box is sized for Nc:
-          // the last chunk may be narrower, so it is loaded block by block when it is)
-          if (ncol == Nc) {
-            tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb + (n0 >> 3));
-          } else {
-            for (int q = 0; q < (ncol >> 3); ++q)
-              tma_load_4d(sx + p.x_bytes + q * p.g_slab_bytes, &maps.x[E2E_MAX_SRC - 1], full_bar(stage), w0 * 4, h0, d,
-                          b * p.grad_cb + (n0 >> 3) + q);
-          }
-          if (++stage == S) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        const uint32_t sx = smem_base + stage * p.stage_bytes;
+        for (int e = lane; e < ne; e += 32) {
+          const e2e_centry_t ce = s_cents[e];
+          const int cb = b * p.src_cb[ce.src] + ce.blk;
+          if (HALO)
+            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
+                        d + p.ivd + ce.dd, cb);
+          else if (p.merged)
+            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
+                        h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
+          else
+            tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
+                        h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
+        }
+        // gradient tile: ncol / 8 channel blocks starting at block n0 / 8 (the 4-D box is sized for Nc:
+        // a narrower last chunk is loaded block by block)
+        if (ncol == Nc) {
+          if (lane == 31)
+            tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb + (n0 >> 3));
+        } else {
+          for (int q = lane; q < (ncol >> 3); q += 32)
+            tma_load_4d(sx + p.x_bytes + q * p.g_slab_bytes, &maps.x[E2E_MAX_SRC - 1], full_bar(stage), w0 * 4, h0, d,
+                        b * p.grad_cb + (n0 >> 3) + q);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
       // D=f32, A=B=bf16, A and B MN-major, N=ncol, M=128
@@ -862,6 +866,176 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
   }
 }
 
+
+// -------------------------------------------------------------------------------------
+// "g-shift" weight-gradient kernel for narrow layers (Npad <= 48): the tap shift is applied to the
+// GRADIENT operand instead of x,
+//     dW[kh,kw][e][n] = sum_u  x[u][e] * g[u - (kh-1, kw-1)][n],
+// so one unshifted x tile (A, M = 16 entries x 8 ch) is multiplied against the three kw-shifted copies
+// of the haloed gradient window stacked along N (B, N = 3 * Npad, copies loaded by three TMA boxes
+// into [kw][blk][rows][8 vox]) -- 3 MMAs (one per kh: a row offset of the B start address) of N = 144
+// instead of 9 MMAs of N = 48 per 16 voxels.  The SS-mode MMA is bound by shared-memory operand
+// reads (ncu: l1tex__data_pipe_tc_wavefronts_mem_shared at 79 % of peak in wgrad_tc_kernel); this
+// form reads A once per 3 taps: 68 instead of 132 wavefronts per (16 voxels x 9 taps).
+// 3 accumulators (kh) x 3*Npad columns live in TMEM across all voxel tiles of the CTA.
+// Tile = 8 (H) x 8 (W) voxels; jobs = (16-entry group) x (voxel split).
+// -------------------------------------------------------------------------------------
+struct WgsParams {
+  int B, D, H, W;
+  int n_cent, Npad, ivd;
+  int tiles_h, tiles_w, n_tiles;
+  int n_groups, splits, tiles_per_split;
+  int x_slab_bytes, g_slab_bytes, x_bytes, stage_bytes, stages;
+  int src_cb[E2E_MAX_SRC];
+  int grad_cb;
+  const e2e_centry_t* cents;
+  const e2e_tap_t* taps;
+  float* dwp;
+};
+
+constexpr int GS_TH = 8;                    // tile rows
+constexpr int GS_WROWS = GS_TH + 2;         // gradient window rows (H halo)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__ WgMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[20];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ e2e_centry_t s_cents[16];
+  __shared__ int s_tap_of[9];               // [kh * 3 + kw] -> tap index of the plan
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Npad = p.Npad, N3 = 3 * p.Npad, S = p.stages;
+  int job = blockIdx.x;
+  const int split = job % p.splits;
+  const int mg = job / p.splits;
+  const int e0 = mg * 16;
+  const int ne = min(16, p.n_cent - e0);
+  const int tile_lo = split * p.tiles_per_split;
+  const int tile_hi = min(p.n_tiles, tile_lo + p.tiles_per_split);
+  const int my_tiles = tile_hi - tile_lo;
+
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
+  const uint32_t done_bar = smem_u32(&bars[16]);
+
+  if (threadIdx.x < ne) s_cents[threadIdx.x] = p.cents[e0 + threadIdx.x];
+  if (threadIdx.x < 9) {
+    const e2e_tap_t t = p.taps[threadIdx.x];
+    s_tap_of[(t.dh + 1) * 3 + (t.dw + 1)] = threadIdx.x;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+  if (my_tiles > 0) {
+    if (warp == 0) {
+      // producer WARP: lane 0 waits for the stage and arms the barrier, then lanes 0..ne-1 issue the x
+      // boxes and lanes 16..18 the three gradient copies in parallel (19 TMA issues from one thread
+      // per 64-voxel tile could not keep up with 12 MMAs)
+      int stage = 0, phase = 0;
+      const uint32_t tx = (uint32_t)ne * (uint32_t)(GS_TH * 128) + 3u * (uint32_t)(Npad >> 3) * (uint32_t)p.g_slab_bytes;
+      e2e_centry_t ce = s_cents[lane < ne ? lane : 0];
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        int t = tile;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h; t /= p.tiles_h;
+        const int d = t % p.D;
+        const int b = t / p.D;
+        const int h0 = ht * GS_TH, w0 = wt * 8;
+        if (lane == 0) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), tx);
+        }
+        __syncwarp();
+        const uint32_t sx = smem_base + stage * p.stage_bytes;
+        if (lane < ne) {
+          tma_load_4d(sx + lane * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), w0 * 4, h0, d + p.ivd + ce.dd,
+                      b * p.src_cb[ce.src] + ce.blk);
+        } else if (lane >= 16 && lane < 19) {
+          // three kw-shifted copies of the haloed gradient window: copy kw holds g[., w - (kw - 1)]
+          const int kw = lane - 16;
+          tma_load_4d(sx + p.x_bytes + kw * (Npad >> 3) * p.g_slab_bytes, &maps.g, full_bar(stage),
+                      (w0 - (kw - 1)) * 4, h0 - 1, d, b * p.grad_cb);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1) {
+      // D=f32, A=B=bf16, A and B MN-major, N = 3*Npad, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
+      int stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sx = smem_base + stage * p.stage_bytes;
+          const uint32_t sg = sx + p.x_bytes;
+          const uint64_t a0 = make_desc(sx, 128, p.x_slab_bytes);
+          const uint64_t b0 = make_desc(sg, 128, p.g_slab_bytes);
+          const uint32_t a_hi = (uint32_t)(a0 >> 32), b_hi = (uint32_t)(b0 >> 32);
+          const uint32_t a_lo0 = (uint32_t)a0, b_lo0 = (uint32_t)b0;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int k = 0; k < GS_TH / 2; ++k)
+              // x rows 2k, 2k+1 of the tile  x  gradient window rows 2k + 2 - kh, +1 (row = 128 B = 8 units)
+              tc_mma_f16_lh(tmem_base + (uint32_t)(kh * N3), a_lo0 + (uint32_t)(2 * k * 8), a_hi,
+                            b_lo0 + (uint32_t)((2 * k + 2 - kh) * 8), b_hi, idesc, (it | k) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) tc_commit(done_bar);
+      __syncwarp();
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;             // accumulator row = (entry r/8, channel r%8)
+      const int el = r >> 3, j = r & 7;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int e = e0 + el;
+      const bool valid = el < ne;
+      for (int kh = 0; kh < 3; ++kh) {
+        for (int kw = 0; kw < 3; ++kw) {
+          const int t = s_tap_of[kh * 3 + kw];
+          float* base = p.dwp + ((size_t)(((e >> 1) * 9 + t) * 2 + (e & 1)) * Npad) * 8 + j;
+          const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * N3 + kw * Npad);
+          for (int c = 0; c < Npad; c += 16) {
+            uint32_t v[16];
+            tc_ld16(acc + c, v);
+            tc_wait_ld();
+            if (valid) {
+#pragma unroll
+              for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
 }  // namespace
 
 // 1: stride-1 3x3 halo form, 2: 1-tap point form, 0: not served
@@ -879,6 +1053,69 @@ int e2e_wgrad_tc_supported(const e2e_wgrad_t* p) {
   return 0;
 }
 
+static int wgrad_gshift_launch(const e2e_wgrad_t* g, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t st) {
+  WgsParams p{};
+  p.B = g->B; p.D = g->Do; p.H = g->Ho; p.W = g->Wo;
+  p.n_cent = g->n_cent; p.Npad = g->Npad; p.ivd = g->ivd;
+  p.tiles_h = (p.H + GS_TH - 1) / GS_TH;
+  p.tiles_w = (p.W + 7) / 8;
+  p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  p.n_groups = (g->n_cent + 15) / 16;
+  p.x_slab_bytes = GS_TH * 128;
+  p.g_slab_bytes = GS_WROWS * 128;
+  p.x_bytes = 16 * p.x_slab_bytes;
+  p.stage_bytes = (p.x_bytes + 3 * (g->Npad / 8) * p.g_slab_bytes + 127) / 128 * 128;
+  int stages = SMEM_BUDGET / p.stage_bytes;
+  if (stages > 6) stages = 6;
+  p.stages = stages;
+  int splits = e2e_num_sms() / p.n_groups;
+  if (splits > p.n_tiles) splits = p.n_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+  splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.splits = splits;
+  p.cents = g->cents; p.taps = g->taps; p.dwp = g->dwp; p.grad_cb = g->grad_cb;
+  WgMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+    const int si = i < g->n_src ? i : 0;
+    p.src_cb[i] = g->src_cb[si];
+    cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+    cuuint32_t box[4] = {32, (cuuint32_t)GS_TH, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("wgrad_gshift: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
+      return E2E_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.W * p.H * 16, (cuuint64_t)p.W * p.H * p.D * 16};
+    cuuint32_t box[4] = {32, (cuuint32_t)GS_WROWS, 1, (cuuint32_t)(g->Npad / 8)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps.g, CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->grad), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("wgrad_gshift: cuTensorMapEncodeTiled failed with %d (grad)", (int)r);
+      return E2E_ERR_CUDA;
+    }
+  }
+  const int smem_bytes = p.stages * p.stage_bytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    E2E_CUDA(cudaFuncSetAttribute(wgrad_gshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
+    attr_done = true;
+  }
+  wgrad_gshift_kernel<<<p.n_groups * p.splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+  E2E_LAUNCHED("wgrad_gshift");
+  return E2E_OK;
+}
+
 int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   const int form = e2e_wgrad_tc_supported(g);
   if (!form) {
@@ -890,6 +1127,11 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   if (!encode) {
     e2e_set_error("wgrad_tc: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return E2E_ERR_CUDA;
+  }
+  {
+    static int allow = -1;
+    if (allow < 0) { const char* e = getenv("E2E_TC_GSHIFT"); allow = e ? atoi(e) : 1; }
+    if (halo && allow && g->Npad <= 48 && g->n_src <= E2E_MAX_SRC) return wgrad_gshift_launch(g, encode, st);
   }
   WgParams p{};
   p.B = g->B; p.D = g->Do; p.H = g->Ho; p.W = g->Wo;
