@@ -45,6 +45,8 @@ struct TcParams {
   int rows;                        // window rows per slab: 18 (halo) or 16 (point)
   int need_bounds;                 // destination offsets / strides can leave the destination grid
   int merged;                      // source maps are 4-D with the merged (W, channel) inner dimension
+  int serial_prod;                 // halo form: one thread issues all TMA ops of a stage (A/B test)
+  int pps;                         // K pairs (16 channels each) per pipeline stage
   int poll;                        // E2E_TC_POLL: 0 all lanes poll, 1 one lane, 2 one lane + backoff
   int b_res;                       // packed weights of the CTA's (fixed) column chunk stay resident in smem
   int b_region_bytes;              // size of that region (then the A stages follow)
@@ -278,51 +280,76 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;     // TMA destinations need 128 B; keep 1 KB
 
   if (warp == 0) {
-    // ================================================= TMA producer
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      const uint32_t txa = 2u * (uint32_t)p.rows * (uint32_t)rowpitch;
-      const int nwork = p.n_tiles * p.n_chunks;
-      if (p.b_res && (int)blockIdx.x < nwork) {
-        // resident mode: gridDim.x is a multiple of n_chunks, so this CTA only ever sees one chunk;
-        // its whole packed operand [pair][tap][2][npad][8] is fetched once
-        const int ch = blockIdx.x % p.n_chunks;
-        const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
-        mbar_expect_tx(bfull_bar, bbytes * (uint32_t)npairs);
-        for (int pr = 0; pr < npairs; ++pr)
-          bulk_copy_g2s(smem_base + pr * bbytes, p.wpacked[ch] + (size_t)pr * (bbytes / 2), bbytes, bfull_bar);
-      }
-      for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
-        int t = work / p.n_chunks;
-        const int ch = work - t * p.n_chunks;
-        const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
-        const bf16* wsrc = p.wpacked[ch];
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h; t /= p.tiles_h;
-        const int d = t % p.D;
-        const int b = t / p.D;
-        const int h0 = ht * TH, w0 = wt * 8 * MS;
-        for (int pr = 0; pr < npairs; ++pr) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), p.b_res ? txa : txa + bbytes);
-          const uint32_t sa = smem_base + p.b_region_bytes + stage * p.stage_bytes;
+    // ================================================= TMA producer WARP: lane 0 waits for the stage and
+    // arms its barrier; then lanes 0 .. 2*np-1 issue the A slabs of the stage's np K pairs and lanes
+    // 16 .. 16+np-1 their packed-weight copies, in parallel (a single issuing thread cannot keep up
+    // with the short MMA bursts of the 1-tap form)
+    int stage = 0, phase = 0;
+    const uint32_t txa = 2u * (uint32_t)p.rows * (uint32_t)rowpitch;
+    const int nwork = p.n_tiles * p.n_chunks;
+    const int pps = p.pps;
+    if (lane == 0 && p.b_res && (int)blockIdx.x < nwork) {
+      // resident mode: gridDim.x is a multiple of n_chunks, so this CTA only ever sees one chunk;
+      // its whole packed operand [pair][tap][2][npad][8] is fetched once
+      const int ch = blockIdx.x % p.n_chunks;
+      const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
+      mbar_expect_tx(bfull_bar, bbytes * (uint32_t)npairs);
+      for (int pr = 0; pr < npairs; ++pr)
+        bulk_copy_g2s(smem_base + pr * bbytes, p.wpacked[ch] + (size_t)pr * (bbytes / 2), bbytes, bfull_bar);
+    }
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      int t = work / p.n_chunks;
+      const int ch = work - t * p.n_chunks;
+      const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
+      const bf16* wsrc = p.wpacked[ch];
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int b = t / p.D;
+      const int h0 = ht * TH, w0 = wt * 8 * MS;
+      for (int pr0 = 0; pr0 < npairs; pr0 += pps) {
+        const int np = min(pps, npairs - pr0);
+        const uint32_t sa = smem_base + p.b_region_bytes + stage * p.stage_bytes;
+        if (HALO && p.serial_prod) {
+          if (lane == 0) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), p.b_res ? txa : txa + bbytes);
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const e2e_centry_t ce = s_cents[2 * pr + hf];
-            if (HALO)
+            for (int hf = 0; hf < 2; ++hf) {
+              const e2e_centry_t ce = s_cents[2 * pr0 + hf];
               tma_load_4d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
                           d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
-            else if (p.merged)
-              tma_load_4d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
-                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
-            else
-              tma_load_5d(sa + hf * p.a_slab_bytes, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
-                          h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+            }
+            if (!p.b_res)
+              bulk_copy_g2s(sa + p.a_stage_bytes, wsrc + (size_t)pr0 * (bbytes / 2), bbytes, full_bar(stage));
           }
-          if (!p.b_res)
-            bulk_copy_g2s(sa + p.a_stage_bytes, wsrc + (size_t)pr * (bbytes / 2), bbytes, full_bar(stage));
           if (++stage == S) { stage = 0; phase ^= 1; }
+          continue;
         }
+        if (lane == 0) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), (uint32_t)np * (p.b_res ? txa : txa + bbytes));
+        }
+        __syncwarp();
+        if (lane < 2 * np) {
+          const int i = lane >> 1, hf = lane & 1;
+          const e2e_centry_t ce = s_cents[2 * (pr0 + i) + hf];
+          const uint32_t dsta = sa + i * p.a_stage_bytes + hf * p.a_slab_bytes;
+          if (HALO)
+            tma_load_4d(dsta, &maps.m[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1, d + p.ivd + ce.dd,
+                        b * p.src_cb[ce.src] + ce.blk);
+          else if (p.merged)
+            tma_load_4d(dsta, &maps.m[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4, h0 * p.ish + p.ivh + ce.dh,
+                        d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+          else
+            tma_load_5d(dsta, &maps.m[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
+                        h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+        } else if (!p.b_res && lane >= 16 && lane < 16 + np) {
+          const int i = lane - 16;
+          bulk_copy_g2s(sa + pps * p.a_stage_bytes + i * p.b_stage_bytes, wsrc + (size_t)(pr0 + i) * (bbytes / 2), bbytes,
+                        full_bar(stage));
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -336,6 +363,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     for (int t = 0; t < NT; ++t) tapu[t] = (uint32_t)s_tapoff[t] >> 4;
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     const uint32_t a_stage_units = (uint32_t)p.a_stage_bytes >> 4;
+    const uint32_t b_stage_units = (uint32_t)p.b_stage_bytes >> 4;
     const uint32_t sa0 = (smem_base + (uint32_t)p.b_region_bytes) >> 4;
     const uint32_t sb0 = smem_base >> 4;
     const int nwork = p.n_tiles * p.n_chunks;
@@ -353,20 +381,25 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       mbar_wait_warp(tempty_bar(as), aphase ^ 1, 0, p.poll);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + (uint32_t)(as * MS * Npad);
-      for (int pr = 0; pr < npairs; ++pr) {
+      for (int pr0 = 0; pr0 < npairs; pr0 += p.pps) {
+        const int np = min(p.pps, npairs - pr0);
         mbar_wait_warp(full_bar(stage), phase, 0, p.poll);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units;
-          const uint32_t b_lo = p.b_res ? b_lo0 + sb0 + (uint32_t)pr * (uint32_t)(NT * 2) * (uint32_t)npc
-                                        : b_lo0 + sa0 + (uint32_t)stage * stage_units + a_stage_units;
-          const uint32_t first = pr ? 1u : 0u;
+          for (int i = 0; i < np; ++i) {
+            const int pr = pr0 + i;
+            const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units + (uint32_t)i * a_stage_units;
+            const uint32_t b_lo = p.b_res ? b_lo0 + sb0 + (uint32_t)pr * (uint32_t)(NT * 2) * (uint32_t)npc
+                                          : b_lo0 + sa0 + (uint32_t)stage * stage_units + (uint32_t)p.pps * a_stage_units +
+                                                (uint32_t)i * b_stage_units;
+            const uint32_t first = pr ? 1u : 0u;
 #pragma unroll
-          for (int t = 0; t < NT; ++t) {
+            for (int t = 0; t < NT; ++t) {
 #pragma unroll
-            for (int j = 0; j < MS; ++j)
-              tc_mma_f16_lh(acc0 + (uint32_t)(j * Npad), a_lo + tapu[t] + (uint32_t)(j * 8), a_hi,
-                            b_lo + (uint32_t)t * b_tap_units, b_hi, idesc, t ? 1u : first);
+              for (int j = 0; j < MS; ++j)
+                tc_mma_f16_lh(acc0 + (uint32_t)(j * Npad), a_lo + tapu[t] + (uint32_t)(j * 8), a_hi,
+                              b_lo + (uint32_t)t * b_tap_units, b_hi, idesc, t ? 1u : first);
+            }
           }
           tc_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
         }
@@ -563,21 +596,41 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
   p.a_slab_bytes = (p.rows * rowpitch + 127) / 128 * 128;
   p.a_stage_bytes = 2 * p.a_slab_bytes;
   p.b_stage_bytes = n_taps * 2 * npmax * 16;
-  p.stage_bytes = (p.a_stage_bytes + p.b_stage_bytes + 127) / 128 * 128;
   int grid = e2e_num_sms();
-  // resident weights: the whole packed operand of a chunk (all K pairs) fits beside >= 3 A stages
   const int npairs = g->n_cent / 2;
+  // K pairs per pipeline stage: 1 for the halo form (9*m MMAs per pair), up to 4 for the 1-tap form
+  // (m MMAs per pair: the barrier hand-shake would dominate)
+  int pps = halo ? 1 : 4;
+  {
+    static int force = -1;
+    if (force < 0) { const char* e = getenv("E2E_TC_PPS"); force = e ? atoi(e) : 0; }
+    if (force >= 1 && force <= 8) pps = force;
+  }
+  if (pps > npairs) pps = npairs;
+  {
+    static int sp = -1;
+    if (sp < 0) { const char* e = getenv("E2E_TC_SERIAL"); sp = e ? atoi(e) : 1; }
+    p.serial_prod = (halo && pps == 1) ? sp : 0;
+  }
+  // resident weights: the whole packed operand of a chunk (all K pairs) fits beside >= 3 A stages
   p.b_res = 0; p.b_region_bytes = 0;
   {
     const int region = (npairs * p.b_stage_bytes + 1023) / 1024 * 1024;
     const int gres = (grid / n) * n;
     static int allow = -1;
     if (allow < 0) { const char* e = getenv("E2E_TC_BRES"); allow = e ? atoi(e) : 1; }
-    if (allow && region <= 112 * 1024 && gres >= n && region + 3 * p.a_stage_bytes <= SMEM_BUDGET) {
-      p.b_res = 1; p.b_region_bytes = region; p.stage_bytes = p.a_stage_bytes; grid = gres;
+    if (allow && region <= 112 * 1024 && gres >= n && region + 3 * pps * p.a_stage_bytes <= SMEM_BUDGET) {
+      p.b_res = 1; p.b_region_bytes = region; grid = gres;
     }
   }
-  int stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
+  int stages;
+  for (;;) {
+    p.stage_bytes = p.b_res ? pps * p.a_stage_bytes : (pps * (p.a_stage_bytes + p.b_stage_bytes) + 127) / 128 * 128;
+    stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
+    if (stages >= 3 || pps == 1) break;
+    --pps;
+  }
+  p.pps = pps;
   if (stages > 8) stages = 8;
   if (stages < 2) {
     e2e_set_error("conv_tc_fwd: stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
