@@ -105,10 +105,12 @@ class SegmentationNetwork(NeuralNetwork):
         self._tile_shard = None         # (rank, world_size, process_group) or None
 
     # ------------------------------------------------------------------ multi-GPU tile sharding
-    def set_tile_sharding(self, rank: int = 0, world_size: int = 1, group=None):
-        """tiles[rank::world_size] are predicted here; the accumulators are summed with one
-        NCCL all-reduce before normalisation (option A)."""
-        self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group)
+    def set_tile_sharding(self, rank: int = 0, world_size: int = 1, group=None, result_on=None):
+        """tiles[rank::world_size] are predicted here; the accumulators are summed with one NCCL
+        collective before normalisation (option A).  result_on=None: all-reduce, every
+        rank returns the full (seg, softmax); result_on=r: reduce to rank r only (half the traffic),
+        the other ranks return (None, None)."""
+        self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group, result_on)
 
     @staticmethod
     def _shard_tiles(tiles, rank: int, world_size: int):
@@ -116,11 +118,16 @@ class SegmentationNetwork(NeuralNetwork):
         return list(tiles)[int(rank)::int(world_size)]
 
     @staticmethod
-    def _reduce_accumulators(agg, wsum, group=None):
-        """the one exchange step of sharded sliding-window inference: sum the per-rank accumulators"""
+    def _reduce_accumulators(agg, wsum, group=None, dst=None):
+        """the one exchange step of sharded sliding-window inference: sum the per-rank accumulators
+        (on every rank, or on rank `dst` only)"""
         import torch.distributed as dist
-        dist.all_reduce(agg, group=group)
-        dist.all_reduce(wsum, group=group)
+        if dst is None:
+            dist.all_reduce(agg, group=group)
+            dist.all_reduce(wsum, group=group)
+        else:
+            dist.reduce(agg, dst=dst, group=group)
+            dist.reduce(wsum, dst=dst, group=group)
 
     # ------------------------------------------------------------------ public API
     def predict_3D(self, x: np.ndarray, do_mirroring: bool, mirror_axes: Tuple[int, ...] = (0, 1, 2),
@@ -287,7 +294,12 @@ class SegmentationNetwork(NeuralNetwork):
                                 for (a, b, c) in grp])
             self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, grp)
         if shard is not None:
-            self._reduce_accumulators(agg, wsum, shard[2])
+            self._reduce_accumulators(agg, wsum, shard[2], shard[3])
+            if shard[3] is not None and shard[0] != shard[3]:
+                ev1.record()
+                torch.cuda.current_stream().synchronize()
+                self._last_num_tiles, self._last_tile_loop_ms = num_tiles, ev0.elapsed_time(ev1)
+                return None, None
 
         seg = self._finalize(agg, wsum)                       # agg now holds agg / wsum
         ev1.record()

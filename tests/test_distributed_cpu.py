@@ -73,7 +73,11 @@ def _fake_net(x):
     return np.stack([x[0], -x[0], 0.5 * x[0] * x[0]], 0).astype(np.float32)
 
 
-def _sharded_window(rank, world):
+def _sharded_window_root(rank, world):
+    return _sharded_window(rank, world, dst=0)
+
+
+def _sharded_window(rank, world, dst=None):
     from e2enet_medical_b200.network_architecture.neural_network import SegmentationNetwork
     from oracle import window as owin
     rs = np.random.RandomState(3)
@@ -91,7 +95,9 @@ def _sharded_window(rank, world):
         agg[:, a:a + patch[0], b:b + patch[1], c:c + patch[2]] += pr
         wsum[a:a + patch[0], b:b + patch[1], c:c + patch[2]] += gauss
     ta, tw = torch.from_numpy(agg), torch.from_numpy(wsum)
-    SegmentationNetwork._reduce_accumulators(ta, tw)
+    SegmentationNetwork._reduce_accumulators(ta, tw, None, dst)     # all-reduce, or reduce to rank dst
+    if dst is not None and rank != dst:
+        return None, [tuple(t) for t in mine], len(tiles)
     return (ta / tw).numpy(), [tuple(t) for t in mine], len(tiles)
 
 
@@ -108,3 +114,14 @@ def test_sharded_sliding_window_gloo():
                                     use_gaussian=True)[:2]
     np.testing.assert_allclose(p0, probs, rtol=2e-6, atol=1e-7)
     assert (p0.argmax(0) == seg).mean() > 0.9999
+
+
+def test_sharded_sliding_window_reduce_to_root_gloo():
+    from oracle import window as owin
+    (p0, t0, n), (p1, t1, _) = _run(_sharded_window_root)
+    assert p1 is None and len(t0) + len(t1) == n
+    rs = np.random.RandomState(3)
+    vol = rs.randn(1, 20, 30, 26).astype(np.float32)
+    _, probs = owin.predict_tiled(lambda t: _fake_net(t), vol, 3, (8, 16, 12), 0.5, do_mirroring=False,
+                                  use_gaussian=True)[:2]
+    np.testing.assert_allclose(p0, probs, rtol=2e-6, atol=1e-7)
