@@ -291,18 +291,20 @@ def inference_leg(dev, world, rank, args):
     net.eval()
     net.do_ds = False
     net.inference_apply_nonlin = softmax_helper
-    net.set_tile_sharding(rank, world, None, 0 if world > 1 else None)   # one NCCL reduce to rank 0
+    # N > 1: slab ownership -- contiguous tile ranges per rank, neighbour exchange of the overlap planes,
+    # every rank finalises and returns the x-slab it owns
+    net.set_tile_sharding(rank, world, None, "slab" if world > 1 else None)
     net.pinned_output_buffers = True       # results land in reused pinned host buffers (documented opt-in)
     vol = np.random.RandomState(0).randn(1, *vol_shape).astype(np.float32)
     small = vol[:, :64, :160, :320].copy()                       # warm-up: 3 tiles
     net.predict_3D(small, False, (0, 1, 2), True, 0.5, PATCH, None, True, "constant", None, True, False, True)
-    net._pinned_out = {"seg": torch.empty(vol_shape, dtype=torch.int64, pin_memory=True),
-                       "probs": torch.empty((16,) + vol_shape, dtype=torch.float32, pin_memory=True)}
+    if world == 1:
+        net._pinned_out = {"seg": torch.empty(vol_shape, dtype=torch.int64, pin_memory=True),
+                           "probs": torch.empty((16,) + vol_shape, dtype=torch.float32, pin_memory=True)}
+    else:
+        # un-timed full-size pass: allocates the slab-sized pinned buffers and warms NCCL's P2P channels
+        net.predict_3D(vol, False, (0, 1, 2), True, 0.5, PATCH, None, True, "constant", None, True, False, True)
     if world > 1:
-        # NCCL warm-up at the real message size (channel / buffer set-up is lazy per size class)
-        warm = torch.zeros((16,) + vol_shape, dtype=torch.float32, device=dev)
-        dist.reduce(warm, dst=0)
-        del warm
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -313,6 +315,10 @@ def inference_leg(dev, world, rank, args):
     # device-only time of the tile loop (volume resident, results left on the device)
     dev_ms = net._last_tile_loop_ms
     n_tiles = net._last_num_tiles
+    pe = net._last_phase_events
+    phases = {"tile_loop_ms": pe[0].elapsed_time(pe[1])}
+    if len(pe) > 2:
+        phases["exchange_ms_incl_wait_for_neighbours"] = pe[1].elapsed_time(pe[2])
     if world > 1:
         t = torch.tensor([dt, dev_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -321,13 +327,15 @@ def inference_leg(dev, world, rank, args):
     return {"metric": "inference voxels/s", "value": nvox / (dev_ms / 1e3), "unit": "voxels/s",
             "e2e": {"value": nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(vol.nbytes),
                     "d2h_bytes_per_step": int(seg.nbytes + probs.nbytes) if seg is not None else 0},
-            "ms_per_volume": dev_ms, "e2e_ms_per_volume": dt * 1e3, "tiles": n_tiles,
+            "ms_per_volume": dev_ms, "e2e_ms_per_volume": dt * 1e3, "tiles": n_tiles, "rank0_phases": phases,
             "tiles_per_s": n_tiles / (dev_ms / 1e3),
             "config": {"workload": "E2ENet AMOS-CT-shaped sliding-window inference: %dx%dx%d volume, 16 classes, patch "
                                    "64x160x160, step 0.5, gaussian, no mirroring (BASELINE.json configs[2]); value = "
                                    "tile loop + reduce + finalise on resident data, e2e = predict_3D NumPy->NumPy (pinned_output_buffers=True)"
                                    % vol_shape, "tiles_sharded_over": world,
-                       "exchange": "none" if world == 1 else "one NCCL reduce of the fp32 accumulators to rank 0"}}
+                       "exchange": "none" if world == 1 else
+                       "slab ownership: NCCL point-to-point exchange of the overlap planes between neighbouring "
+                       "ranks; every rank returns its own x-slab"}}
 
 
 def main():

@@ -109,13 +109,70 @@ class SegmentationNetwork(NeuralNetwork):
         """tiles[rank::world_size] are predicted here; the accumulators are summed with one NCCL
         collective before normalisation (option A).  result_on=None: all-reduce, every
         rank returns the full (seg, softmax); result_on=r: reduce to rank r only (half the traffic),
-        the other ranks return (None, None)."""
+        the other ranks return (None, None); result_on="slab": slab ownership (option B) -- ranks
+        predict contiguous x-major tile ranges into accumulators that cover only their own x-extent,
+        exchange just the overlap planes with their neighbours and return the (seg, softmax) of the
+        x-slab they own (`self._last_slab` = (x_lo, x_hi) in un-padded coordinates)."""
         self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group, result_on)
 
     @staticmethod
     def _shard_tiles(tiles, rank: int, world_size: int):
         """round-robin partition of the sliding-window tiles over ranks (every tile exactly once)"""
         return list(tiles)[int(rank)::int(world_size)]
+
+    @staticmethod
+    def _slab_plan(tiles, px: int, X: int, world_size: int):
+        """slab ownership (SURVEY 8(e) option B).  `tiles` is x-major; rank r predicts the contiguous
+        chunk tiles[cut[r]:cut[r+1]] and OWNS the x-planes [bx[r], bx[r+1]) with bx[r] = x-origin of its
+        first tile (bx[0] = 0, bx[world] = X).  Its tiles reach up to hi[r] = last x-origin + px, so
+        the planes [bx[r+1], hi[r]) are contributions to the next rank(s) -- the only data exchanged."""
+        n = len(tiles)
+        cut = [(r * n) // world_size for r in range(world_size + 1)]
+        bx, hi = [], []
+        for r in range(world_size):
+            mine = tiles[cut[r]:cut[r + 1]]
+            bx.append(int(mine[0][0]) if mine else None)
+            hi.append(int(mine[-1][0]) + px if mine else None)
+        # ranks without tiles own nothing; fill boundaries monotonically
+        nxt = X
+        for r in range(world_size - 1, -1, -1):
+            if bx[r] is None:
+                bx[r], hi[r] = nxt, nxt
+            nxt = bx[r]
+        bx[0] = 0
+        bx.append(X)
+        return cut, bx, hi
+
+    @staticmethod
+    def _slab_exchange(agg, wsum, rank: int, bx, hi, group=None):
+        """agg (C, hi[rank]-bx[rank], Y, Z) / wsum hold this rank's contributions on x in [bx[rank], hi[rank]).
+        Sends the planes owned by later ranks to them, receives earlier ranks' contributions to the own slab
+        and adds them.  Point-to-point over NCCL (NVLink/NVSwitch: all pairs move concurrently)."""
+        import torch.distributed as dist
+        world = len(bx) - 1
+        ops_, keep = [], []
+        x0 = bx[rank]
+        for q in range(rank + 1, world):                  # sends: planes [max(bx[q], x0), min(bx[q+1], hi[rank]))
+            lo, up = max(bx[q], x0), min(bx[q + 1], hi[rank])
+            if up > lo:
+                a = agg[:, lo - x0:up - x0].contiguous()
+                w = wsum[lo - x0:up - x0].contiguous()
+                keep += [a, w]
+                ops_ += [dist.P2POp(dist.isend, a, q, group), dist.P2POp(dist.isend, w, q, group)]
+        recvs = []
+        for s_ in range(rank):                            # receives: earlier ranks reaching into the own slab
+            lo, up = max(bx[rank], bx[s_]), min(bx[rank + 1], hi[s_])
+            if up > lo and hi[s_] > bx[rank]:
+                a = torch.empty((agg.shape[0], up - lo) + tuple(agg.shape[2:]), dtype=agg.dtype, device=agg.device)
+                w = torch.empty((up - lo,) + tuple(wsum.shape[1:]), dtype=wsum.dtype, device=wsum.device)
+                recvs.append((lo, up, a, w))
+                ops_ += [dist.P2POp(dist.irecv, a, s_, group), dist.P2POp(dist.irecv, w, s_, group)]
+        if ops_:
+            for req in dist.batch_isend_irecv(ops_):
+                req.wait()
+        for lo, up, a, w in recvs:
+            agg[:, lo - x0:up - x0] += a
+            wsum[lo - x0:up - x0] += w
 
     @staticmethod
     def _reduce_accumulators(agg, wsum, group=None, dst=None):
@@ -278,13 +335,20 @@ class SegmentationNetwork(NeuralNetwork):
             gauss = torch.from_numpy(self._gaussian_3d).to(dev, non_blocking=True).contiguous()
 
         vol = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(dev, non_blocking=True)
-        agg = torch.zeros((self.num_classes,) + tuple(data_shape[1:]), dtype=torch.float32, device=dev)
-        wsum = torch.zeros(tuple(data_shape[1:]), dtype=torch.float32, device=dev)
-
         tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
         shard = self._tile_shard
-        if shard is not None:
+        slab = None
+        xoff, xext = 0, data_shape[1]
+        if shard is not None and shard[3] == "slab":
+            cut, bx, hi = self._slab_plan(tiles, patch_size[0], data_shape[1], shard[1])
+            slab = (bx, hi)
+            tiles = tiles[cut[shard[0]]:cut[shard[0] + 1]]
+            xoff, xext = bx[shard[0]], max(hi[shard[0]], bx[shard[0] + 1]) - bx[shard[0]]
+        elif shard is not None:
             tiles = self._shard_tiles(tiles, shard[0], shard[1])
+        # accumulators cover x in [xoff, xoff + xext) (the whole padded volume unless slab mode)
+        agg = torch.zeros((self.num_classes, xext) + tuple(data_shape[2:]), dtype=torch.float32, device=dev)
+        wsum = torch.zeros((xext,) + tuple(data_shape[2:]), dtype=torch.float32, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         nb = max(1, int(getattr(self, "tile_batch", 4)))      # tiles per forward (exact: per-sample norm)
@@ -292,19 +356,46 @@ class SegmentationNetwork(NeuralNetwork):
             grp = tiles[i0:i0 + nb]
             tile = torch.stack([vol[:, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]]
                                 for (a, b, c) in grp])
-            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum, grp)
-        if shard is not None:
+            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum,
+                                  [(a - xoff, b, c) for (a, b, c) in grp])
+        ev_t = torch.cuda.Event(enable_timing=True)
+        ev_t.record()
+        self._last_phase_events = (ev0, ev_t)
+        if slab is not None:
+            bx, hi = slab
+            self._slab_exchange(agg, wsum, shard[0], bx, hi, shard[2])
+            ev_r = torch.cuda.Event(enable_timing=True)
+            ev_r.record()
+            self._last_phase_events = (ev0, ev_t, ev_r)
+            own = bx[shard[0] + 1] - bx[shard[0]]
+            agg, wsum = agg[:, :own].contiguous(), wsum[:own].contiguous()      # the planes this rank owns
+        elif shard is not None:
             self._reduce_accumulators(agg, wsum, shard[2], shard[3])
+            ev_r = torch.cuda.Event(enable_timing=True)
+            ev_r.record()
+            self._last_phase_events = (ev0, ev_t, ev_r)
             if shard[3] is not None and shard[0] != shard[3]:
                 ev1.record()
                 torch.cuda.current_stream().synchronize()
                 self._last_num_tiles, self._last_tile_loop_ms = num_tiles, ev0.elapsed_time(ev1)
                 return None, None
 
+        if agg.shape[1] == 0:                                 # slab mode: this rank owns no planes
+            ev1.record()
+            torch.cuda.current_stream().synchronize()
+            self._last_num_tiles, self._last_tile_loop_ms, self._last_slab = num_tiles, ev0.elapsed_time(ev1), (0, 0)
+            return None, None
         seg = self._finalize(agg, wsum)                       # agg now holds agg / wsum
         ev1.record()
         self._last_tile_events, self._last_num_tiles = (ev0, ev1), num_tiles
-        sp = tuple(slicer[1:])
+        sp = list(slicer[1:])
+        if slab is not None:
+            # un-pad: intersect the owned planes [xoff, xoff + own) with the un-padded x-range
+            lo = max(sp[0].start, xoff)
+            up = min(sp[0].stop, xoff + agg.shape[1])
+            self._last_slab = (lo - sp[0].start, max(up, lo) - sp[0].start)
+            sp[0] = slice(lo - xoff, max(up, lo) - xoff)
+        sp = tuple(sp)
         probs = agg[(slice(None),) + sp]
         seg = seg[sp]
         if regions_class_order is None:

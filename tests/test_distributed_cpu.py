@@ -125,3 +125,47 @@ def test_sharded_sliding_window_reduce_to_root_gloo():
     _, probs = owin.predict_tiled(lambda t: _fake_net(t), vol, 3, (8, 16, 12), 0.5, do_mirroring=False,
                                   use_gaussian=True)[:2]
     np.testing.assert_allclose(p0, probs, rtol=2e-6, atol=1e-7)
+
+
+def _slab_window(rank, world):
+    """slab ownership (SURVEY 8(e) option B): contiguous tile ranges, local accumulators over the own
+    x-extent only, neighbour exchange of the overlap planes"""
+    from e2enet_medical_b200.network_architecture.neural_network import SegmentationNetwork as S
+    from oracle import window as owin
+    rs = np.random.RandomState(3)
+    vol = rs.randn(1, 40, 30, 26).astype(np.float32)
+    patch = (8, 16, 12)
+    steps = owin.compute_steps(patch, vol.shape[1:], 0.5)
+    gauss = owin.gaussian_map(patch)
+    tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
+    cut, bx, hi = S._slab_plan(tiles, patch[0], vol.shape[1], world)
+    mine = tiles[cut[rank]:cut[rank + 1]]
+    x0, ext = bx[rank], max(hi[rank], bx[rank + 1]) - bx[rank]
+    agg = np.zeros((3, ext) + vol.shape[2:], np.float32)
+    wsum = np.zeros((ext,) + vol.shape[2:], np.float32)
+    for (a, b, c) in mine:
+        t = vol[:, a:a + patch[0], b:b + patch[1], c:c + patch[2]]
+        pr = owin.softmax0(_fake_net(t)) * gauss
+        agg[:, a - x0:a - x0 + patch[0], b:b + patch[1], c:c + patch[2]] += pr
+        wsum[a - x0:a - x0 + patch[0], b:b + patch[1], c:c + patch[2]] += gauss
+    ta, tw = torch.from_numpy(agg), torch.from_numpy(wsum)
+    S._slab_exchange(ta, tw, rank, bx, hi)
+    own = bx[rank + 1] - bx[rank]
+    return (ta[:, :own] / tw[:own]).numpy(), (bx[rank], bx[rank + 1]), len(mine), len(tiles)
+
+
+def test_slab_sharded_sliding_window_gloo():
+    from oracle import window as owin
+    for world in (2, 3):
+        out = _run(_slab_window, world)
+        assert sum(o[2] for o in out) == out[0][3], "every tile predicted exactly once"
+        rs = np.random.RandomState(3)
+        vol = rs.randn(1, 40, 30, 26).astype(np.float32)
+        _, probs = owin.predict_tiled(lambda t: _fake_net(t), vol, 3, (8, 16, 12), 0.5, do_mirroring=False,
+                                      use_gaussian=True)[:2]
+        covered = 0
+        for p_, (lo, up), _, _ in out:
+            assert lo == covered, "owned slabs tile the x axis"
+            covered = up
+            np.testing.assert_allclose(p_, probs[:, lo:up], rtol=2e-6, atol=1e-7)
+        assert covered == vol.shape[1]
