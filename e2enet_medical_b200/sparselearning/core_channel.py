@@ -258,8 +258,13 @@ class Masking(object):
         print(f"Overall sparsity {total_nonzero / total_params}")
 
     # ------------------------------------------------------------------ step (reference :290-317)
-    def step(self):
-        self.apply_mask()
+    def step(self, _mask_already_applied=False):
+        """reference :290-317.  `_mask_already_applied` (extension, default off): the apply_mask of this
+        iteration already ran on the device -- it is part of a replayed CUDA graph of the training step
+        (training.TrainStep.enable_graph) -- so only the host bookkeeping and, on update iterations,
+        the prune / regrow run here."""
+        if not _mask_already_applied:
+            self.apply_mask()
         if self.decay_flag:
             self.death_rate_decay.step()
             self.death_rate = self.death_rate_decay.get_dr()

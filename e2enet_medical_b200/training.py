@@ -123,6 +123,7 @@ class TrainStep(object):
         self.mask.add_module(self.network, sparse_init='uniform', density=density)
         self.world_size = world_size
         self._flat = None
+        self._graph = None
         # the trainer's loss (nnUNetTrainer_simple.py:100,200-215): fused statistics kernels, or plain torch
         if fused_loss:
             from .loss_functions import DC_and_CE_loss, MultipleOutputLoss2
@@ -135,7 +136,8 @@ class TrainStep(object):
         """data-parallel gradient mean over NCCL (one flat bucket; grads are ~95 MB fp32)."""
         allreduce_mean_grads(list(self.network.parameters()), self.world_size)
 
-    def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
+    def _device_step(self, data, targets):
+        """everything of one iteration that runs on the device (no host synchronisation)"""
         self.optimizer.zero_grad()
         output = self.network(data)
         l = self.loss(output, targets)
@@ -144,5 +146,48 @@ class TrainStep(object):
             self._allreduce_grads()
         torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
         self.optimizer.step()
-        self.mask.step()
         return l.detach()
+
+    def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
+        if self._graph is not None:
+            return self._graph_step(data, targets)
+        l = self._device_step(data, targets)
+        self.mask.step()
+        return l
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def enable_graph(self, data: torch.Tensor, targets: Sequence[torch.Tensor], warmup: int = 3):
+        """captures one training iteration (forward, loss, backward, gradient all-reduce, clip, SGD,
+        apply_mask: ~750 kernel launches) into ONE CUDA graph.  Later `step()` calls copy the batch into
+        the static input buffers and replay it; Masking's host bookkeeping and the rare prune / regrow
+        update stay eager.  Shapes must not change afterwards."""
+        assert self._graph is None
+        self._static_data = data.clone()
+        self._static_targets = [t.clone() for t in targets]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):            # lazy state: momentum buffers, plans, tensor maps, pack registry
+                self._device_step(self._static_data, self._static_targets)
+                self.mask.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        from . import _lib
+        self.optimizer.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            self._static_loss = self._device_step(self._static_data, self._static_targets)
+            self.mask.apply_mask()
+        self.graph_launches = _lib.launch_count() - n0       # kernels of libe2enet_b200.so inside one replay
+        self._graph = graph                                   # (capture records, it does not execute)
+        return self
+
+    def _graph_step(self, data, targets):
+        if data.data_ptr() != self._static_data.data_ptr():
+            self._static_data.copy_(data, non_blocking=True)
+            for s_, t in zip(self._static_targets, targets):
+                s_.copy_(t, non_blocking=True)
+        self._graph.replay()
+        self.mask.step(_mask_already_applied=True)            # host bookkeeping; prune / regrow when due
+        return self._static_loss

@@ -579,3 +579,33 @@ def test_fused_ds_loss_vs_oracle(dev, batch_dice):
     assert abs(got.item() - ref.item()) < 2e-5 * max(1.0, abs(ref.item())), (got.item(), ref.item())
     for a, r in zip(dev_in, ref_in):
         assert rel(a.grad, r.grad) < 2e-4, rel(a.grad, r.grad)
+
+
+# ------------------------------------------------------------------------------ whole-step CUDA graph
+def test_train_step_cuda_graph_matches_eager(dev):
+    """one training iteration captured in a CUDA graph (forward, fused loss, backward, clip, SGD,
+    apply_mask) replays to the same loss trajectory and the same weights as eager execution (fp32
+    atomics in the split-K weight-gradient flush are the only source of difference)."""
+    from e2enet_medical_b200.training import POOLS, TrainStep, synthetic_batch
+    pools, patch = POOLS["hippo"], (40, 56, 40)
+    data, targets = synthetic_batch(1, 1, 3, patch, pools, seed=1)
+    data, targets = data.to(dev), [t.to(dev) for t in targets]
+    out = {}
+    for mode in ("eager", "graph"):
+        random.seed(0)
+        ts = TrainStep(1, 3, pools, patch, 0.2, 0.5, 4, dev, 1, seed=0, base=16)     # prune/regrow every 4 steps
+        if mode == "graph":
+            ts.enable_graph(data, targets, warmup=2)
+        else:
+            for _ in range(2):
+                ts.step(data, targets)
+        random.seed(5)
+        losses = [float(ts.step(data, targets)) for _ in range(6)]                   # crosses an update step
+        w = torch.cat([p.detach().flatten() for p in ts.network.parameters()]).double().cpu()
+        masks = {k: v.clone().cpu() for k, v in ts.mask.masks.items()}
+        out[mode] = (losses, w, masks, ts.mask.steps)
+        del ts
+    assert out["eager"][3] == out["graph"][3]
+    for a, b in zip(out["eager"][0], out["graph"][0]):
+        assert abs(a - b) < 2e-3 * abs(a), (out["eager"][0], out["graph"][0])
+    assert float((out["eager"][1] - out["graph"][1]).norm() / out["eager"][1].norm()) < 2e-2
