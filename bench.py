@@ -252,8 +252,7 @@ def run_ours(args):
     if rank != 0:
         if not args.no_inference:
             inference_leg(dev, world, rank, args)
-        if world > 1:
-            dist.destroy_process_group()
+        _finish_ranks(ts, world)
         return
     peaks = measured_peaks()
     value = BATCH * world * args.steps / (ms / 1e3)
@@ -294,8 +293,25 @@ def run_ours(args):
                                 "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x96x96 crop "
                                           "(0.18 patch), %d steps of %.1f s" % (n, dt)}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    _finish_ranks(ts, world)
+
+
+def _finish_ranks(ts, world):
+    """multi-rank teardown: a captured CUDA graph holds NCCL kernels of the process group, and destroying
+    the communicator under it can block forever -- drop the graph, synchronise, and leave without the
+    NCCL destructor (the processes are exiting anyway)"""
+    if world <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    ts._graph = None
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def inference_leg(dev, world, rank, args):
