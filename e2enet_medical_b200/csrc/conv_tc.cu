@@ -521,6 +521,200 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+
+// =====================================================================================
+// kw-stacked forward kernel for NARROW stride-1 3x3 layers (Cout <= 80).
+//
+// An SS-mode tcgen05.mma with M = 128, N = 48, K = 16 reads 4 KB of A and 1.5 KB of B from shared
+// memory for 24 cycles of math: ncu shows conv_tc_kernel on these layers at 71 % of the tensor core's
+// shared-memory read pipe and 27 % of its math pipe.  Here the three kw taps are stacked along N:
+//     D'[v][kw * Np + n] = sum_{kh, c}  X[v + (kh - 1) rows][c] * W[kh][kw][c][n]      (N = 3 * Np)
+//     out[h][w][n]       = D'[h][w - 1][0 * Np + n] + D'[h][w][1 * Np + n] + D'[h][w + 1][2 * Np + n]
+// so A is read once per THREE taps (3 MMAs of N = 144 per 16 channels instead of 9 of N = 48) and the
+// W shift happens in the epilogue as two lane shuffles: a tile is 4 (H) x 32 (W) positions, TMEM lane
+// = (row, w), one row per warp quadrant.  Lanes 0 and 31 only feed their neighbours, so tiles advance
+// by 30 in W.  The A window is [6 rows][32 voxels][8 ch] per 8-channel block (no W halo: row pitch
+// 512 B makes the 16 core matrices of the M tile contiguous, SBO = 128).  Packed weights
+// [pair][kh][2][3*Np][8] stay resident in shared memory; 4 K pairs per pipeline stage.
+// =====================================================================================
+constexpr int S3_TH = 4, S3_TW = 32, S3_ADV = 30, S3_ROWS = S3_TH + 2;
+constexpr int S3_SLAB = S3_ROWS * S3_TW * 16;      // 3072 B
+constexpr int S3_PPS = 4;
+constexpr int S3_EPI_WARPS = 8;
+constexpr int S3_THREADS = 64 + 32 * S3_EPI_WARPS;
+
+struct S3Params {
+  int B, D, H, W;
+  int n_cent, Np, N3, ivd;          // Np = padded Cout (multiple of 8), N3 = 3 * Np (multiple of 16)
+  int stages, acc_stages;
+  int tiles_h, tiles_w, n_tiles;
+  int b_region_bytes, stage_bytes;
+  int src_cb[E2E_MAX_SRC];
+  int dst_cb;
+  const e2e_centry_t* cents;
+  const bf16* wpacked;
+  bf16* dst;
+};
+
+__global__ void __launch_bounds__(S3_THREADS, 1)
+conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[32];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ e2e_centry_t s_cents[MAX_CENT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N3 = p.N3, Np = p.Np, S = p.stages, AS = p.acc_stages;
+  const int npairs = p.n_cent >> 1;
+  auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+  auto empty_bar = [&](int s) { return smem_u32(&bars[8 + s]); };
+  auto tfull_bar = [&](int a) { return smem_u32(&bars[16 + a]); };
+  auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
+  const uint32_t bfull_bar = smem_u32(&bars[24]);
+
+  for (int i = threadIdx.x; i < p.n_cent; i += blockDim.x) s_cents[i] = p.cents[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), S3_EPI_WARPS); }
+    mbar_init(bfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  const uint32_t bbytes = 3u * 2u * 16u * (uint32_t)N3;          // packed weights of one K pair
+
+  if (warp == 0) {
+    // ================================================= TMA producer warp
+    int stage = 0, phase = 0;
+    if (lane == 0 && (int)blockIdx.x < p.n_tiles) {
+      mbar_expect_tx(bfull_bar, bbytes * (uint32_t)npairs);
+      for (int pr = 0; pr < npairs; ++pr)
+        bulk_copy_g2s(smem_base + pr * bbytes, p.wpacked + (size_t)pr * (bbytes / 2), bbytes, bfull_bar);
+    }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int b = t / p.D;
+      const int h0 = ht * S3_TH, w0 = wt * S3_ADV - 1;
+      for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
+        const int np = min(S3_PPS, npairs - pr0);
+        if (lane == 0) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), (uint32_t)np * 2u * (uint32_t)S3_SLAB);
+        }
+        __syncwarp();
+        if (lane < 2 * np) {
+          const e2e_centry_t ce = s_cents[2 * pr0 + lane];
+          tma_load_4d(smem_base + p.b_region_bytes + stage * p.stage_bytes + lane * S3_SLAB, &maps.m[ce.src],
+                      full_bar(stage), w0 * 4, h0 - 1, d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
+    const uint64_t adesc = make_desc(0, S3_SLAB, 128);             // LBO: next 8 channels, SBO: next 8 voxels
+    const uint64_t bdesc = make_desc(0, N3 * 16, 128);
+    const uint32_t a_hi = (uint32_t)(adesc >> 32), a_lo0 = (uint32_t)adesc;
+    const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
+    const uint32_t sa0 = (smem_base + (uint32_t)p.b_region_bytes) >> 4, sb0 = smem_base >> 4;
+    const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+    const uint32_t b_tap_units = (uint32_t)(2 * N3);               // one kh slice of a pair, in 16-byte units
+    int stage = 0, phase = 0, as = 0, aphase = 0;
+    if ((int)blockIdx.x < p.n_tiles) {
+      mbar_wait(bfull_bar, 0);
+      tc_fence_after();
+    }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(as * N3);
+      for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
+        const int np = min(S3_PPS, npairs - pr0);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int i = 0; i < np; ++i) {
+            const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units + (uint32_t)i * (uint32_t)(2 * S3_SLAB >> 4);
+            const uint32_t b_lo = b_lo0 + sb0 + (uint32_t)(pr0 + i) * 3u * b_tap_units;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)        // window rows kh .. kh+3: one row = 512 B = 32 units
+              tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
+                            (pr0 + i + kh) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one_sync()) tc_commit(tfull_bar(as));
+      __syncwarp();
+      if (++as == AS) { as = 0; aphase ^= 1; }
+    }
+  } else {
+    // ================================================= epilogue: 2 warps per TMEM lane quadrant (= tile row),
+    // each takes every other 8-channel block of the result
+    const int q = warp & 3;                    // tile row
+    const int grp = (warp - 2) >> 2;
+    const int nblk = Np >> 3;
+    int as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int wt = t % p.tiles_w; t /= p.tiles_w;
+      const int ht = t % p.tiles_h; t /= p.tiles_h;
+      const int d = t % p.D;
+      const int b = t / p.D;
+      const int h = ht * S3_TH + q;
+      const int w = wt * S3_ADV - 1 + lane;
+      const bool ok = lane >= 1 && lane <= S3_ADV && h < p.H && w < p.W;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N3);
+      for (int cb = grp; cb < nblk; cb += S3_EPI_WARPS / 4) {
+        uint32_t v0[8], v1[8], v2[8];
+        tc_ld8(acc + cb * 8, v0);
+        tc_ld8(acc + Np + cb * 8, v1);
+        tc_ld8(acc + 2 * Np + cb * 8, v2);
+        tc_wait_ld();
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);     // D'[w - 1][kw = 0]
+          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);  // D'[w + 1][kw = 2]
+          o[e] = left + __uint_as_float(v1[e]) + right;
+        }
+        if (ok) {
+          bf16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
+          *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                     pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == AS) { as = 0; aphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
 }  // namespace
 
 // 1: stride-1 3x3 halo form, 2: 1-tap point form, 0: not served by this kernel
@@ -539,7 +733,69 @@ int e2e_conv_tc_supported(const e2e_gemm_t* p) {
     if (16 * p->ish > 256 || 32 * p->isw > 256) return 0;
     return 2;
   }
+  if (p->n_taps == 3) {
+    // kw-stacked forward of a narrow stride-1 layer: Npad = 3 * (padded Cout), one destination, in place
+    if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->osd != 1 || p->osh != 1 || p->osw != 1) return 0;
+    if (p->ivh != 0 || p->ivw != 0 || p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
+    if (p->Dd != p->Di || p->Hd != p->Hi || p->Wd != p->Wi || p->n_dst != 1) return 0;
+    if (p->Npad % 48 != 0 || p->Npad > 240) return 0;
+    const int region = ((p->n_cent / 2) * 3 * 2 * 16 * p->Npad + 1023) / 1024 * 1024;
+    if (region + 3 * S3_PPS * 2 * S3_SLAB > SMEM_BUDGET) return 0;       // resident weights + 3 stages
+    return 3;
+  }
   return 0;
+}
+
+static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t st) {
+  S3Params p{};
+  p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
+  p.n_cent = g->n_cent; p.N3 = g->Npad; p.Np = g->Npad / 3; p.ivd = g->ivd;
+  p.acc_stages = 512 / p.N3;
+  if (p.acc_stages > 4) p.acc_stages = 4;
+  const int npairs = g->n_cent / 2;
+  p.b_region_bytes = (npairs * 3 * 2 * 16 * p.N3 + 1023) / 1024 * 1024;
+  p.stage_bytes = S3_PPS * 2 * S3_SLAB;
+  int stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.tiles_h = (p.H + S3_TH - 1) / S3_TH;
+  p.tiles_w = (p.W + S3_ADV - 1) / S3_ADV;
+  p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  p.cents = g->cents;
+  p.wpacked = reinterpret_cast<const bf16*>(g->wpacked);
+  p.dst = reinterpret_cast<bf16*>(g->dst[0]);
+  p.dst_cb = g->dst_cb[0];
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int i = 0; i < E2E_MAX_SRC; ++i) {
+    const int si = i < g->n_src ? i : 0;
+    p.src_cb[i] = g->src_cb[si];
+    cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
+    cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(S3_TW * 4), (cuuint32_t)S3_ROWS, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      e2e_set_error("conv_tc3: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
+      return E2E_ERR_CUDA;
+    }
+  }
+  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncAttributes fa;
+    E2E_CUDA(cudaFuncGetAttributes(&fa, conv_tc3_kernel));
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024 - (int)fa.sharedSizeBytes));
+    attr_done = true;
+  }
+  int grid = e2e_num_sms();
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  conv_tc3_kernel<<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);
+  E2E_LAUNCHED("conv_tc3");
+  return E2E_OK;
 }
 
 // gs[0..n): column chunks of ONE GEMM (same sources, grids, channel entries, taps and destinations;
@@ -562,6 +818,13 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
   if (!encode) {
     e2e_set_error("conv_tc_fwd: cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
     return E2E_ERR_CUDA;
+  }
+  if (form == 3) {
+    if (n != 1) {
+      e2e_set_error("conv_tc_fwd: the kw-stacked form takes a single column chunk");
+      return E2E_ERR_UNSUPPORTED;
+    }
+    return conv_tc3_launch(g, encode, st);
   }
   // host copies of the plan tables are not available here: in the halo form taps must have
   // |dh|,|dw| <= 1 and channel entries dh = dw = 0; the Python plan builder guarantees it.

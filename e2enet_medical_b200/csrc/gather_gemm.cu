@@ -527,6 +527,10 @@ static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
   if (allow_tc && p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, 1, st);
+  if (p->n_taps == 3) {
+    e2e_set_error("gather_gemm: a kw-stacked plan (3 taps, N = 3 x Cout) is only executable by the tcgen05 kernel");
+    return E2E_ERR_UNSUPPORTED;
+  }
   const int N = p->Npad;
   if (N % 128 == 0) return launch_gemm<8>(p, st);
   if (N % 96 == 0) return launch_gemm<6>(p, st);

@@ -17,7 +17,7 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1}
+CONFIG = {"impl": 1, "stack3": True}
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
@@ -307,7 +307,13 @@ class ShiftConvINLReLU(torch.autograd.Function):
         Cb = plan.cout // 8
         impl = CONFIG["impl"]
         raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
-        run_gemm_chunks(plan.fwd_chunks, weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], impl)
+        if impl == 1 and plan.fwd3 is not None and CONFIG.get("stack3", True):
+            # narrow layer: kw-stacked tcgen05 kernel (N = 3 x Cout per MMA)
+            run_gemm(plan.fwd3, pack_weights(plan.fwd3, weight, mask), srcs, (D, H, W), (Do, Ho, Wo), B, [raw],
+                     (Do, Ho, Wo), [Cb], impl)
+        else:
+            run_gemm_chunks(plan.fwd_chunks, weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb],
+                            impl)
         V = Do * Ho * Wo
         nch = _nchunk(V, B * Cb)
         partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)

@@ -116,3 +116,33 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
         assert rel(y, yr) < ULP, (impl, rel(y, yr))
         assert rel(dx, xr.grad) < ULP, (impl, rel(dx, xr.grad))
         assert rel(gw, wr.grad) < 2e-4, (impl, rel(gw, wr.grad))
+
+
+@pytest.mark.parametrize("src,cout,spatial,B", [
+    ([48, 48], 48, (3, 9, 70), 2),          # loc4-style: 3 W tiles (advance 30), ragged H (4-row tiles) and W
+    ([48], 48, (2, 160, 160), 1),           # full-resolution rows
+    ([96], 16, (5, 16, 33), 2),             # Np = 16, 6 K pairs
+    ([80], 8, (4, 7, 31), 1),               # Cout 8 padded to 16, one W tile + 1 voxel
+])
+def test_tcgen05_kw_stacked_forward(src, cout, spatial, B):
+    """kw-stacked forward kernel (N = 3 x Cout per MMA, W shift applied in the epilogue by lane shuffles)
+    vs the standard halo-form kernel on the same packed operands."""
+    from e2enet_medical_b200 import ops
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(2)
+    cin = sum(src)
+    plan = build_shiftconv_plan(src, cout, (1, 1, 1))
+    assert plan.fwd3 is not None
+    D, H, W = spatial
+    bf = lambda t: t.bfloat16().float()
+    xs8 = [ops.nc_to_c8(bf(torch.from_numpy(rs.standard_normal((B, c) + spatial).astype(np.float32))).to(dev)) for c in src]
+    w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
+    Cb = cout // 8
+    a = torch.full((B, Cb, D, H, W, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+    b_ = torch.full_like(a, float("nan"))
+    ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (D, H, W), B, [a], (D, H, W), [Cb], 1)
+    ops.run_gemm(plan.fwd3, ops.pack_weights(plan.fwd3, w, None), xs8, (D, H, W), (D, H, W), B, [b_], (D, H, W), [Cb], 1)
+    torch.cuda.synchronize()
+    assert not torch.isnan(b_.float()).any()
+    assert rel(b_, a) < ULP, rel(b_, a)

@@ -188,3 +188,36 @@ def test_real_layer_plans_are_consistent():
         assert len(seen) == nvar
         for par, cols in seen.items():
             assert sorted(cols) == list(range(cin)), (src, stride, par)
+
+
+@pytest.mark.parametrize("src,cout,spatial", [([72], 8, (3, 4, 6)), ([40, 40], 16, (4, 3, 5))])
+def test_kw_stacked_forward_plan(src, cout, spatial):
+    """fwd3 (narrow layers, tcgen05 only): column kw*Np + n of the 3-tap (kh) GEMM holds
+    D'[v] = sum_{kh,c} x~[v + (kh-1) rows][c] W[n,c,kh,kw]; the kernel's epilogue adds the three column
+    groups with W shifts -1 / 0 / +1.  Interpreting the plan on CPU and applying that shift-sum must
+    reproduce the convolution."""
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    rs = np.random.RandomState(5)
+    cin, B = sum(src), 1
+    D, H, W = spatial
+    xs = [rs.standard_normal((B, c) + spatial) for c in src]
+    w = rs.standard_normal((cout, cin, 1, 3, 3))
+    plan = build_shiftconv_plan(src, cout, (1, 1, 1))
+    p3 = plan.fwd3
+    assert p3 is not None and p3.n_taps == 3 and p3.Npad % 48 == 0
+    npo = p3.Npad // 3
+    ref = F.conv3d(onet.shift_depth(torch.cat([torch.from_numpy(a) for a in xs], 1)), torch.from_numpy(w), None,
+                   padding=(0, 1, 1)).numpy()
+    dprime = pi.gemm_planar(p3, pi.pack(p3, w), [pi.to_c8(a) for a in xs], (D, H, W), (D, H, W), B, p3.Npad)
+    out = np.zeros((B, npo, D, H, W))
+    for kw in range(3):
+        g = dprime[:, kw * npo:(kw + 1) * npo]
+        sh = kw - 1                                  # out[w] += D'_kw[w + kw - 1]
+        if sh == 0:
+            out += g
+        elif sh < 0:
+            out[..., 1:] += g[..., :-1]
+        else:
+            out[..., :-1] += g[..., 1:]
+    np.testing.assert_allclose(out[:, :cout], ref, atol=1e-9)
+    assert not out[:, cout:].any()

@@ -78,8 +78,12 @@ def main():
         wpd = [ops.pack_weights(v, w, None) for v in plan.dgrad]
 
         def fwd():
-            ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
-                                [cout // 8], impl)
+            if impl == 1 and plan.fwd3 is not None and os.environ.get("E2E_STACK3", "1") == "1":
+                ops.run_gemm(plan.fwd3, ops.pack_weights(plan.fwd3, w, None), xs8, (D, H, W), (Do, Ho, Wo), B, [raw],
+                             (Do, Ho, Wo), [cout // 8], impl)
+            else:
+                ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                                    [cout // 8], impl)
 
         def dgrad():
             if plan.dgrad_needs_zero:
