@@ -645,13 +645,18 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one_sync()) {
-          for (int i = 0; i < np; ++i) {
-            const uint32_t a_lo = a_lo0 + sa0 + (uint32_t)stage * stage_units + (uint32_t)i * (uint32_t)(2 * S3_SLAB >> 4);
-            const uint32_t b_lo = b_lo0 + sb0 + (uint32_t)(pr0 + i) * 3u * b_tap_units;
+          const uint32_t a_st = a_lo0 + sa0 + (uint32_t)stage * stage_units;
+          const uint32_t b_st = b_lo0 + sb0 + (uint32_t)pr0 * 3u * b_tap_units;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)        // window rows kh .. kh+3: one row = 512 B = 32 units
-              tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
-                            (pr0 + i + kh) ? 1u : 0u);
+          for (int i = 0; i < S3_PPS; ++i) {      // fully unrolled issue sequence (np <= S3_PPS)
+            if (i < np) {
+              const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
+              const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)      // window rows kh .. kh+3: one row = 512 B = 32 units
+                tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
+                              (i + kh) ? 1u : (pr0 ? 1u : 0u));
+            }
           }
           tc_commit(empty_bar(stage));
         }
@@ -681,23 +686,35 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N3);
-      for (int cb = grp; cb < nblk; cb += S3_EPI_WARPS / 4) {
-        uint32_t v0[8], v1[8], v2[8];
-        tc_ld8(acc + cb * 8, v0);
-        tc_ld8(acc + Np + cb * 8, v1);
-        tc_ld8(acc + 2 * Np + cb * 8, v2);
-        tc_wait_ld();
-        float o[8];
+      constexpr int EB = 3;                      // blocks per TMEM round trip (9 loads in flight)
+      for (int cb0 = grp; cb0 < nblk; cb0 += EB * (S3_EPI_WARPS / 4)) {
+        uint32_t v[EB][3][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[e]), 1);     // D'[w - 1][kw = 0]
-          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[e]), 1);  // D'[w + 1][kw = 2]
-          o[e] = left + __uint_as_float(v1[e]) + right;
+        for (int u = 0; u < EB; ++u) {
+          const int cb = cb0 + u * (S3_EPI_WARPS / 4);
+          if (cb < nblk) {
+            tc_ld8(acc + cb * 8, v[u][0]);
+            tc_ld8(acc + Np + cb * 8, v[u][1]);
+            tc_ld8(acc + 2 * Np + cb * 8, v[u][2]);
+          }
         }
-        if (ok) {
-          bf16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
-          *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                     pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        tc_wait_ld();
+#pragma unroll
+        for (int u = 0; u < EB; ++u) {
+          const int cb = cb0 + u * (S3_EPI_WARPS / 4);
+          if (cb >= nblk) break;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[u][0][e]), 1);     // D'[w - 1][kw = 0]
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[u][2][e]), 1);  // D'[w + 1][kw = 2]
+            o[e] = left + __uint_as_float(v[u][1][e]) + right;
+          }
+          if (ok) {
+            bf16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
+            *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                       pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          }
         }
       }
       tc_fence_before();
