@@ -221,3 +221,24 @@ def test_kw_stacked_forward_plan(src, cout, spatial):
             out[..., :-1] += g[..., 1:]
     np.testing.assert_allclose(out[:, :cout], ref, atol=1e-9)
     assert not out[:, cout:].any()
+
+
+def test_product_state_dict_matches_reference_inventory():
+    """drop-in contract: the product network built with the trainer's positional arguments has
+    exactly the reference's state_dict keys / shapes / registration order (golden dumped from the unmodified
+    reference), for all three training configs.  Construction needs no GPU."""
+    import json
+    from e2enet_medical_b200.training import POOLS, build_network
+    inv = json.load(open(os.path.join(ROOT, "tests", "golden", "param_inventory.json")))
+    for tag, in_ch, ncls, patch in (("btcv", 1, 14, (64, 160, 160)), ("brats", 4, 4, (128, 128, 128)),
+                                    ("hippo", 1, 3, (40, 56, 40))):
+        net = build_network(in_ch, ncls, POOLS[tag], patch)
+        sd = net.state_dict()
+        assert [[k, list(v.shape)] for k, v in sd.items()] == inv[tag], tag
+        assert [k for k, _ in net.named_parameters()] == inv[tag + "_named_parameters"], tag
+        assert all(v.dtype == torch.float32 for v in sd.values())
+    # the Masking selection rule of the reference (core_channel.py:320-336): 35 masked tensors for config 2
+    net = build_network(1, 14, POOLS["btcv"], (64, 160, 160))
+    sel = [n for n, p in net.named_parameters()
+           if (('loc' in n and 'context' not in n) or 'up' in n) and 'bias' not in n and 'instnorm' not in n]
+    assert len(sel) == 35 and sum(dict(net.named_parameters())[n].numel() for n in sel) == 17975040
