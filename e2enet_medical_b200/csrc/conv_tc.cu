@@ -137,6 +137,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA prefetch of a box into L2 (no shared memory, no barrier): issued a few tiles ahead so that the
+// real load finds its data in L2 and the pipeline depth only has to cover L2 latency
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -546,6 +553,7 @@ constexpr int S3_THREADS = 64 + 32 * S3_EPI_WARPS;
 struct S3Params {
   int B, D, H, W;
   int n_cent, Np, N3, ivd;          // Np = padded Cout (multiple of 8), N3 = 3 * Np (multiple of 16)
+  int prefetch;                     // L2 prefetch distance in tiles of this CTA (0 = off)
   int stages, acc_stages;
   int tiles_h, tiles_w, n_tiles;
   int b_region_bytes, stage_bytes;
@@ -606,6 +614,13 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       const int d = t % p.D;
       const int b = t / p.D;
       const int h0 = ht * S3_TH, w0 = wt * S3_ADV - 1;
+      const int ptile = tile + p.prefetch * (int)gridDim.x;
+      const bool pf_ok = p.prefetch > 0 && ptile < p.n_tiles;
+      int pt = pf_ok ? ptile : tile;
+      const int pwt = pt % p.tiles_w; pt /= p.tiles_w;
+      const int pht = pt % p.tiles_h; pt /= p.tiles_h;
+      const int pd = pt % p.D, pb = pt / p.D;
+      const int ph0 = pht * S3_TH, pw0 = pwt * S3_ADV - 1;
       for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
         const int np = min(S3_PPS, npairs - pr0);
         if (lane == 0) {
@@ -617,6 +632,8 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
           const e2e_centry_t ce = s_cents[2 * pr0 + lane];
           tma_load_4d(smem_base + p.b_region_bytes + stage * p.stage_bytes + lane * S3_SLAB, &maps.m[ce.src],
                       full_bar(stage), w0 * 4, h0 - 1, d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
+          if (pf_ok)                               // same boxes of the tile this CTA processes p.prefetch rounds later
+            tma_prefetch_4d(&maps.m[ce.src], pw0 * 4, ph0 - 1, pd + p.ivd + ce.dd, pb * p.src_cb[ce.src] + ce.blk);
         }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
@@ -778,6 +795,11 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   p.tiles_h = (p.H + S3_TH - 1) / S3_TH;
   p.tiles_w = (p.W + S3_ADV - 1) / S3_ADV;
   p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("E2E_TC_PREFETCH"); pf = e ? atoi(e) : 0; }   // measured: 0.34 -> 0.44 ms with prefetch on (the TMA unit, not latency, is the limit)
+    p.prefetch = pf;
+  }
   p.cents = g->cents;
   p.wpacked = reinterpret_cast<const bf16*>(g->wpacked);
   p.dst = reinterpret_cast<bf16*>(g->dst[0]);
