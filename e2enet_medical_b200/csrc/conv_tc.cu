@@ -538,15 +538,19 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 //     D'[v][kw * Np + n] = sum_{kh, c}  X[v + (kh - 1) rows][c] * W[kh][kw][c][n]      (N = 3 * Np)
 //     out[h][w][n]       = D'[h][w - 1][0 * Np + n] + D'[h][w][1 * Np + n] + D'[h][w + 1][2 * Np + n]
 // so A is read once per THREE taps (3 MMAs of N = 144 per 16 channels instead of 9 of N = 48) and the
-// W shift happens in the epilogue as two lane shuffles: a tile is 4 (H) x 32 (W) positions, TMEM lane
-// = (row, w), one row per warp quadrant.  Lanes 0 and 31 only feed their neighbours, so tiles advance
-// by 30 in W.  The A window is [6 rows][32 voxels][8 ch] per 8-channel block (no W halo: row pitch
-// 512 B makes the 16 core matrices of the M tile contiguous, SBO = 128).  Packed weights
-// [pair][kh][2][3*Np][8] stay resident in shared memory; 4 K pairs per pipeline stage.
+// W shift happens in the epilogue as two lane shuffles: an M tile is 4 (H) x 32 (W) positions, TMEM
+// lane = (row, w), one row per warp quadrant.  Lanes 0 and 31 only feed their neighbours, so tiles
+// advance by 30 in W.  A work item is TWO vertically adjacent M tiles that share one A window
+// [10 rows][32 voxels][8 ch] per 8-channel block (half the TMA boxes per voxel -- the TMA unit, not
+// the tensor pipe, bounds this kernel -- and 1.25x instead of 1.5x H-halo traffic; no W halo: row
+// pitch 512 B makes the 16 core matrices of an M tile contiguous, SBO = 128).  Their accumulators
+// rotate through three 3*Np-column TMEM slots, so the epilogue of one M tile overlaps the MMAs of the
+// next work item.  Packed weights [pair][kh][2][3*Np][8] stay resident in shared memory.
 // =====================================================================================
-constexpr int S3_TH = 4, S3_TW = 32, S3_ADV = 30, S3_ROWS = S3_TH + 2;
-constexpr int S3_SLAB = S3_ROWS * S3_TW * 16;      // 3072 B
-constexpr int S3_PPS = 4;
+constexpr int S3_MT = 2;                            // M tiles (4 rows each) per work item: they share one window
+constexpr int S3_TH = 4 * S3_MT, S3_TW = 32, S3_ADV = 30, S3_ROWS = S3_TH + 2;
+constexpr int S3_SLAB = S3_ROWS * S3_TW * 16;      // 5120 B: [10 rows][32 voxels][8 ch]
+constexpr int S3_PPS = 2;                           // K pairs per pipeline stage (2 * 3 * S3_MT = 12 MMAs)
 constexpr int S3_EPI_WARPS = 8;
 constexpr int S3_THREADS = 64 + 32 * S3_EPI_WARPS;
 
@@ -648,15 +652,23 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     const uint32_t sa0 = (smem_base + (uint32_t)p.b_region_bytes) >> 4, sb0 = smem_base >> 4;
     const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
     const uint32_t b_tap_units = (uint32_t)(2 * N3);               // one kh slice of a pair, in 16-byte units
-    int stage = 0, phase = 0, as = 0, aphase = 0;
+    int stage = 0, phase = 0;
+    uint32_t mcount = 0;                       // M tiles issued so far: slot = mcount % AS, phase = (mcount / AS) & 1
     if ((int)blockIdx.x < p.n_tiles) {
       mbar_wait(bfull_bar, 0);
       tc_fence_after();
     }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(as), aphase ^ 1);
+      uint32_t acc[S3_MT];
+      int slot[S3_MT];
+#pragma unroll
+      for (int mt = 0; mt < S3_MT; ++mt) {
+        const uint32_t mc = mcount + mt;
+        slot[mt] = (int)(mc % (uint32_t)AS);
+        mbar_wait(tempty_bar(slot[mt]), ((mc / (uint32_t)AS) & 1u) ^ 1u);
+        acc[mt] = tmem_base + (uint32_t)(slot[mt] * N3);
+      }
       tc_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(as * N3);
       for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
         const int np = min(S3_PPS, npairs - pr0);
         mbar_wait(full_bar(stage), phase);
@@ -670,9 +682,12 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
               const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
               const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh)      // window rows kh .. kh+3: one row = 512 B = 32 units
-                tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
-                              (i + kh) ? 1u : (pr0 ? 1u : 0u));
+              for (int kh = 0; kh < 3; ++kh) {    // M tile mt reads window rows 4*mt + kh .. +3: one row = 32 units
+#pragma unroll
+                for (int mt = 0; mt < S3_MT; ++mt)
+                  tc_mma_f16_lh(acc[mt], a_lo + (uint32_t)((4 * mt + kh) * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units,
+                                b_hi, idesc, (i + kh) ? 1u : (pr0 ? 1u : 0u));
+              }
             }
           }
           tc_commit(empty_bar(stage));
@@ -680,9 +695,12 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      if (elect_one_sync()) tc_commit(tfull_bar(as));
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int mt = 0; mt < S3_MT; ++mt) tc_commit(tfull_bar(slot[mt]));
+      }
       __syncwarp();
-      if (++as == AS) { as = 0; aphase ^= 1; }
+      mcount += S3_MT;
     }
   } else {
     // ================================================= epilogue: 2 warps per TMEM lane quadrant (= tile row),
@@ -690,15 +708,18 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     const int q = warp & 3;                    // tile row
     const int grp = (warp - 2) >> 2;
     const int nblk = Np >> 3;
-    int as = 0, aphase = 0;
+    uint32_t mcount = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int t = tile;
       const int wt = t % p.tiles_w; t /= p.tiles_w;
       const int ht = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
       const int b = t / p.D;
-      const int h = ht * S3_TH + q;
       const int w = wt * S3_ADV - 1 + lane;
+     for (int mt = 0; mt < S3_MT; ++mt, ++mcount) {
+      const int as = (int)(mcount % (uint32_t)AS);
+      const uint32_t aphase = (mcount / (uint32_t)AS) & 1u;
+      const int h = ht * S3_TH + 4 * mt + q;
       const bool ok = lane >= 1 && lane <= S3_ADV && h < p.H && w < p.W;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
@@ -737,7 +758,7 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
-      if (++as == AS) { as = 0; aphase ^= 1; }
+     }
     }
   }
 
