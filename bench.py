@@ -1,11 +1,14 @@
 """bench.py -- E2ENet hot-path benchmark on B200 (contract: see the task's Measurement section).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|infer]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--no-inference]
 
 Workload at every N: BASELINE.json configs[1] -- E2ENet BTCV-shaped training: batch 2 per GPU
 (weak scaling), 1x64x160x160 CT patches, 14 classes, DSFF density 0.2, SGD(nesterov) +
-clip + Masking.step() every iteration.  One "step" = one full training iteration of one batch.
-Prints ONE JSON line (rank 0).
+clip + Masking.step() every iteration.  One "step" = one full training iteration of one batch:
+`value` replays it as ONE CUDA graph with the batch resident, `e2e` adds the pinned-host -> device copy
+of the batch and the loss read-back, `roofline` comes from an eager pass with per-launch CUDA events.
+The `inference` object is BASELINE.json configs[2] (sliding-window voxels/s, tiles sharded over the N
+ranks).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -128,10 +131,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = []
-    import torch
     # each "step" = the bounded sample below; warm-up folded into cpu_baseline_patches_per_s
-    t0 = time.perf_counter()
     val, dt, n = cpu_baseline_patches_per_s(budget_s=max(10.0, 6.0 * max(args.steps, 1)))
     line = {
         "impl": "reference", "metric": "train patches/s", "value": val, "unit": "patches/s", "n_gpus": args.gpus,
