@@ -189,5 +189,9 @@ class TrainStep(object):
             for s_, t in zip(self._static_targets, targets):
                 s_.copy_(t, non_blocking=True)
         self._graph.replay()
+        # the replay changed weights (SGD, apply_mask) behind torch's version counters: any EAGER use of the
+        # network after this (validation, inference) must repack its operands
+        from . import ops
+        ops.bump_weight_epoch()
         self.mask.step(_mask_already_applied=True)            # host bookkeeping; prune / regrow when due
         return self._static_loss

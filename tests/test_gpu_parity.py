@@ -603,6 +603,14 @@ def test_train_step_cuda_graph_matches_eager(dev):
         losses = [float(ts.step(data, targets)) for _ in range(6)]                   # crosses an update step
         w = torch.cat([p.detach().flatten() for p in ts.network.parameters()]).double().cpu()
         masks = {k: v.clone().cpu() for k, v in ts.mask.masks.items()}
+        if mode == "graph":
+            # an eager forward right after replays must see the replayed weights (packed-operand cache)
+            from e2enet_medical_b200 import ops
+            with torch.no_grad():
+                y1 = ts.network(data)[0].clone()
+                ops.bump_weight_epoch()
+                y2 = ts.network(data)[0]
+            assert torch.equal(y1, y2), "stale packed weights after CUDA-graph replays"
         out[mode] = (losses, w, masks, ts.mask.steps)
         del ts
     assert out["eager"][3] == out["graph"][3]
