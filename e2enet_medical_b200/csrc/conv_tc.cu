@@ -776,6 +776,13 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
 int e2e_conv_tc_supported(const e2e_gemm_t* p) {
   if (p->out_mode != 0) return 0;
   if (p->Npad > 256 || p->Npad % 16 != 0 || p->n_cent > MAX_CENT) return 0;
+  {
+    // the epilogue indexes destination voxels with 32 bits
+    long long mx = 0;
+    for (int i = 0; i < p->n_dst && i < E2E_MAX_SRC; ++i)
+      if (p->dst_cb[i] > mx) mx = p->dst_cb[i];
+    if ((long long)p->B * mx * p->Dd * p->Hd * (long long)p->Wd >= (1ll << 31)) return 0;
+  }
   if (p->n_taps == 9) {
     if (p->isd != 1 || p->ish != 1 || p->isw != 1 || p->osd != 1 || p->osh != 1 || p->osw != 1) return 0;
     if (p->ivh != 0 || p->ivw != 0) return 0;

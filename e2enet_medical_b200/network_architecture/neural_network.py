@@ -439,8 +439,8 @@ class SegmentationNetwork(NeuralNetwork):
     def _internal_maybe_mirror_and_pred_3D(self, x: Union[np.ndarray, torch.Tensor], mirror_axes: tuple,
                                            do_mirroring: bool = True,
                                            mult: np.ndarray or torch.Tensor = None) -> torch.Tensor:
-        """API-parity entry (reference :500-565): returns the mirrored / weighted prediction of one
-        tile as a (1, ncls, x, y, z) fp32 CUDA tensor."""
+        """API-parity entry (reference :500-565): returns the mirrored / weighted prediction of the
+        b tiles in x as a (b, ncls, x, y, z) fp32 CUDA tensor."""
         assert len(x.shape) == 5, 'x must be (b, c, x, y, z)'
         dev = self._device()
         x = maybe_to_torch(x).to(dev).float()
@@ -448,7 +448,8 @@ class SegmentationNetwork(NeuralNetwork):
         if mult is not None:
             g = maybe_to_torch(mult).to(dev).float().contiguous()
         sp = tuple(x.shape[2:])
-        agg = torch.zeros((self.num_classes,) + sp, dtype=torch.float32, device=dev)
+        out = torch.zeros((x.shape[0], self.num_classes) + sp, dtype=torch.float32, device=dev)
         wsum = torch.zeros(sp, dtype=torch.float32, device=dev)
-        self._accumulate_tile(x, mirror_axes, do_mirroring, g, agg, wsum, (0, 0, 0))
-        return agg[None]
+        for i in range(x.shape[0]):                 # one accumulator per sample (they are separate results)
+            self._accumulate_tile(x[i:i + 1], mirror_axes, do_mirroring, g, out[i], wsum, (0, 0, 0))
+        return out
