@@ -242,3 +242,34 @@ def test_product_state_dict_matches_reference_inventory():
     sel = [n for n, p in net.named_parameters()
            if (('loc' in n and 'context' not in n) or 'up' in n) and 'bias' not in n and 'instnorm' not in n]
     assert len(sel) == 35 and sum(dict(net.named_parameters())[n].numel() for n in sel) == 17975040
+
+
+def test_slab_plan_properties():
+    """slab ownership plan of sharded sliding-window inference: for any volume / patch / step / rank count the
+    owned x-slabs tile [0, X) exactly once, every tile is predicted by exactly one rank, a rank's tiles start
+    inside or after its own slab, and every plane a rank touches beyond its slab is owned by a LATER rank
+    (contributions only flow forward, which is what _slab_exchange implements)."""
+    from e2enet_medical_b200.network_architecture.neural_network import SegmentationNetwork as S
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        patch = tuple(int(v) for v in rs.randint(4, 40, 3))
+        vol = tuple(int(p + rs.randint(0, 4 * p)) for p in patch)
+        step = float(rs.choice([0.25, 0.5, 0.75, 1.0]))
+        world = int(rs.randint(1, 12))
+        steps = S._compute_steps_for_sliding_window(patch, vol, step)
+        tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
+        cut, bx, hi = S._slab_plan(tiles, patch[0], vol[0], world)
+        assert cut[0] == 0 and cut[-1] == len(tiles) and all(cut[i] <= cut[i + 1] for i in range(world))
+        assert bx[0] == 0 and bx[-1] == vol[0] and all(bx[i] <= bx[i + 1] for i in range(world)), (bx, vol)
+        for r in range(world):
+            mine = tiles[cut[r]:cut[r + 1]]
+            for (a, _, _) in mine:
+                assert a >= bx[r], "a rank never contributes to planes owned by an earlier rank"
+                assert a + patch[0] <= max(hi[r], bx[r + 1])
+            if mine:
+                assert hi[r] == mine[-1][0] + patch[0] and hi[r] <= vol[0]
+        # every plane is covered by the tiles of ranks <= its owner (so the owner ends up with the full sum)
+        for r in range(world):
+            for x in {bx[r], max(bx[r], bx[r + 1] - 1)} if bx[r + 1] > bx[r] else ():
+                contrib = [q for q in range(world) for (a, _, _) in tiles[cut[q]:cut[q + 1]] if a <= x < a + patch[0]]
+                assert contrib and max(contrib) <= r, (x, r, contrib)
