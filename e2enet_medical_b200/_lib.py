@@ -100,6 +100,10 @@ SIGNATURES = {
     "e2e_in_apply": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP]),
     "e2e_in_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _I32, _VP, _VP, _VP, _VP,
                              _VP, _VP]),
+    "e2e_in_apply_pool": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP,
+                                    _VP, _VP]),
+    "e2e_in_bwd_pool": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                  _I32, _VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
     "e2e_maxpool_fwd": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "e2e_maxpool_bwd": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "e2e_add_inplace": (C.c_int, [_VP, _VP, _I64, _VP]),

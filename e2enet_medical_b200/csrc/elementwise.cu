@@ -316,6 +316,163 @@ __global__ void in_bwd_param_kernel(const float* __restrict__ sums, const float*
   if (dbias) dbias[c] = (float)bi;
 }
 
+// ------------------------------------------------------------------ InstanceNorm + LeakyReLU fused with the
+// MaxPool3d(kernel == stride) that consumes the same activation (the down* modules read x{i}_{j} right after
+// its block produced it, unetpp_d.py:453-478): one thread per POOLED voxel normalises its window, writes the
+// kd*kh*kw activations, the pooled maximum and its arg-max.  Saves the pool's re-read of the activation;
+// backward folds the pooled gradient into the norm backward (no separate max-pool backward, no gradient add).
+// Requires D % kd == H % kh == W % kw == 0 and kd*kh*kw <= 8.
+struct PoolGeo { int D, H, W, kd, kh, kw; };
+
+__device__ __forceinline__ void pool_decode(long long vo, const PoolGeo& g, int& od, int& oh, int& ow) {
+  const int Wo = g.W / g.kw, Ho = g.H / g.kh;
+  ow = (int)(vo % Wo);
+  const long long t = vo / Wo;
+  oh = (int)(t % Ho);
+  od = (int)(t / Ho);
+}
+
+__global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* __restrict__ raw, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, float slope, int Cb, PoolGeo g,
+                                                                   int nchunk, uint4* __restrict__ out, uint4* __restrict__ pooled,
+                                                                   uint2* __restrict__ amax) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int cb = plane % Cb;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float ga = gamma[cb * 8 + j], r = rstd[plane * 8 + j];
+    sc[j] = ga * r;
+    sh[j] = beta[cb * 8 + j] - mean[plane * 8 + j] * ga * r;
+  }
+  const long long V = (long long)g.D * g.H * g.W;
+  const long long Vo = V / (g.kd * g.kh * g.kw);
+  const long long per = (Vo + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(Vo, lo + per);
+  const uint4* ib = raw + (long long)plane * V;
+  uint4* ob = out + (long long)plane * V;
+  for (long long vo = lo + threadIdx.x; vo < hi; vo += EW_THREADS) {
+    int od, oh, ow;
+    pool_decode(vo, g, od, oh, ow);
+    uint4 r[8];
+    long long src[8];
+    int n = 0;
+    for (int a = 0; a < g.kd; ++a)
+      for (int b = 0; b < g.kh; ++b)
+        for (int c = 0; c < g.kw; ++c, ++n) {
+          src[n] = ((long long)(od * g.kd + a) * g.H + oh * g.kh + b) * g.W + ow * g.kw + c;
+          r[n] = ld_nc_16(ib + src[n]);
+        }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int i = 0; i < n; ++i) {
+      float f[8];
+      unpack8(r[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = f[j] * sc[j] + sh[j];
+        f[j] = z > 0.f ? z : z * slope;
+      }
+      const uint4 pk = pack8(f);
+      ob[src[i]] = pk;
+      unpack8(pk, f);                    // the pool compares the bf16 activations, like the separate kernel
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f[j] > best[j] || (f[j] != f[j] && best[j] == best[j])) { best[j] = f[j]; bi[j] = i; }
+    }
+    const long long po = (long long)plane * Vo + vo;
+    pooled[po] = pack8(best);
+    uint2 am;
+    am.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    am.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    amax[po] = am;
+  }
+}
+
+// backward with the pooled gradient folded in: dy_total[v] = dy[v] + (argmax(window(v)) == v ? dyp[window(v)] : 0)
+// PASS 0: partial[plane][chunk][0..7] = sum dz, [8..15] = sum dz*xhat;  PASS 1: draw and partial2 = sum draw
+template <int PASS>
+__global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ dyp,
+                                                                 const uint2* __restrict__ amax, const uint4* __restrict__ raw,
+                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                 const float* __restrict__ sums, float slope, int Cb, PoolGeo g,
+                                                                 int nchunk, uint4* __restrict__ draw, float* __restrict__ partial) {
+  const int plane = blockIdx.y, chunk = blockIdx.x;
+  const int cb = plane % Cb;
+  const long long V = (long long)g.D * g.H * g.W;
+  const long long Vo = V / (g.kd * g.kh * g.kw);
+  const float invV = 1.0f / (float)V;
+  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
+    ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
+    m1[j] = PASS ? sums[plane * 16 + j] * invV : 0.f;
+    m2[j] = PASS ? sums[plane * 16 + 8 + j] * invV : 0.f;
+  }
+  const long long per = (Vo + nchunk - 1) / nchunk;
+  const long long lo = chunk * per, hi = min(Vo, lo + per);
+  const uint4* xb = raw + (long long)plane * V;
+  const uint4* gb = dy ? dy + (long long)plane * V : nullptr;
+  uint4* ob = PASS ? draw + (long long)plane * V : nullptr;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (long long vo = lo + threadIdx.x; vo < hi; vo += EW_THREADS) {
+    int od, oh, ow;
+    pool_decode(vo, g, od, oh, ow);
+    const long long po = (long long)plane * Vo + vo;
+    const uint2 am = amax[po];
+    float gp[8];
+    unpack8(ld_nc_16(dyp + po), gp);
+    uint4 xr[8], gr[8];
+    long long src[8];
+    int n = 0;
+    for (int a = 0; a < g.kd; ++a)
+      for (int b = 0; b < g.kh; ++b)
+        for (int c = 0; c < g.kw; ++c, ++n) {
+          src[n] = ((long long)(od * g.kd + a) * g.H + oh * g.kh + b) * g.W + ow * g.kw + c;
+          xr[n] = ld_nc_16(xb + src[n]);
+          gr[n] = gb ? ld_nc_16(gb + src[n]) : make_uint4(0, 0, 0, 0);
+        }
+    for (int i = 0; i < n; ++i) {
+      float x[8], gv[8], o[8];
+      unpack8(xr[i], x);
+      unpack8(gr[i], gv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t a = ((j < 4 ? am.x : am.y) >> ((j & 3) * 8)) & 0xffu;
+        const float gt = gv[j] + (a == (uint32_t)i ? gp[j] : 0.f);
+        const float xh = (x[j] - mu[j]) * rs[j];
+        const float z = xh * ga[j] + be[j];
+        const float dz = z > 0.f ? gt : gt * slope;
+        if (PASS == 0) {
+          acc[j] += dz;
+          acc[8 + j] += dz * xh;
+        } else {
+          o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+        }
+      }
+      if (PASS) {
+        const uint4 pk = pack8(o);
+        ob[src[i]] = pk;
+        float ro[8];
+        unpack8(pk, ro);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+      }
+    }
+  }
+  if (PASS == 0)
+    block_reduce_store<16>(acc, partial + ((long long)plane * nchunk + chunk) * 16);
+  else
+    block_reduce_store<8>(acc, partial + ((long long)plane * nchunk + chunk) * 8);
+}
+
 // ------------------------------------------------------------------ MaxPool3d, kernel == stride
 __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                                  uint2* __restrict__ amax, int BCb, int D, int H, int W,
@@ -476,6 +633,52 @@ extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, co
   in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, sums,
                                                    slope, Cb, V, nchunk, (uint4*)draw, partial);
   E2E_LAUNCHED("in_bwd_apply");
+  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  E2E_LAUNCHED("in_bwd_param");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_apply_pool(const void* raw, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W,
+                                 int32_t kd, int32_t kh, int32_t kw, void* out, void* pooled, uint8_t* argmax, void* stream) {
+  E2E_ARG(raw && mean && rstd && gamma && beta && out && pooled && argmax && B > 0 && Cb > 0, "in_apply_pool: bad arguments");
+  E2E_ARG(kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 8 && D % kd == 0 && H % kh == 0 && W % kw == 0,
+          "in_apply_pool: window (%d,%d,%d) must divide (%d,%d,%d) and hold at most 8 voxels", kd, kh, kw, D, H, W);
+  const PoolGeo g{D, H, W, kd, kh, kw};
+  const long long Vo = (long long)D * H * W / (kd * kh * kw);
+  int nchunk = (int)((Vo + 1023) / 1024);
+  const int want = (e2e_num_sms() * 8 + B * Cb - 1) / (B * Cb);
+  if (nchunk > want) nchunk = want;
+  if (nchunk < 1) nchunk = 1;
+  in_apply_pool_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk, (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+  E2E_LAUNCHED("in_apply_pool");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
+                               const float* rstd, const float* gamma, const float* beta, float slope, int32_t B, int32_t Cb,
+                               int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* partial,
+                               int32_t nchunk, float* sums, void* draw, float* dgamma, float* dbeta, float* dbias,
+                               void* stream) {
+  E2E_ARG(dyp && argmax && raw && mean && rstd && gamma && beta && partial && sums && draw && dgamma && dbeta,
+          "in_bwd_pool: null pointer");
+  E2E_ARG(B > 0 && Cb > 0 && nchunk > 0 && kd * kh * kw <= 8 && D % kd == 0 && H % kh == 0 && W % kw == 0,
+          "in_bwd_pool: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const PoolGeo g{D, H, W, kd, kh, kw};
+  const dim3 grid(nchunk, B * Cb);
+  in_bwd_pool_kernel<0><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax,
+                                                      (const uint4*)raw, mean, rstd, gamma, beta, nullptr, slope, Cb, g, nchunk,
+                                                      nullptr, partial);
+  E2E_LAUNCHED("in_bwd_pool_reduce");
+  const int n = B * Cb * 16 * 32;
+  in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
+  E2E_LAUNCHED("in_bwd_final");
+  in_bwd_pool_kernel<1><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax,
+                                                      (const uint4*)raw, mean, rstd, gamma, beta, sums, slope, Cb, g, nchunk,
+                                                      (uint4*)draw, partial);
+  E2E_LAUNCHED("in_bwd_pool_apply");
   in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;

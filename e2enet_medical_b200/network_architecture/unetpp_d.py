@@ -96,6 +96,7 @@ class ConvDropoutNormNonlin(nn.Module):
         self.lrelu = self.nonlin(**self.nonlin_kwargs)
         self._plans = {}
         self.e2e_weight_mask = None      # set by the drop-in Masking (same storage as Masking.masks[name])
+        self.e2e_pool_k = None           # set by Generic_UNetPlusPlus: kernel of the MaxPool3d that reads this output
 
     # -- checks that the configuration is the one the kernels implement
     def _check(self):
@@ -119,26 +120,39 @@ class ConvDropoutNormNonlin(nn.Module):
             self._plans[key] = build_shiftconv_plan(key, self.conv.out_channels, tuple(self.conv.stride))
         return self._plans[key]
 
-    def forward_c8(self, srcs, src_channels):
-        """srcs: C8 tensors forming the (virtual) channel concat; returns a C8 tensor."""
+    def forward_c8(self, srcs, src_channels, pool_k=None):
+        """srcs: C8 tensors forming the (virtual) channel concat; returns a C8 tensor (or (y, y_pooled)
+        when pool_k names the MaxPool3d kernel that consumes this activation)."""
         plan = self.plan_for(src_channels)
         return ops.ShiftConvINLReLU.apply(plan, float(self.lrelu.negative_slope), self.conv.weight, self.conv.bias,
-                                          self.instnorm.weight, self.instnorm.bias, self.e2e_weight_mask, *srcs)
+                                          self.instnorm.weight, self.instnorm.bias, self.e2e_weight_mask, pool_k, *srcs)
 
     def forward(self, x):
         if isinstance(x, C8):
+            k = self.e2e_pool_k if ops.CONFIG.get("fuse_pool", True) else None
+            if k is not None:
+                sp = x.parts[0].shape[2:5]
+                st = tuple(self.conv.stride)
+                og = ((sp[0] - 1) // st[0] + 1, (sp[1] - 1) // st[1] + 1, (sp[2] - 1) // st[2] + 1)
+                if any(o % kk for o, kk in zip(og, k)) or k[0] * k[1] * k[2] > 8 or k == (1, 1, 1):
+                    k = None                       # window does not tile the grid: the separate pool kernel handles it
+            if k is not None:
+                y, yp = self.forward_c8(x.parts, x.channels, k)
+                return C8(y, [self.conv.out_channels], pooled=(yp, k))
             return C8(self.forward_c8(x.parts, x.channels), [self.conv.out_channels])
         y = self.forward_c8([ops.ToC8.apply(x)], [x.shape[1]])
         return ops.FromC8.apply(y, self.conv.out_channels)
 
 
 class C8(object):
-    """A (virtual concat of) channel-blocked activation(s) travelling between the drop-in modules."""
-    __slots__ = ("parts", "channels")
+    """A (virtual concat of) channel-blocked activation(s) travelling between the drop-in modules.
+    `pooled` = (tensor, kernel): the max-pooled copy its producer already made in the same pass."""
+    __slots__ = ("parts", "channels", "pooled")
 
-    def __init__(self, parts, channels):
+    def __init__(self, parts, channels, pooled=None):
         self.parts = list(parts) if isinstance(parts, (list, tuple)) else [parts]
         self.channels = list(channels)
+        self.pooled = pooled
 
     @property
     def tensor(self):
@@ -343,6 +357,18 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
         self.seg_outputs = nn.ModuleList(seg)
 
         self._tplans, self._splans = {}, {}
+        # node x{i}_{j} is max-pooled by down*[.] (kernel pools[i]) iff x{i+1}_{j+1} exists, i.e. i + j <= 3
+        # (forward below); its producing block then emits the pooled copy in the same pass
+        for i in range(num_pool):
+            for j in range(0, num_pool - i):
+                if i + j > num_pool - 2:
+                    continue
+                if j == 0:
+                    last = self.conv_blocks_context[i].blocks[-1]
+                else:
+                    last = getattr(self, "loc%d" % (num_pool - i - j))[j - 1][-1].blocks[-1]
+                if isinstance(last, ConvDropoutNormNonlin):
+                    last.e2e_pool_k = pools[i]
         if self.weightInitializer is not None:
             self.apply(self.weightInitializer)
 
@@ -357,7 +383,10 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
         return C8(y, [mod.out_channels])
 
     def _pool(self, mod: nn.MaxPool3d, x: C8) -> C8:
-        return C8(ops.MaxPool.apply(x.tensor, _triple(mod.kernel_size)), x.channels)
+        k = _triple(mod.kernel_size)
+        if x.pooled is not None and tuple(x.pooled[1]) == k:
+            return C8(x.pooled[0], x.channels)         # produced by the block's fused norm + pool pass
+        return C8(ops.MaxPool.apply(x.tensor, k), x.channels)
 
     def _seg(self, k: int, x: C8):
         mod = self.seg_outputs[k]

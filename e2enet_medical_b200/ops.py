@@ -17,7 +17,7 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1, "stack3": True}
+CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True}
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
@@ -297,7 +297,10 @@ class ShiftConvINLReLU(torch.autograd.Function):
     any per-channel constant exactly."""
 
     @staticmethod
-    def forward(ctx, plan: ShiftConvPlan, slope: float, weight, bias, gamma, beta, mask, *srcs):
+    def forward(ctx, plan: ShiftConvPlan, slope: float, weight, bias, gamma, beta, mask, pool_k, *srcs):
+        """pool_k: None, or the (kd, kh, kw) of the MaxPool3d that consumes this activation: then the pooled
+        tensor is produced by the same pass (returns (y, y_pooled)) and its gradient is folded into the norm
+        backward."""
         lib = _lib.load()
         for s in srcs:
             _need_cuda(s, "shiftconv")
@@ -323,24 +326,39 @@ class ShiftConvINLReLU(torch.autograd.Function):
                    "in_stats")
         y = torch.empty_like(raw)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        ctx.plan, ctx.slope, ctx.mask, ctx.grid = plan, slope, mask, (B, D, H, W, Do, Ho, Wo)
+        ctx.pool_k = None
+        if pool_k is not None:
+            kd, kh, kw = (int(v) for v in pool_k)
+            yp = torch.empty((B, Cb, Do // kd, Ho // kh, Wo // kw, 8), dtype=torch.bfloat16, device=dev)
+            am = torch.empty(yp.shape, dtype=torch.uint8, device=dev)
+            _lib.check(lib.e2e_in_apply_pool(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, Do, Ho, Wo,
+                                             kd, kh, kw, _p(y), _p(yp), _p(am), _lib.stream_ptr()), "in_apply_pool")
+            ctx.pool_k = (kd, kh, kw)
+            ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, am, *srcs)
+            return y, yp
         _lib.check(lib.e2e_in_apply(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, V, _p(y),
                                     _lib.stream_ptr()), "in_apply")
-        ctx.plan, ctx.slope, ctx.mask, ctx.grid = plan, slope, mask, (B, D, H, W, Do, Ho, Wo)
         ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, *srcs)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dyp=None):
         lib = _lib.load()
         plan: ShiftConvPlan = ctx.plan
         weight, gamma, beta, raw, mean, rstd = ctx.saved_tensors[:6]
-        srcs = ctx.saved_tensors[6:]
+        am = None
+        if ctx.pool_k is not None:
+            am = ctx.saved_tensors[6]
+            srcs = ctx.saved_tensors[7:]
+        else:
+            srcs = ctx.saved_tensors[6:]
         B, D, H, W, Do, Ho, Wo = ctx.grid
-        dev = dy.device
+        dev = raw.device
         Cb = plan.cout // 8
         V = Do * Ho * Wo
         impl = CONFIG["impl"]
-        dy = dy.contiguous()
+        dy = dy.contiguous() if dy is not None else None
         nch = _nchunk(V, B * Cb)
         partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
         sums = torch.empty(B * Cb * 16, dtype=torch.float32, device=dev)
@@ -349,15 +367,23 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dbeta = torch.empty_like(dgamma)
         dbias = torch.empty_like(dgamma)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        _lib.check(lib.e2e_in_bwd(_p(dy), _p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), ctx.slope, B, Cb, V,
-                                  _p(partial), nch, _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
-                                  _lib.stream_ptr()), "in_bwd")
+        if am is not None and dyp is not None:
+            kd, kh, kw = ctx.pool_k
+            _lib.check(lib.e2e_in_bwd_pool(_p(dy), _p(dyp.contiguous()), _p(am), _p(raw), _p(mean), _p(rstd), _p(g32),
+                                           _p(b32), ctx.slope, B, Cb, Do, Ho, Wo, kd, kh, kw, _p(partial), nch, _p(sums),
+                                           _p(draw), _p(dgamma), _p(dbeta), _p(dbias), _lib.stream_ptr()), "in_bwd_pool")
+        else:
+            if dy is None:
+                dy = torch.zeros_like(raw)
+            _lib.check(lib.e2e_in_bwd(_p(dy), _p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), ctx.slope, B, Cb, V,
+                                      _p(partial), nch, _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
+                                      _lib.stream_ptr()), "in_bwd")
         # weight gradient (dense, also at masked positions: SURVEY H3)
         gw = None
         if ctx.needs_input_grad[2]:
             gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl)
         # data gradients of every source
-        need = [ctx.needs_input_grad[7 + i] for i in range(len(srcs))]
+        need = [ctx.needs_input_grad[8 + i] for i in range(len(srcs))]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(need):
             outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.empty_like(s)) for s in srcs]
@@ -369,7 +395,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
                                 [s.shape[1] for s in srcs], impl)
             dsrcs = [o if n else None for o, n in zip(outs, need)]
         return (None, None, gw, dbias.to(weight.dtype) if ctx.needs_input_grad[3] else None,
-                dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, *dsrcs)
+                dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, *dsrcs)
 
 
 class TConv(torch.autograd.Function):

@@ -158,6 +158,18 @@ int e2e_in_bwd(const void* dy, const void* raw, const float* mean, const float* 
                const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* partial, int32_t nchunk,
                float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
 
+/* InstanceNorm + LeakyReLU fused with the MaxPool3d(kernel == stride) that consumes the same activation
+ * (down* modules, unetpp_d.py:453-478,523-524): writes out (full resolution), pooled and its arg-max in one
+ * pass; the backward folds the pooled gradient dyp into the norm backward (dy may be null = no other
+ * consumer).  Requires the window to divide the grid and kd*kh*kw <= 8. */
+int e2e_in_apply_pool(const void* raw, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                      float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh,
+                      int32_t kw, void* out, void* pooled, uint8_t* argmax, void* stream);
+int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
+                    const float* rstd, const float* gamma, const float* beta, float slope, int32_t B, int32_t Cb,
+                    int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* partial, int32_t nchunk,
+                    float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
+
 /* ---------------------------------------------------------------- MaxPool3d (kernel == stride) */
 int e2e_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t BCb, int32_t D, int32_t H, int32_t W,
                     int32_t kd, int32_t kh, int32_t kw, void* stream);

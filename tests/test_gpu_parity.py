@@ -617,3 +617,45 @@ def test_train_step_cuda_graph_matches_eager(dev):
     for a, b in zip(out["eager"][0], out["graph"][0]):
         assert abs(a - b) < 2e-3 * abs(a), (out["eager"][0], out["graph"][0])
     assert float((out["eager"][1] - out["graph"][1]).norm() / out["eager"][1].norm()) < 2e-2
+
+
+# ------------------------------------------------------------------------------ fused norm + max-pool
+@pytest.mark.parametrize("k,spatial", [((1, 2, 2), (5, 12, 16)), ((2, 2, 2), (6, 8, 12))])
+def test_fused_norm_pool_matches_separate_kernels(dev, k, spatial):
+    """ShiftConvINLReLU with pool_k (one pass writes the activation, its max-pooled copy and the arg-max; the
+    backward folds the pooled gradient into the norm backward) vs the same block followed by the separate
+    MaxPool op: forward bit-identical, gradients equal up to the bf16 rounding of the gradient fan-in add."""
+    from e2enet_medical_b200 import ops
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    rs = np.random.RandomState(4)
+    B, src, cout = 2, [16, 8], 16
+    plan = build_shiftconv_plan(src, cout, (1, 1, 1))
+    cin = sum(src)
+    mk = lambda a: torch.from_numpy(a.astype(np.float32)).to(dev)
+    w0 = mk(rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9))
+    ga0, be0 = mk(1 + 0.1 * rs.standard_normal(cout)), mk(0.1 * rs.standard_normal(cout))
+    xs0 = [mk(rs.standard_normal((B, c) + spatial)) for c in src]
+    po = tuple(s // kk for s, kk in zip(spatial, k))
+    gy = mk(rs.standard_normal((B, cout) + spatial))
+    gp = mk(rs.standard_normal((B, cout) + po))
+    res = []
+    for fused in (False, True):
+        w, ga, be = (t.clone().requires_grad_(True) for t in (w0, ga0, be0))
+        bias = torch.zeros(cout, device=dev, requires_grad=True)
+        xs = [t.clone().requires_grad_(True) for t in xs0]
+        xs8 = [ops.ToC8.apply(t) for t in xs]
+        if fused:
+            y8, yp8 = ops.ShiftConvINLReLU.apply(plan, 0.01, w, bias, ga, be, None, k, *xs8)
+        else:
+            y8 = ops.ShiftConvINLReLU.apply(plan, 0.01, w, bias, ga, be, None, None, *xs8)
+            yp8 = ops.MaxPool.apply(y8, k)
+        y, yp = ops.FromC8.apply(y8, cout), ops.FromC8.apply(yp8, cout)
+        ((y * gy).sum() + (yp * gp).sum()).backward()
+        res.append((y.detach(), yp.detach(), w.grad, ga.grad, be.grad, [t.grad for t in xs]))
+    a, b_ = res
+    assert torch.equal(a[0], b_[0]) and torch.equal(a[1], b_[1])
+    assert torch.equal(a[1], torch.nn.functional.max_pool3d(a[0], k))
+    for u, v in zip(a[2:5], b_[2:5]):
+        assert rel(v, u) < 1e-2, rel(v, u)
+    for u, v in zip(a[5], b_[5]):
+        assert rel2(v, u) < 1e-2, rel2(v, u)
