@@ -332,6 +332,7 @@ __device__ __forceinline__ void pool_decode(long long vo, const PoolGeo& g, int&
   od = (int)(t / Ho);
 }
 
+template <int KD, int KH, int KW>      // window shape as template: the per-window arrays must stay in registers
 __global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* __restrict__ raw, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float slope, int Cb, PoolGeo g,
@@ -355,19 +356,24 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* 
   for (long long vo = lo + threadIdx.x; vo < hi; vo += EW_THREADS) {
     int od, oh, ow;
     pool_decode(vo, g, od, oh, ow);
-    uint4 r[8];
-    long long src[8];
-    int n = 0;
-    for (int a = 0; a < g.kd; ++a)
-      for (int b = 0; b < g.kh; ++b)
-        for (int c = 0; c < g.kw; ++c, ++n) {
-          src[n] = ((long long)(od * g.kd + a) * g.H + oh * g.kh + b) * g.W + ow * g.kw + c;
-          r[n] = ld_nc_16(ib + src[n]);
+    constexpr int n = KD * KH * KW;
+    uint4 r[n];
+    long long src[n];
+#pragma unroll
+    for (int a = 0; a < KD; ++a)
+#pragma unroll
+      for (int b = 0; b < KH; ++b)
+#pragma unroll
+        for (int c = 0; c < KW; ++c) {
+          const int i = (a * KH + b) * KW + c;
+          src[i] = ((long long)(od * KD + a) * g.H + oh * KH + b) * g.W + ow * KW + c;
+          r[i] = ld_nc_16(ib + src[i]);
         }
     float best[8];
     int bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
     for (int i = 0; i < n; ++i) {
       float f[8];
       unpack8(r[i], f);
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* 
 
 // backward with the pooled gradient folded in: dy_total[v] = dy[v] + (argmax(window(v)) == v ? dyp[window(v)] : 0)
 // PASS 0: partial[plane][chunk][0..7] = sum dz, [8..15] = sum dz*xhat;  PASS 1: draw and partial2 = sum draw
-template <int PASS>
+template <int PASS, int KD, int KH, int KW>
 __global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ dyp,
                                                                  const uint2* __restrict__ amax, const uint4* __restrict__ raw,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -429,16 +435,21 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __
     const uint2 am = amax[po];
     float gp[8];
     unpack8(ld_nc_16(dyp + po), gp);
-    uint4 xr[8], gr[8];
-    long long src[8];
-    int n = 0;
-    for (int a = 0; a < g.kd; ++a)
-      for (int b = 0; b < g.kh; ++b)
-        for (int c = 0; c < g.kw; ++c, ++n) {
-          src[n] = ((long long)(od * g.kd + a) * g.H + oh * g.kh + b) * g.W + ow * g.kw + c;
-          xr[n] = ld_nc_16(xb + src[n]);
-          gr[n] = gb ? ld_nc_16(gb + src[n]) : make_uint4(0, 0, 0, 0);
+    constexpr int n = KD * KH * KW;
+    uint4 xr[n], gr[n];
+    long long src[n];
+#pragma unroll
+    for (int a = 0; a < KD; ++a)
+#pragma unroll
+      for (int b = 0; b < KH; ++b)
+#pragma unroll
+        for (int c = 0; c < KW; ++c) {
+          const int i = (a * KH + b) * KW + c;
+          src[i] = ((long long)(od * KD + a) * g.H + oh * KH + b) * g.W + ow * KW + c;
+          xr[i] = ld_nc_16(xb + src[i]);
+          gr[i] = gb ? ld_nc_16(gb + src[i]) : make_uint4(0, 0, 0, 0);
         }
+#pragma unroll
     for (int i = 0; i < n; ++i) {
       float x[8], gv[8], o[8];
       unpack8(xr[i], x);
@@ -650,8 +661,18 @@ extern "C" int e2e_in_apply_pool(const void* raw, const float* mean, const float
   const int want = (e2e_num_sms() * 8 + B * Cb - 1) / (B * Cb);
   if (nchunk > want) nchunk = want;
   if (nchunk < 1) nchunk = 1;
-  in_apply_pool_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk, (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+  const dim3 grid(nchunk, B * Cb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (kd == 1 && kh == 2 && kw == 2)
+    in_apply_pool_kernel<1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
+                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+  else if (kd == 2 && kh == 2 && kw == 2)
+    in_apply_pool_kernel<2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
+                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+  else {
+    e2e_set_error("in_apply_pool: window (%d,%d,%d) is not instantiated (use the separate max-pool kernel)", kd, kh, kw);
+    return E2E_ERR_UNSUPPORTED;
+  }
   E2E_LAUNCHED("in_apply_pool");
   return E2E_OK;
 }
@@ -668,17 +689,30 @@ extern "C" int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* a
   cudaStream_t st = (cudaStream_t)stream;
   const PoolGeo g{D, H, W, kd, kh, kw};
   const dim3 grid(nchunk, B * Cb);
-  in_bwd_pool_kernel<0><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax,
-                                                      (const uint4*)raw, mean, rstd, gamma, beta, nullptr, slope, Cb, g, nchunk,
-                                                      nullptr, partial);
+  const bool k122 = kd == 1 && kh == 2 && kw == 2, k222 = kd == 2 && kh == 2 && kw == 2;
+  if (!k122 && !k222) {
+    e2e_set_error("in_bwd_pool: window (%d,%d,%d) is not instantiated", kd, kh, kw);
+    return E2E_ERR_UNSUPPORTED;
+  }
+#define E2E_BWD_POOL(PASS, DRAW, SUMS)                                                                                     \
+  do {                                                                                                                     \
+    if (k122)                                                                                                              \
+      in_bwd_pool_kernel<PASS, 1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
+                                                                     (const uint4*)raw, mean, rstd, gamma, beta, SUMS, slope, Cb, \
+                                                                     g, nchunk, DRAW, partial);                           \
+    else                                                                                                                   \
+      in_bwd_pool_kernel<PASS, 2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
+                                                                     (const uint4*)raw, mean, rstd, gamma, beta, SUMS, slope, Cb, \
+                                                                     g, nchunk, DRAW, partial);                           \
+  } while (0)
+  E2E_BWD_POOL(0, nullptr, nullptr);
   E2E_LAUNCHED("in_bwd_pool_reduce");
   const int n = B * Cb * 16 * 32;
   in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
   E2E_LAUNCHED("in_bwd_final");
-  in_bwd_pool_kernel<1><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax,
-                                                      (const uint4*)raw, mean, rstd, gamma, beta, sums, slope, Cb, g, nchunk,
-                                                      (uint4*)draw, partial);
+  E2E_BWD_POOL(1, (uint4*)draw, sums);
   E2E_LAUNCHED("in_bwd_pool_apply");
+#undef E2E_BWD_POOL
   in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;

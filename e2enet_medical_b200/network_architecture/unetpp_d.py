@@ -134,7 +134,7 @@ class ConvDropoutNormNonlin(nn.Module):
                 sp = x.parts[0].shape[2:5]
                 st = tuple(self.conv.stride)
                 og = ((sp[0] - 1) // st[0] + 1, (sp[1] - 1) // st[1] + 1, (sp[2] - 1) // st[2] + 1)
-                if any(o % kk for o, kk in zip(og, k)) or k[0] * k[1] * k[2] > 8 or k == (1, 1, 1):
+                if any(o % kk for o, kk in zip(og, k)) or tuple(k) not in ((1, 2, 2), (2, 2, 2)):
                     k = None                       # window does not tile the grid: the separate pool kernel handles it
             if k is not None:
                 y, yp = self.forward_c8(x.parts, x.channels, k)
