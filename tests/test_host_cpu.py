@@ -273,3 +273,47 @@ def test_slab_plan_properties():
             for x in {bx[r], max(bx[r], bx[r + 1] - 1)} if bx[r + 1] > bx[r] else ():
                 contrib = [q for q in range(world) for (a, _, _) in tiles[cut[q]:cut[q + 1]] if a <= x < a + patch[0]]
                 assert contrib and max(contrib) <= r, (x, r, contrib)
+
+
+def test_shiftconv_plans_random_geometries():
+    """randomised host-plan check (fixed seed): arbitrary source splits, strides, odd grids -- forward (column
+    chunks), weight gradient and every data-gradient variant of the plan tables reproduce torch's
+    conv3d(shift_depth(cat(x))) through the numpy interpreter."""
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    rs = np.random.RandomState(123)
+    for trial in range(8):
+        nsrc = int(rs.randint(1, 4))
+        src = [int(rs.choice([1, 4, 8, 12, 16, 20])) for _ in range(nsrc)]
+        cout = int(rs.choice([8, 16, 24]))
+        stride = tuple(int(v) for v in rs.choice([1, 2], 3)) if trial % 2 else (1, 1, 1)
+        spatial = tuple(int(v) for v in rs.randint(3, 7, 3))
+        cin, B = sum(src), 1
+        xs = [rs.standard_normal((B, c) + spatial) for c in src]
+        w = rs.standard_normal((cout, cin, 1, 3, 3))
+        plan = build_shiftconv_plan(src, cout, stride)
+        D, H, W = spatial
+        Do, Ho, Wo = plan.out_grid(D, H, W)
+        tx = [torch.from_numpy(a).requires_grad_(True) for a in xs]
+        tw = torch.from_numpy(w).requires_grad_(True)
+        ref = F.conv3d(onet.shift_depth(torch.cat(tx, 1)), tw, None, stride=stride, padding=(0, 1, 1))
+        x8 = [pi.to_c8(a) for a in xs]
+        raw = np.zeros((B, cout // 8, Do, Ho, Wo, 8))
+        for ch in plan.fwd_chunks:
+            pi.gemm(ch, pi.pack(ch, w), x8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo))
+        np.testing.assert_allclose(pi.from_c8(raw, cout), ref.detach().numpy(), atol=1e-9, err_msg=str((src, cout, stride)))
+        gy = rs.standard_normal(tuple(ref.shape))
+        (ref * torch.from_numpy(gy)).sum().backward()
+        g8 = pi.to_c8(gy)
+        gw = pi.wgrad(plan.wgrad, x8, (D, H, W), (Do, Ho, Wo), B, g8, w.shape)
+        np.testing.assert_allclose(gw, tw.grad.numpy(), atol=1e-9, err_msg=str((src, cout, stride)))
+        outs = [np.full(a.shape, 0.0 if plan.dgrad_needs_zero else np.nan) for a in x8]
+        for grp in plan.dgrad_groups:
+            it = plan.dgrad_iter_grid(grp[0], D, H, W)
+            if min(it) <= 0:
+                continue
+            for var in grp:
+                pi.gemm(var, pi.pack(var, w), [g8], (Do, Ho, Wo), it, B, outs, (D, H, W))
+        for o, t, c in zip(outs, tx, src):
+            got = pi.from_c8(o, c)
+            assert not np.isnan(got).any(), (src, cout, stride)
+            np.testing.assert_allclose(got, t.grad.numpy(), atol=1e-9, err_msg=str((src, cout, stride)))
