@@ -127,6 +127,183 @@ def cpu_baseline_patches_per_s(budget_s=20.0, crop=(32, 96, 96)):
     return frac / dt, dt, n
 
 
+def cpu_baseline_config0(budget_s=12.0):
+    """BASELINE.json configs[0], unscaled: E2ENet 3d_fullres, density 0.2, fwd + DS loss + bwd on ONE synthetic
+    1x1x40x56x40 Hippocampus-shaped patch on the host cores (oracle port, fp32, all threads)."""
+    import numpy as np
+    import torch
+    import random
+    from oracle import masking as omask
+    from oracle import network as onet
+    from e2enet_medical_b200.training import POOLS
+    torch.set_num_threads(os.cpu_count() or 1)
+    pools, patch, ncls = POOLS["hippo"], (40, 56, 40), 3
+    shapes = onet.param_shapes(1, 48, ncls, pools)
+    params = onet.det_params(shapes, seed=0)
+    random.seed(0)
+    for k, m in omask.init_uniform(shapes, DENSITY).items():
+        params[k].mul_(torch.from_numpy(m))
+    plist = [v.requires_grad_(True) for v in params.values()]
+    rs = np.random.RandomState(1)
+    x = torch.from_numpy(rs.rand(1, 1, *patch).astype(np.float32))
+    tg, sp = [], np.array(patch)
+    for k in range(4):
+        tg.append(torch.from_numpy(np.round(rs.rand(1, 1, *sp) * (ncls - 1)).astype(np.float32)))
+        sp = sp // np.array(pools[k])
+
+    def one():
+        for q in plist:
+            q.grad = None
+        onet.ds_loss(onet.unetpp_forward(params, x, pools), tg).backward()
+
+    one()
+    t0, n = time.perf_counter(), 0
+    while n < 3 or (time.perf_counter() - t0 < budget_s and n < 20):
+        one()
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": "patches/s", "ms_per_patch": dt * 1e3, "cores": os.cpu_count(), "kind": "port",
+            "sample": "BASELINE.json configs[0] unscaled: oracle fwd + DS loss + bwd on one 1x1x40x56x40 patch, fp32, "
+                      "%d timed iterations" % n}
+
+
+def torch_cudnn_baseline(dev, steps=4):
+    """the 'honest before' (SURVEY 2.3 / 8d): the reference's stock PyTorch / cuDNN path on the SAME B200.  The
+    oracle's functional restatement of the reference network (torch ops: F.pad-free slicing shift, torch.cat,
+    cuDNN Conv3d / ConvTranspose3d, InstanceNorm, LeakyReLU, MaxPool3d) runs on CUDA under autocast exactly as
+    nnUNetTrainer_simple.run_iteration does (fp16 + GradScaler, :549-564) and under bf16 autocast: config 2
+    training iteration (B=2) and the config-3 per-tile forward.  A comparator only: nothing here is shipped."""
+    import numpy as np
+    import torch
+    import random
+    from collections import OrderedDict
+    from oracle import masking as omask
+    from oracle import network as onet
+    from e2enet_medical_b200.training import POOLS, synthetic_batch
+    pools = POOLS["btcv"]
+    out = {"what": "stock torch %s / cuDNN %s on this GPU through oracle.network (functional restatement of the "
+                   "reference modules), TF32 allowed as torch defaults" % (torch.__version__, torch.backends.cudnn.version())}
+    torch.backends.cudnn.benchmark = True
+    shapes = onet.param_shapes(IN_CH, 48, NCLS, pools)
+    params = OrderedDict((k, v.to(dev)) for k, v in onet.det_params(shapes, seed=0).items())
+    random.seed(0)
+    masks = {k: torch.from_numpy(m).to(dev) for k, m in omask.init_uniform(shapes, DENSITY).items()}
+    with torch.no_grad():
+        for k, m in masks.items():
+            params[k].mul_(m)
+    plist = [v.requires_grad_(True) for v in params.values()]
+    data, targets = synthetic_batch(BATCH, IN_CH, NCLS, PATCH, pools, seed=1)
+    x, tg = data.to(dev), [t.to(dev) for t in targets]
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    for mode in ("fp16", "bf16"):
+        opt = torch.optim.SGD(plist, 1e-2, weight_decay=3e-5, momentum=0.99, nesterov=True)
+        scaler = torch.amp.GradScaler("cuda", enabled=(mode == "fp16"))
+        dt_ = torch.float16 if mode == "fp16" else torch.bfloat16
+
+        def one():
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=dt_):
+                outs = onet.unetpp_forward(params, x, pools)
+                l = onet.ds_loss(outs, tg)
+            scaler.scale(l).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(plist, 12)
+            scaler.step(opt)
+            scaler.update()
+            with torch.no_grad():                       # Masking.apply_mask as the reference does it (core_channel.py:427-434)
+                for k, m in masks.items():
+                    params[k].data = params[k].data * m
+                    st = opt.state[params[k]]
+                    if 'momentum_buffer' in st:
+                        st['momentum_buffer'] = st['momentum_buffer'] * m
+            return l
+
+        try:
+            for _ in range(3):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = ev(), ev()
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["train_" + mode] = {"ms_per_step": ms, "patches_per_s": BATCH / (ms / 1e3),
+                                    "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        except Exception as e:                          # noqa: BLE001 -- a comparator must not kill the bench line
+            out["train_" + mode] = {"error": repr(e)[:200]}
+        del opt
+        for q in plist:
+            q.grad = None
+        torch.cuda.empty_cache()
+    # config-3 per-tile forward (B=1 tile, 16 classes), as predict_3D runs it: autocast + no_grad
+    shapes16 = onet.param_shapes(1, 48, 16, pools)
+    p16 = OrderedDict((k, v.to(dev)) for k, v in onet.det_params(shapes16, seed=0).items())
+    tile = torch.randn((1, 1) + PATCH, device=dev)
+    for mode in ("fp16", "bf16"):
+        dt_ = torch.float16 if mode == "fp16" else torch.bfloat16
+        try:
+            with torch.no_grad(), torch.autocast("cuda", dtype=dt_):
+                for _ in range(3):
+                    onet.unetpp_forward(p16, tile, pools, deep_supervision=False)
+                torch.cuda.synchronize()
+                e0, e1 = ev(), ev()
+                e0.record()
+                for _ in range(steps):
+                    torch.softmax(onet.unetpp_forward(p16, tile, pools, deep_supervision=False), 1)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out["tile_forward_" + mode] = {"ms_per_tile": ms, "voxels_per_s_324_tiles": 78643200.0 / (324 * ms / 1e3)}
+        except Exception as e:                          # noqa: BLE001
+            out["tile_forward_" + mode] = {"error": repr(e)[:200]}
+    torch.backends.cudnn.benchmark = False
+    return out
+
+
+def masking_update_leg(ts, dev):
+    """BASELINE.json configs[4] / SURVEY 8(d): wall time and kernel launches of Masking.step() WITH a prune /
+    regrow update on the config-2 network (35 masked tensors, 2 072 832 kernels), and without."""
+    import torch
+    import random
+    from e2enet_medical_b200 import _lib
+    m = ts.mask
+    keep = m.prune_every_k_steps
+    res = {}
+    for tag, every in (("step_no_update", None), ("step_with_update", 1)):
+        m.prune_every_k_steps = every
+        random.seed(1)
+        m.step()                                       # warm-up (allocations)
+        torch.cuda.synchronize()
+        n0, t0 = _lib.launch_count(), time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            m.step()
+        torch.cuda.synchronize()
+        res[tag] = {"wall_ms": (time.perf_counter() - t0) / reps * 1e3, "launches": (_lib.launch_count() - n0) / reps}
+    m.prune_every_k_steps = keep
+    res["what"] = ("Masking.step() on the config-2 network: apply_mask + death-rate decay (+ kernel_death for all 35 "
+                   "tensors, host random.sample growth, kernel_growth, apply_mask, counts when updating); wall clock "
+                   "incl. the host-side sampling and the read-backs the reference's bookkeeping needs")
+    return res
+
+
+def measured_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture of this round (never typed in):
+    profiles/*_traffic.json = {"kernel": ..., "dram_read_bytes": ..., "dram_write_bytes": ..., "algorithmic_bytes": ...}"""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if not cands:
+        return None, None
+    d = json.load(open(cands[-1]))
+    return float(d["dram_read_bytes"]) + float(d["dram_write_bytes"]), \
+        "%s (%s; algorithmic bytes %.4g)" % (d.get("kernel"), os.path.basename(cands[-1]), d.get("algorithmic_bytes", 0))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -272,11 +449,10 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tf_sustained"],
-                     # one `ncu --set full` capture of the family's largest launch (loc4 forward, conv_tc_kernel<1,4>,
-                     # profiles/r01_ncu_conv_tc_loc4_fwd_details.txt): dram read 618.8 MB + write 286.0 MB per launch
-                     # vs 943.7 MB algorithmic (2 x 48-ch bf16 sources + 48-ch bf16 result): no wasted re-reads
-                     "traffic": 904.8e6,
-                     "traffic_of": "conv_tc_kernel<1,4> loc4 forward launch (algorithmic bytes 943.7e6, 271.8 GFLOP)",
+                     # dram bytes per launch of the family's largest launch, read from the committed ncu capture
+                     # (profiles/r*_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); null if absent
+                     "traffic": measured_traffic()[0],
+                     "traffic_of": measured_traffic()[1],
                      "kernel": "tcgen05 conv / transposed-conv / 1x1 GEMM launches of one step: conv_tc_kernel (fwd + "
                                "dgrad; key 'gemm') and wgrad_tc_kernel (key 'wgrad'); dense 2MNK FLOPs",
                      "per_kind": {k: dict(v, frac=v["achieved_tflops"] / peaks["tf_sustained"]) for k, v in per_kind.items()},
@@ -287,14 +463,29 @@ def run_ours(args):
     }
     if not args.no_inference:
         line["inference"] = inference_leg(dev, world, rank, args)
+    if world == 1 and not args.no_extras:
+        try:
+            line["masking_update"] = masking_update_leg(ts, dev)
+        except Exception as e:                          # noqa: BLE001
+            line["masking_update"] = {"error": repr(e)[:200]}
+        ts._graph = None
+        del ts
+        torch.cuda.empty_cache()
+        line["torch_cudnn_baseline"] = torch_cudnn_baseline(dev)
+        tb = line["torch_cudnn_baseline"].get("train_fp16", {})
+        if "patches_per_s" in tb:
+            line["speedup_vs_torch_cudnn_fp16"] = {"device": value / tb["patches_per_s"], "e2e": e2e / tb["patches_per_s"]}
+        ts = None
     if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline_config0"] = cpu_baseline_config0()
         v, dt, n = cpu_baseline_patches_per_s()
         line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x96x96 crop "
                                           "(0.18 patch), %d steps of %.1f s" % (n, dt)}
     print(json.dumps(line))
     sys.stdout.flush()
-    _finish_ranks(ts, world)
+    if ts is not None:
+        _finish_ranks(ts, world)
 
 
 def _finish_ranks(ts, world):
@@ -385,6 +576,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel-impl", type=int, default=1, help="0: mma.sync gather kernels, 1: tcgen05 where available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the Masking-update and stock torch/cuDNN comparator legs")
     ap.add_argument("--no-graph", action="store_true", help="time eager steps only (no whole-step CUDA graph)")
     ap.add_argument("--no-inference", action="store_true", help="skip the sliding-window inference leg")
     ap.add_argument("--infer-volume", type=int, nargs=3, default=[300, 512, 512])

@@ -52,6 +52,8 @@ class GemmParams(C.Structure):
         ("out_mode", C.c_int32),
         ("impl", C.c_int32),
         ("col_bounds", C.c_int32),
+        ("stats", C.c_void_p),
+        ("stats_ctot", C.c_int32),
     ]
 
 
@@ -90,12 +92,15 @@ SIGNATURES = {
     "e2e_launch_count": (C.c_longlong, []),
     "e2e_gather_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
     "e2e_gather_gemm_multi": (C.c_int, [C.POINTER(GemmParams), _I32, _VP]),
+    "e2e_gather_gemm_stats_slots": (C.c_int, [C.POINTER(GemmParams), _I32]),
+    "e2e_in_stats_final": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _F, _VP, _VP, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
     "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_pack_weights_multi": (C.c_int, [_VP, _I32, _I64, _VP]),
     "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_nc_to_c8": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),
     "e2e_c8_to_nc": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),
+    "e2e_shift_depth": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I64, _I32, _I32, _VP]),
     "e2e_in_stats": (C.c_int, [_VP, _I32, _I32, _I64, _F, _VP, _I32, _VP, _VP, _VP]),
     "e2e_in_apply": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP]),
     "e2e_in_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _I32, _VP, _VP, _VP, _VP,
@@ -108,7 +113,7 @@ SIGNATURES = {
     "e2e_maxpool_bwd": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "e2e_add_inplace": (C.c_int, [_VP, _VP, _I64, _VP]),
     "e2e_mask_apply_multi": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I64, _VP]),
-    "e2e_mask_kernel_l1": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_mask_kernel_l1": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP]),
     "e2e_mask_kth": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP]),
     "e2e_mask_kill": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP, _VP]),
     "e2e_mask_dead_list": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP]),

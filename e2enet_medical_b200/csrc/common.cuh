@@ -105,13 +105,30 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-static inline int e2e_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
+// per-device caches: the SM count and "function attribute already set" flags are properties of the
+// CURRENT device, not of the process (one process may drive several GPUs)
+constexpr int E2E_MAX_DEVICES = 64;
+static inline int e2e_cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < E2E_MAX_DEVICES) ? dev : 0;
 }
+static inline int e2e_num_sms() {
+  static int sms[E2E_MAX_DEVICES] = {0};
+  const int dev = e2e_cur_device();
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+// true exactly once per (call site flag array, current device)
+struct E2eDevOnce {
+  bool done[E2E_MAX_DEVICES] = {false};
+  bool first() {
+    const int dev = e2e_cur_device();
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};

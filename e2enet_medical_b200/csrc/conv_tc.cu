@@ -66,6 +66,11 @@ struct TcParams {
   int npad[TC_MAX_CHUNKS];
   void* dst[E2E_MAX_SRC];
   int dst_cb[E2E_MAX_SRC];
+  // InstanceNorm statistics of the (bf16-rounded) result, reduced in the epilogue: every epilogue warp owns the
+  // slot  stats[((blockIdx.x * epi_warps + w) * B + b) * 2 + {0: sum, 1: sum of squares}][stats_ctot]
+  float* stats;
+  int stats_ctot;                  // channels per row of `stats` (destination channel = col.blk * 8 + e)
+  int stats_smem_off;              // byte offset of the per-warp accumulators [epi_warps][2][Npad] in dynamic smem
 };
 
 struct alignas(64) TcMaps {
@@ -212,12 +217,47 @@ __device__ __forceinline__ void tc_mma_f16_lh(uint32_t d_tmem, uint32_t a_lo, ui
       : "memory");
 }
 
+// Column sums over the 32 lanes of a warp for 32 columns at once: a halving butterfly (16 + 8 + 4 + 2 + 1 = 31
+// shuffles instead of 32 x 5); on return lane L holds the sum over all lanes of v[L].  v is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+// the same for 8 columns: lane L ends with the sum over all 32 lanes of v[L & 7]
+__device__ __forceinline__ float warp_colsum8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float r = v[0];
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
 struct ColInfo {            // one 8-column block of the result, decoded once per CTA
   int32_t off;              // voxel offset of (blk, od, oh, ow) inside one sample of the destination
   int32_t bstride;          // voxels per sample of that destination (dst_cb * Dd * Hd * Wd)
   int16_t od, oh, ow;
   int8_t dst;               // -1: dead block
   uint8_t chmask;
+  int32_t blk;              // destination channel block (statistics are indexed by destination channel)
 };
 
 constexpr int EPI_WARPS = 16;            // upper bound; the launch picks 8 or 16 (blockDim.x = 64 + 32 * warps)
@@ -257,6 +297,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     ci.dst = (int8_t)dst;
     ci.chmask = (uint8_t)c.chmask;
     ci.od = (int16_t)c.od; ci.oh = (int16_t)c.oh; ci.ow = (int16_t)c.ow;
+    ci.blk = c.blk;
     ci.off = dst >= 0 ? c.blk * plane + (c.od * p.Hd + c.oh) * p.Wd + c.ow : 0;
     ci.bstride = dst >= 0 ? p.dst_cb[dst] * plane : 0;
     s_cols[i] = ci;
@@ -426,6 +467,34 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     const int need_bounds = p.need_bounds;      // bit 0: depth, 1: H, 2: W may leave the destination grid
     int as = 0, aphase = 0;
     const int nwork = p.n_tiles * p.n_chunks;
+    // InstanceNorm statistics: this warp's accumulators [2][Npad] in shared memory, flushed to its own global
+    // slot whenever the (sample, column chunk) of the work items changes (both are monotonic per CTA or alternate
+    // with a short period) -- no atomics anywhere, so the statistics are bit-reproducible
+    const bool do_stats = p.stats != nullptr;
+    float* wstat = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off)) + (warp - 2) * 2 * Npad;
+    float* gslot = do_stats ? p.stats + (size_t)(blockIdx.x * epi_warps + (warp - 2)) * p.B * 2 * p.stats_ctot : nullptr;
+    int sb = -1, sch = -1;
+    auto flush_stats = [&](int fb, int fch) {
+      const int fn = p.npad[fch];
+      const ColInfo* fc = s_cols + fch * 32;
+      __syncwarp();
+      for (int c = lane; c < fn; c += 32) {
+        const ColInfo col = fc[c >> 3];
+        if (col.dst >= 0) {
+          float* g = gslot + (size_t)fb * 2 * p.stats_ctot + col.blk * 8 + (c & 7);
+          g[0] += wstat[c];
+          g[p.stats_ctot] += wstat[Npad + c];
+        }
+        wstat[c] = 0.f;
+        wstat[Npad + c] = 0.f;
+      }
+      __syncwarp();
+    };
+    if (do_stats) {
+      for (int i = lane; i < p.B * 2 * p.stats_ctot; i += 32) gslot[i] = 0.f;
+      for (int c = lane; c < 2 * Npad; c += 32) wstat[c] = 0.f;
+      __syncwarp();
+    }
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
       int t = work / p.n_chunks;
       const int ch = work - t * p.n_chunks;
@@ -436,6 +505,10 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       const int ht = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
       const int b = t / p.D;
+      if (do_stats && (b != sb || ch != sch)) {
+        if (sb >= 0) flush_stats(sb, sch);
+        sb = b; sch = ch;
+      }
       const int h = ht * TH + (r >> 3);
       const int hs = h * p.osh, ds = d * p.osd;
       mbar_wait_warp(tfull_bar(as), aphase, 64, p.poll);
@@ -452,6 +525,21 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         tc_ld16(acc0 + j * Npad + c0, v);
         if (two) tc_ld16(acc0 + j * Npad + c0 + 16, v + 16);
         tc_wait_ld();
+        if (do_stats) {
+          // sums of the values exactly as stored (bf16-rounded), rows outside the grid excluded
+          float t1[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t1[i] = (inb && (i < 16 || two)) ? bf16_round(__uint_as_float(v[i])) : 0.f;
+          float t2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t2[i] = t1[i] * t1[i];
+          const float s1 = warp_colsum32(t1, lane);
+          const float s2 = warp_colsum32(t2, lane);
+          if (c0 + lane < npc) {
+            wstat[c0 + lane] += s1;
+            wstat[Npad + c0 + lane] += s2;
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (u >= 2 && !two) break;
@@ -503,6 +591,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       if (lane == 0) mbar_arrive(tempty_bar(as));
       if (++as == AS) { as = 0; aphase ^= 1; }
     }
+    if (do_stats && sb >= 0) flush_stats(sb, sch);
   }
 
   tc_fence_before();
@@ -566,6 +655,9 @@ struct S3Params {
   const e2e_centry_t* cents;
   const bf16* wpacked;
   bf16* dst;
+  float* stats;                     // see TcParams::stats (slot = blockIdx.x * S3_EPI_WARPS + epilogue warp)
+  int stats_ctot;
+  int stats_smem_off;               // per-warp accumulators [S3_EPI_WARPS][2][Np]
 };
 
 __global__ void __launch_bounds__(S3_THREADS, 1)
@@ -709,6 +801,28 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     const int grp = (warp - 2) >> 2;
     const int nblk = Np >> 3;
     uint32_t mcount = 0;
+    const bool do_stats = p.stats != nullptr;
+    float* wstat = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off)) + (warp - 2) * 2 * Np;
+    float* gslot = do_stats ? p.stats + (size_t)(blockIdx.x * S3_EPI_WARPS + (warp - 2)) * p.B * 2 * p.stats_ctot : nullptr;
+    int sb = -1;
+    auto flush_stats = [&](int fb) {
+      __syncwarp();
+      for (int c = lane; c < Np; c += 32) {
+        float* g = gslot + (size_t)fb * 2 * p.stats_ctot + c;
+        if (c < p.stats_ctot) {
+          g[0] += wstat[c];
+          g[p.stats_ctot] += wstat[Np + c];
+        }
+        wstat[c] = 0.f;
+        wstat[Np + c] = 0.f;
+      }
+      __syncwarp();
+    };
+    if (do_stats) {
+      for (int i = lane; i < p.B * 2 * p.stats_ctot; i += 32) gslot[i] = 0.f;
+      for (int c = lane; c < 2 * Np; c += 32) wstat[c] = 0.f;
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int t = tile;
       const int wt = t % p.tiles_w; t /= p.tiles_w;
@@ -716,6 +830,10 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       const int d = t % p.D;
       const int b = t / p.D;
       const int w = wt * S3_ADV - 1 + lane;
+      if (do_stats && b != sb) {
+        if (sb >= 0) flush_stats(sb);
+        sb = b;
+      }
      for (int mt = 0; mt < S3_MT; ++mt, ++mcount) {
       const int as = (int)(mcount % (uint32_t)AS);
       const uint32_t aphase = (mcount / (uint32_t)AS) & 1u;
@@ -753,6 +871,20 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
             *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
           }
+          if (do_stats) {
+            float t1[8], t2[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              t1[e] = ok ? bf16_round(o[e]) : 0.f;
+              t2[e] = t1[e] * t1[e];
+            }
+            const float s1 = warp_colsum8(t1, lane);
+            const float s2 = warp_colsum8(t2, lane);
+            if (lane < 8) {
+              wstat[cb * 8 + lane] += s1;
+              wstat[Np + cb * 8 + lane] += s2;
+            }
+          }
         }
       }
       tc_fence_before();
@@ -760,6 +892,7 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       if (lane == 0) mbar_arrive(tempty_bar(as));
      }
     }
+    if (do_stats && sb >= 0) flush_stats(sb);
   }
 
   tc_fence_before();
@@ -802,13 +935,13 @@ int e2e_conv_tc_supported(const e2e_gemm_t* p) {
     if (p->Dd != p->Di || p->Hd != p->Hi || p->Wd != p->Wi || p->n_dst != 1) return 0;
     if (p->Npad % 48 != 0 || p->Npad > 240) return 0;
     const int region = ((p->n_cent / 2) * 3 * 2 * 16 * p->Npad + 1023) / 1024 * 1024;
-    if (region + 3 * S3_PPS * 2 * S3_SLAB > SMEM_BUDGET) return 0;       // resident weights + 3 stages
+    if (region + 3 * S3_PPS * 2 * S3_SLAB + S3_EPI_WARPS * 2 * (p->Npad / 3) * 4 + 128 > SMEM_BUDGET) return 0;   // resident weights + 3 stages + statistics
     return 3;
   }
   return 0;
 }
 
-static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t st) {
+static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v12000 encode, cudaStream_t st, int* slots_out) {
   S3Params p{};
   p.B = g->B; p.D = g->Di; p.H = g->Hi; p.W = g->Wi;
   p.n_cent = g->n_cent; p.N3 = g->Npad; p.Np = g->Npad / 3; p.ivd = g->ivd;
@@ -817,12 +950,21 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   const int npairs = g->n_cent / 2;
   p.b_region_bytes = (npairs * 3 * 2 * 16 * p.N3 + 1023) / 1024 * 1024;
   p.stage_bytes = S3_PPS * 2 * S3_SLAB;
-  int stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
+  const int stats_bytes = (S3_EPI_WARPS * 2 * p.Np * 4 + 127) / 128 * 128;      // always reserved: same geometry with / without
+  int stages = (SMEM_BUDGET - p.b_region_bytes - stats_bytes) / p.stage_bytes;
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.tiles_h = (p.H + S3_TH - 1) / S3_TH;
   p.tiles_w = (p.W + S3_ADV - 1) / S3_ADV;
   p.n_tiles = p.B * p.D * p.tiles_h * p.tiles_w;
+  {
+    int grid0 = e2e_num_sms();
+    if (grid0 > p.n_tiles) grid0 = p.n_tiles;
+    if (slots_out) { *slots_out = grid0 * S3_EPI_WARPS; return E2E_OK; }
+  }
+  p.stats = g->stats;
+  p.stats_ctot = g->stats_ctot;
+  p.stats_smem_off = p.b_region_bytes + p.stages * p.stage_bytes;
   {
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("E2E_TC_PREFETCH"); pf = e ? atoi(e) : 0; }   // measured: 0.34 -> 0.44 ms with prefetch on (the TMA unit, not latency, is the limit)
@@ -849,14 +991,13 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
       return E2E_ERR_CUDA;
     }
   }
-  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + stats_bytes + 1024;
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncAttributes fa;
     E2E_CUDA(cudaFuncGetAttributes(&fa, conv_tc3_kernel));
     E2E_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   227 * 1024 - (int)fa.sharedSizeBytes));
-    attr_done = true;
   }
   int grid = e2e_num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
@@ -867,7 +1008,19 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
 
 // gs[0..n): column chunks of ONE GEMM (same sources, grids, channel entries, taps and destinations;
 // different packed weights / column tables / widths), executed by one launch
-int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
+static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* slots_out);
+
+int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) { return conv_tc_fwd_impl(gs, n, st, nullptr); }
+
+// number of statistics slots (CTAs x epilogue warps) the launch for gs[0..n) would write; 0 if it is not served
+// by a tcgen05 kernel
+int e2e_conv_tc_stats_slots(const e2e_gemm_t* gs, int n) {
+  int slots = 0;
+  if (conv_tc_fwd_impl(gs, n, nullptr, &slots) != E2E_OK) return 0;
+  return slots;
+}
+
+static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* slots_out) {
   const e2e_gemm_t* g = gs;
   int form = e2e_conv_tc_supported(g);
   if (n < 1 || n > TC_MAX_CHUNKS) form = 0;
@@ -891,7 +1044,7 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
       e2e_set_error("conv_tc_fwd: the kw-stacked form takes a single column chunk");
       return E2E_ERR_UNSUPPORTED;
     }
-    return conv_tc3_launch(g, encode, st);
+    return conv_tc3_launch(g, encode, st, slots_out);
   }
   // host copies of the plan tables are not available here: in the halo form taps must have
   // |dh|,|dw| <= 1 and channel entries dh = dw = 0; the Python plan builder guarantees it.
@@ -942,6 +1095,10 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     if (sp < 0) { const char* e = getenv("E2E_TC_SERIAL"); sp = e ? atoi(e) : 1; }
     p.serial_prod = (halo && pps == 1) ? sp : 0;
   }
+  // statistics requested (or queried): 8 epilogue warps x [2][Npad] fp32 accumulators come out of the stage budget
+  const bool want_stats = g->stats != nullptr || slots_out != nullptr;
+  const int stats_bytes = want_stats ? (8 * 2 * npmax * 4 + 127) / 128 * 128 : 0;
+  const int budget = SMEM_BUDGET - stats_bytes;
   // resident weights: the whole packed operand of a chunk (all K pairs) fits beside >= 3 A stages
   p.b_res = 0; p.b_region_bytes = 0;
   {
@@ -949,14 +1106,14 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     const int gres = (grid / n) * n;
     static int allow = -1;
     if (allow < 0) { const char* e = getenv("E2E_TC_BRES"); allow = e ? atoi(e) : 1; }
-    if (allow && region <= 112 * 1024 && gres >= n && region + 3 * pps * p.a_stage_bytes <= SMEM_BUDGET) {
+    if (allow && region <= 112 * 1024 && gres >= n && region + 3 * pps * p.a_stage_bytes <= budget) {
       p.b_res = 1; p.b_region_bytes = region; grid = gres;
     }
   }
   int stages;
   for (;;) {
     p.stage_bytes = p.b_res ? pps * p.a_stage_bytes : (pps * (p.a_stage_bytes + p.b_stage_bytes) + 127) / 128 * 128;
-    stages = (SMEM_BUDGET - p.b_region_bytes) / p.stage_bytes;
+    stages = (budget - p.b_region_bytes) / p.stage_bytes;
     if (stages >= 3 || pps == 1) break;
     --pps;
   }
@@ -1005,13 +1162,16 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     p.dst[i] = i < g->n_dst ? g->dst[i] : nullptr;
     p.dst_cb[i] = i < g->n_dst ? g->dst_cb[i] : 0;
   }
-  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + 1024;
+  const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + stats_bytes + 1024;
+  p.stats = g->stats;
+  p.stats_ctot = g->stats_ctot;
+  p.stats_smem_off = p.b_region_bytes + p.stages * p.stage_bytes;
   typedef void (*kern_t)(const TcParams, const TcMaps);
   static const kern_t kerns[2][4] = {
       {conv_tc_kernel<false, 1>, conv_tc_kernel<false, 2>, conv_tc_kernel<false, 3>, conv_tc_kernel<false, 4>},
       {conv_tc_kernel<true, 1>, conv_tc_kernel<true, 2>, conv_tc_kernel<true, 3>, conv_tc_kernel<true, 4>}};
-  static bool attr_done = false;
-  if (!attr_done) {
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 4; ++b) {
         cudaFuncAttributes fa;
@@ -1019,7 +1179,6 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
         E2E_CUDA(cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024 - (int)fa.sharedSizeBytes));
       }
-    attr_done = true;
   }
   if (!p.b_res && grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
   // 16 epilogue warps when a tile has many accumulator columns per MMA (short K loops: data gradients
@@ -1031,6 +1190,8 @@ int e2e_conv_tc_fwd(const e2e_gemm_t* gs, int n, cudaStream_t st) {
     if (force < 0) { const char* e = getenv("E2E_TC_EPI"); force = e ? atoi(e) : 0; }
     if (force == 8 || force == 16) epi = force;
   }
+  if (want_stats) epi = 8;                 // the statistics accumulators are sized for 8 epilogue warps
+  if (slots_out) { *slots_out = grid * epi; return E2E_OK; }
   kerns[halo ? 1 : 0][m - 1]<<<grid, 64 + 32 * epi, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
@@ -1489,10 +1650,9 @@ static int wgrad_gshift_launch(const e2e_wgrad_t* g, PFN_cuTensorMapEncodeTiled_
     }
   }
   const int smem_bytes = p.stages * p.stage_bytes + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     E2E_CUDA(cudaFuncSetAttribute(wgrad_gshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
-    attr_done = true;
   }
   wgrad_gshift_kernel<<<p.n_groups * p.splits, TC_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("wgrad_gshift");
@@ -1620,11 +1780,10 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
     }
   }
   const int smem_bytes = p.stages * p.stage_bytes + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
     E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
-    attr_done = true;
   }
   if (halo)
     wgrad_tc_kernel<true><<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);

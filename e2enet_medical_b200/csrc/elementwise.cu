@@ -4,6 +4,8 @@
 // SM count, fp32 math, deterministic two-stage reductions (no float atomics).
 #include "common.cuh"
 
+#include <string.h>
+
 namespace {
 
 constexpr int EW_THREADS = 256;
@@ -123,6 +125,29 @@ __global__ void in_stats_final_kernel(const float* __restrict__ partial, int pla
   for (int c = lane; c < nchunk; c += 32) {
     s += partial[((long long)plane * nchunk + c) * 16 + j];
     q += partial[((long long)plane * nchunk + c) * 16 + 8 + j];
+  }
+  s = warp_sum_d(s);
+  q = warp_sum_d(q);
+  if (lane) return;
+  const double m = s / (double)V;
+  double var = q / (double)V - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// statistics from the per-slot partials a fused conv epilogue wrote: stats[slot][b][{sum, sumsq}][C].  One WARP per
+// (b, c), lanes stride over the slots in a fixed order (deterministic), fp64 accumulation.
+__global__ void in_stats_from_slots_kernel(const float* __restrict__ stats, int n_slots, int B, int C, long long V, float eps,
+                                           float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  double s = 0.0, q = 0.0;
+  for (int k = lane; k < n_slots; k += 32) {
+    const float* row = stats + ((long long)(k * B + b) * 2) * C + c;
+    s += row[0];
+    q += row[C];
   }
   s = warp_sum_d(s);
   q = warp_sum_d(q);
@@ -561,6 +586,30 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const uint4* __
   }
 }
 
+// ------------------------------------------------------------------ stand-alone depth shift (torch_shift.forward,
+// unetpp_d.py:45-59) on a plain NCDHW tensor of 2- or 4-byte elements: y[b,c,d] = x[b,c,d - s_c] with zero fill,
+// s_c = sign * (c / ceil(C/shift_size) - shift_size/2).  Inside ConvDropoutNormNonlin the shift is folded into
+// the conv's operand fetch; this kernel only serves direct calls of the exported module.  One thread moves one
+// VEC-byte piece of one (b, c, d) row of H*W elements.
+template <typename VEC>
+__global__ void __launch_bounds__(EW_THREADS) shift_depth_kernel(const VEC* __restrict__ x, VEC* __restrict__ y, int C, int D,
+                                                                 long long row_vecs, int group, int half, int sign,
+                                                                 long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / row_vecs, v = i - r * row_vecs;      // r = (b*C + c)*D + d
+    const int d = (int)(r % D);
+    const long long bc = r / D;
+    const int c = (int)(bc % C);
+    const int s = sign * (c / group - half);
+    const int ds = d - s;
+    VEC val;
+    memset(&val, 0, sizeof(VEC));
+    if (ds >= 0 && ds < D) val = x[(bc * D + ds) * row_vecs + v];
+    y[i] = val;
+  }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) add_inplace_kernel(uint4* __restrict__ y, const uint4* __restrict__ x,
                                                                  long long n16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
@@ -608,6 +657,15 @@ extern "C" int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, f
   E2E_LAUNCHED("in_stats_partial");
   const int n = B * Cb * 8 * 32;
   in_stats_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, V, eps, mean, rstd);
+  E2E_LAUNCHED("in_stats_final");
+  return E2E_OK;
+}
+
+extern "C" int e2e_in_stats_final(const float* stats, int32_t n_slots, int32_t B, int32_t C, int64_t V, float eps,
+                                  float* mean, float* rstd, void* stream) {
+  E2E_ARG(stats && mean && rstd && n_slots > 0 && B > 0 && C > 0 && V > 0, "in_stats_final: bad arguments");
+  const int n = B * C * 32;
+  in_stats_from_slots_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n_slots, B, C, V, eps, mean, rstd);
   E2E_LAUNCHED("in_stats_final");
   return E2E_OK;
 }
@@ -747,5 +805,32 @@ extern "C" int e2e_add_inplace(void* y, const void* x, int64_t n_elems, void* st
   add_inplace_kernel<<<ew_blocks(n_elems / 8), EW_THREADS, 0, (cudaStream_t)stream>>>((uint4*)y, (const uint4*)x,
                                                                                       n_elems / 8);
   E2E_LAUNCHED("add_inplace");
+  return E2E_OK;
+}
+
+extern "C" int e2e_shift_depth(const void* x, void* y, int32_t elem_bytes, int32_t B, int32_t C, int32_t D, int64_t HW,
+                               int32_t shift_size, int32_t sign, void* stream) {
+  E2E_ARG(x && y && B > 0 && C > 0 && D > 0 && HW > 0 && shift_size > 0, "shift_depth: bad arguments");
+  E2E_ARG(elem_bytes == 2 || elem_bytes == 4, "shift_depth: element size must be 2 or 4 bytes");
+  E2E_ARG(sign == 1 || sign == -1, "shift_depth: sign must be +1 (forward) or -1 (gradient)");
+  const int group = (C + shift_size - 1) / shift_size, half = shift_size / 2;
+  const long long row_bytes = HW * elem_bytes;
+  const long long rows = (long long)B * C * D;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool a16 = ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  if (row_bytes % 16 == 0 && a16) {
+    const long long total = rows * (row_bytes / 16);
+    shift_depth_kernel<uint4><<<ew_blocks(total), EW_THREADS, 0, st>>>((const uint4*)x, (uint4*)y, C, D, row_bytes / 16, group,
+                                                                         half, sign, total);
+  } else if (elem_bytes == 4) {
+    const long long total = rows * HW;
+    shift_depth_kernel<uint32_t><<<ew_blocks(total), EW_THREADS, 0, st>>>((const uint32_t*)x, (uint32_t*)y, C, D, HW, group,
+                                                                            half, sign, total);
+  } else {
+    const long long total = rows * HW;
+    shift_depth_kernel<uint16_t><<<ew_blocks(total), EW_THREADS, 0, st>>>((const uint16_t*)x, (uint16_t*)y, C, D, HW, group,
+                                                                            half, sign, total);
+  }
+  E2E_LAUNCHED("shift_depth");
   return E2E_OK;
 }

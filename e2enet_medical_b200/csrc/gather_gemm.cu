@@ -447,10 +447,9 @@ int launch_gemm(const e2e_gemm_t* p, cudaStream_t st) {
   const int smem = STAGES * 4096 + STAGES * NT * 32;
   const int smem_epi = (p->out_mode == 0) ? NT * BM * 2 : NT * BM * 4;
   const int smem_bytes = smem > smem_epi ? smem : smem_epi;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     E2E_CUDA(cudaFuncSetAttribute(gather_gemm_kernel<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_done = true;
   }
   dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)(p->Npad / NT));
   gather_gemm_kernel<WN><<<grid, THREADS, smem_bytes, st>>>(*p);
@@ -463,10 +462,9 @@ int launch_wgrad(const e2e_wgrad_t* p, cudaStream_t st) {
   constexpr int MT = 16 * WM;
   constexpr int STAGE_BYTES = (MT / 8) * KT * 16 + SG * KT * 16;
   const int smem_bytes = WSTAGES * STAGE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static E2eDevOnce attr_once;
+  if (attr_once.first()) {
     E2E_CUDA(cudaFuncSetAttribute(gather_wgrad_kernel<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_done = true;
   }
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   const int ntile = (int)((M + KT - 1) / KT);
@@ -490,6 +488,7 @@ int launch_wgrad(const e2e_wgrad_t* p, cudaStream_t st) {
 
 int e2e_conv_tc_fwd(const e2e_gemm_t* p, int n, cudaStream_t st);   // conv_tc.cu
 int e2e_conv_tc_supported(const e2e_gemm_t* p);
+int e2e_conv_tc_stats_slots(const e2e_gemm_t* gs, int n);
 int e2e_wgrad_tc(const e2e_wgrad_t* p, cudaStream_t st);
 int e2e_wgrad_tc_supported(const e2e_wgrad_t* p);
 
@@ -516,6 +515,14 @@ extern "C" int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* strea
   return E2E_OK;
 }
 
+extern "C" int e2e_gather_gemm_stats_slots(const e2e_gemm_t* p, int32_t n) {
+  if (p == nullptr || n < 1 || n > 12 || p->out_mode != 0) return 0;
+  for (int i = 0; i < n; ++i)
+    if (p[i].impl != 1 || !e2e_conv_tc_supported(p + i) || e2e_conv_tc_supported(p + i) != e2e_conv_tc_supported(p)) return 0;
+  if ((long long)p->B * p->Do * p->Ho * p->Wo <= 0) return 0;
+  return e2e_conv_tc_stats_slots(p, n);
+}
+
 static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   E2E_ARG(p != nullptr, "gather_gemm: null params");
   E2E_ARG(p->n_cent > 0 && (p->n_cent & 1) == 0, "gather_gemm: n_cent must be even and > 0 (got %d)", p->n_cent);
@@ -527,6 +534,7 @@ static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
   if (allow_tc && p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, 1, st);
+  E2E_ARG(p->stats == nullptr, "gather_gemm: fused statistics need the tcgen05 path (query e2e_gather_gemm_stats_slots first)");
   if (p->n_taps == 3) {
     e2e_set_error("gather_gemm: a kw-stacked plan (3 taps, N = 3 x Cout) is only executable by the tcgen05 kernel");
     return E2E_ERR_UNSUPPORTED;
@@ -565,7 +573,7 @@ extern "C" int e2e_pack_weights(const float* w, const float* mask, const int32_t
   const long long total = (long long)n_cent * n_taps * Npad;
   if (total <= 0) return E2E_OK;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > e2e_num_sms() * 16) blocks = e2e_num_sms() * 16;
   pack_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       w, mask, rowoff, centoff, tapoff, n_cent, n_taps, Npad, reinterpret_cast<bf16*>(wpacked));
   E2E_LAUNCHED("pack_weights");
@@ -576,7 +584,7 @@ extern "C" int e2e_pack_weights_multi(const e2e_pack_job_t* jobs, int32_t n_jobs
   E2E_ARG(jobs && n_jobs > 0 && total_items >= 0, "pack_weights_multi: bad arguments");
   if (total_items == 0) return E2E_OK;
   long long blocks = (total_items + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > e2e_num_sms() * 16) blocks = e2e_num_sms() * 16;
   pack_weights_multi_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(jobs, n_jobs, total_items);
   E2E_LAUNCHED("pack_weights_multi");
   return E2E_OK;
@@ -589,7 +597,7 @@ extern "C" int e2e_unpack_wgrad(const float* dwp, const int32_t* rowoff, const i
   const long long total = (long long)n_cent * n_taps * Npad * 8;
   if (total <= 0) return E2E_OK;
   int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > e2e_num_sms() * 16) blocks = e2e_num_sms() * 16;
   unpack_wgrad_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dwp, rowoff, centoff, tapoff, n_cent,
                                                                                   n_taps, Npad, grad);
   E2E_LAUNCHED("unpack_wgrad");

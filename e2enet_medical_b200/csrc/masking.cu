@@ -37,24 +37,39 @@ __global__ void __launch_bounds__(256) mask_apply_multi_kernel(float* const* __r
   }
 }
 
-// l1 = sum_kd( sum_kh( sum_kw |w| ) ), each level folded left to right in fp32 (core_channel.py:653-655)
+// One level of the reference's nested `sum(dim=-1)` (core_channel.py:653-655) over n <= 4 fp32 values, with the
+// association of the torch build the reference runs on:
+//   assoc 0 (torch CPU): left to right, ((a0 + a1) + a2) + a3
+//   assoc 1 (torch CUDA, where the reference's Masking lives -- it hard-codes .cuda()): the reduce kernel strides
+//           last_pow2(n) threads over the reduced dimension and combines them with a shuffle tree, i.e.
+//           n = 3: (a0 + a2) + a1,  n = 4: (a0 + a2) + (a1 + a3)   [measured on B200 / torch 2.11:
+//           tests/test_gpu_oracle_fullsize.py::test_cuda_sum_association..., SURVEY H6]
+__device__ __forceinline__ float fold_level(const float* a, int n, int assoc) {
+  if (assoc == 1 && n == 3) return __fadd_rn(__fadd_rn(a[0], a[2]), a[1]);
+  if (assoc == 1 && n == 4) return __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
+  float r = a[0];
+  for (int i = 1; i < n; ++i) r = __fadd_rn(r, a[i]);
+  return r;
+}
+
+// l1 = sum_kd( sum_kh( sum_kw |w| ) ): three nested folds of at most 4 values each
 __global__ void __launch_bounds__(256) kernel_l1_kernel(const float* __restrict__ w, int n_kernels, int kd, int kh, int kw,
-                                                        float* __restrict__ l1) {
+                                                        int assoc, float* __restrict__ l1) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_kernels) return;
   const float* p = w + (long long)i * kd * kh * kw;
-  float tot = 0.f;
+  float planes[4];
   for (int a = 0; a < kd; ++a) {
-    float plane = 0.f;
+    float rows[4];
     for (int b = 0; b < kh; ++b) {
-      float row = fabsf(p[0]);
-      for (int c = 1; c < kw; ++c) row = __fadd_rn(row, fabsf(p[c]));
+      float v[4];
+      for (int c = 0; c < kw; ++c) v[c] = fabsf(p[c]);
       p += kw;
-      plane = (b == 0) ? row : __fadd_rn(plane, row);
+      rows[b] = fold_level(v, kw, assoc);
     }
-    tot = (a == 0) ? plane : __fadd_rn(tot, plane);
+    planes[a] = fold_level(rows, kh, assoc);
   }
-  l1[i] = tot;
+  l1[i] = fold_level(planes, kd, assoc);
 }
 
 // exact k-th smallest of non-negative floats (bit pattern order == value order); one CTA
@@ -207,10 +222,12 @@ extern "C" int e2e_mask_apply_multi(float* const* w, float* const* mom, const fl
   return E2E_OK;
 }
 
-extern "C" int e2e_mask_kernel_l1(const float* w, int32_t n_kernels, int32_t kd, int32_t kh, int32_t kw, float* l1,
+extern "C" int e2e_mask_kernel_l1(const float* w, int32_t n_kernels, int32_t kd, int32_t kh, int32_t kw, int32_t assoc, float* l1,
                                   void* stream) {
   E2E_ARG(w && l1 && n_kernels > 0 && kd > 0 && kh > 0 && kw > 0, "mask_kernel_l1: bad arguments");
-  kernel_l1_kernel<<<(n_kernels + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_kernels, kd, kh, kw, l1);
+  E2E_ARG(kd <= 4 && kh <= 4 && kw <= 4, "mask_kernel_l1: kernel extents above 4 are not on the E2ENet path (got %d,%d,%d)", kd, kh, kw);
+  E2E_ARG(assoc == 0 || assoc == 1, "mask_kernel_l1: assoc must be 0 (torch CPU order) or 1 (torch CUDA order)");
+  kernel_l1_kernel<<<(n_kernels + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_kernels, kd, kh, kw, assoc, l1);
   E2E_LAUNCHED("mask_kernel_l1");
   return E2E_OK;
 }

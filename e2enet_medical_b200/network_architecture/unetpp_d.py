@@ -38,8 +38,9 @@ class InitWeights_He(object):
 
 
 class torch_shift(nn.Module):
-    """Kept for API parity (unetpp_d.py:38-59).  Inside ConvDropoutNormNonlin the shift is not
-    executed as an op: it becomes a per-channel-block depth offset of the conv's operand fetch."""
+    """unetpp_d.py:38-59.  Inside ConvDropoutNormNonlin the shift is not executed as an op: it becomes a
+    per-channel-block depth offset of the conv's operand fetch.  Called directly (as the reference's module
+    can be) it runs a small vectorised CUDA kernel (e2e_shift_depth) on the NCDHW tensor, differentiable."""
 
     def __init__(self, shift_size, dim, dim_num):
         super().__init__()
@@ -48,7 +49,10 @@ class torch_shift(nn.Module):
         self.dim_num = dim_num
 
     def forward(self, x):
-        raise RuntimeError("torch_shift is folded into the shift-conv kernel; call ConvDropoutNormNonlin instead")
+        if self.dim != 2 or self.dim_num != 3:
+            raise NotImplementedError("torch_shift (B200): only the depth shift of 3-D tensors (dim=2, dim_num=3) is "
+                                      "on the E2ENet path (unetpp_d.py:89-90); the H / W variants are ablations")
+        return ops.ShiftDepth.apply(x, self.shift_size)
 
 
 def _triple(v):

@@ -17,7 +17,7 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True}
+CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True}
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
@@ -121,6 +121,16 @@ def _repack_all(device):
         e.key = e.current_key(w)
 
 
+def pack_registry_keepalive(device):
+    """everything a captured CUDA graph's pack_weights_multi launch points at: the job table and, through it,
+    every packed operand / mask / plan table of the device.  A graph owner holds this so that later registry
+    changes (another network on the device, a dead entry) can never free memory the graph still writes."""
+    reg = _PACK_REG.get(str(device))
+    if reg is None:
+        return None
+    return (reg.get("table"), [(e.out, e.mask, e.wref(), e.tables) for e in reg["entries"]])
+
+
 def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
     """bf16 packed operand of `plan` for the current value of weight * mask.  Cached until the weight or
     its mask changes; when it does, every registered operand of the device is repacked by one kernel."""
@@ -162,19 +172,36 @@ def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor]
 
 def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optional[torch.Tensor],
                     srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, dsts: Sequence[torch.Tensor], dst_grid,
-                    dst_cb: Sequence[int], impl: int = 0):
-    """the column chunks of one GEMM (plans differ in columns / packed weights only): one launch."""
+                    dst_cb: Sequence[int], impl: int = 0, want_stats: bool = False):
+    """the column chunks of one GEMM (plans differ in columns / packed weights only): one launch.
+    want_stats: ask the tcgen05 epilogue for the InstanceNorm partial sums of the (single, C8) destination;
+    returns (stats tensor [slots][B][2][C], slots) or None when that launch cannot fuse them."""
     lib = _lib.load()
-    if len(plans) == 1:
-        return run_gemm(plans[0], pack_weights(plans[0], weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid,
-                        dst_cb, impl)
-    arr = (_lib.GemmParams * len(plans))()
+    n = len(plans)
+    arr = (_lib.GemmParams * n)()
     flops = 0.0
     for i, pl in enumerate(plans):
         _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl)
         flops += _plan_flops(pl, B * iter_grid[0] * iter_grid[1] * iter_grid[2])
+    stats = None
+    if want_stats and impl == 1 and CONFIG.get("fuse_stats", True):
+        key = ("_slots", tuple(src_grid), tuple(iter_grid), B, n, str(srcs[0].device))
+        slots = plans[0]._dev.get(key)
+        if slots is None:
+            slots = int(lib.e2e_gather_gemm_stats_slots(arr, n))
+            plans[0]._dev[key] = slots
+        if slots > 0:
+            ctot = 8 * int(dst_cb[0])
+            stats = torch.empty((slots, B, 2, ctot), dtype=torch.float32, device=srcs[0].device)
+            for i in range(n):
+                arr[i].stats = stats.data_ptr()
+                arr[i].stats_ctot = ctot
     with _Timed("gemm", flops):
-        _lib.check(lib.e2e_gather_gemm_multi(arr, len(plans), _lib.stream_ptr()), "gather_gemm_multi")
+        if n == 1:
+            _lib.check(lib.e2e_gather_gemm(C.byref(arr[0]), _lib.stream_ptr()), "gather_gemm")
+        else:
+            _lib.check(lib.e2e_gather_gemm_multi(arr, n, _lib.stream_ptr()), "gather_gemm_multi")
+    return stats
 
 
 def _fill_gemm(p, plan: GemmPlan, wpacked: torch.Tensor, srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl):
@@ -290,6 +317,33 @@ class FromC8(torch.autograd.Function):
         return nc_to_c8(dy), None
 
 
+class ShiftDepth(torch.autograd.Function):
+    """torch_shift.forward (unetpp_d.py:45-59) as a stand-alone op on a plain NCDHW CUDA tensor (fp32 / fp16 /
+    bf16): y[b,c,d] = x[b,c,d - s_c], zero fill.  The network never calls it (the shift is folded into the conv's
+    operand fetch); it backs direct calls of the exported `torch_shift` module."""
+
+    @staticmethod
+    def forward(ctx, x, shift_size):
+        _need_cuda(x, "shift_depth")
+        if x.dim() != 5 or x.element_size() not in (2, 4):
+            raise ValueError("shift_depth: expected a 5-D tensor of 2- or 4-byte elements, got %s %s"
+                             % (tuple(x.shape), x.dtype))
+        ctx.shift_size = int(shift_size)
+        return ShiftDepth._run(x.contiguous(), ctx.shift_size, 1)
+
+    @staticmethod
+    def _run(x, shift_size, sign):
+        B, Cc, D, H, W = x.shape
+        y = torch.empty_like(x)
+        _lib.check(_lib.load().e2e_shift_depth(_p(x), _p(y), x.element_size(), B, Cc, D, H * W, shift_size, sign,
+                                               _lib.stream_ptr()), "shift_depth")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ShiftDepth._run(dy.contiguous(), ctx.shift_size, -1), None
+
+
 class ShiftConvINLReLU(torch.autograd.Function):
     """depth-shift + Conv3d(1,3,3) + InstanceNorm3d(affine) + LeakyReLU over a virtual concat
     of C8 sources (reference: ConvDropoutNormNonlin.forward, unetpp_d.py:102-111).
@@ -310,20 +364,25 @@ class ShiftConvINLReLU(torch.autograd.Function):
         Cb = plan.cout // 8
         impl = CONFIG["impl"]
         raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
+        # the conv epilogue also reduces the InstanceNorm sums of the values it stores (no separate statistics pass)
         if impl == 1 and plan.fwd3 is not None and CONFIG.get("stack3", True):
             # narrow layer: kw-stacked tcgen05 kernel (N = 3 x Cout per MMA)
-            run_gemm(plan.fwd3, pack_weights(plan.fwd3, weight, mask), srcs, (D, H, W), (Do, Ho, Wo), B, [raw],
-                     (Do, Ho, Wo), [Cb], impl)
+            stats = run_gemm_chunks([plan.fwd3], weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb],
+                                    impl, want_stats=True)
         else:
-            run_gemm_chunks(plan.fwd_chunks, weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb],
-                            impl)
+            stats = run_gemm_chunks(plan.fwd_chunks, weight, mask, srcs, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                                    [Cb], impl, want_stats=True)
         V = Do * Ho * Wo
         nch = _nchunk(V, B * Cb)
-        partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
         mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
         rstd = torch.empty_like(mean)
-        _lib.check(lib.e2e_in_stats(_p(raw), B, Cb, V, EPS, _p(partial), nch, _p(mean), _p(rstd), _lib.stream_ptr()),
-                   "in_stats")
+        if stats is not None:
+            _lib.check(lib.e2e_in_stats_final(_p(stats), stats.shape[0], B, Cb * 8, V, EPS, _p(mean), _p(rstd),
+                                              _lib.stream_ptr()), "in_stats_final")
+        else:
+            partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+            _lib.check(lib.e2e_in_stats(_p(raw), B, Cb, V, EPS, _p(partial), nch, _p(mean), _p(rstd), _lib.stream_ptr()),
+                       "in_stats")
         y = torch.empty_like(raw)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         ctx.plan, ctx.slope, ctx.mask, ctx.grid = plan, slope, mask, (B, D, H, W, Do, Ho, Wo)

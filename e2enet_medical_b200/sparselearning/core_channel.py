@@ -135,10 +135,20 @@ class Masking(object):
         else:
             self.prune_every_k_steps = self.args.update_frequency
 
+        # fp32 association of the reference's nested sum(dim=-1) in kernel_death (core_channel.py:653-655).  The
+        # reference's Masking lives on the GPU (it hard-codes .cuda()), where torch's reduce kernel computes
+        # (a0 + a2) + a1 for three values; torch CPU folds left to right.  "cuda" reproduces the reference as it
+        # actually runs; "cpu" reproduces a CPU run of it (the committed goldens were generated on CPU).
+        self.sum_association = "cuda"
         self._tables = None       # cached device pointer tables for the multi-tensor kernels
         self._scratch = {}
 
     # ------------------------------------------------------------------ bookkeeping helpers
+    def _assoc(self) -> int:
+        if self.sum_association not in ("cuda", "cpu"):
+            raise ValueError("Masking.sum_association must be 'cuda' or 'cpu'")
+        return 1 if self.sum_association == "cuda" else 0
+
     def _params(self):
         """[(name, parameter)] of the masked tensors in named_parameters() order (= reference loop order)."""
         out = []
@@ -426,7 +436,8 @@ class Masking(object):
             kd, kh, kw = (int(s) for s in weight.shape[-3:])
             w = weight.data
             assert w.is_contiguous() and w.dtype == torch.float32
-            _lib.check(lib.e2e_mask_kernel_l1(_vp(w), n_kernels, kd, kh, kw, _vp(l1), _lib.stream_ptr()), "kernel_l1")
+            _lib.check(lib.e2e_mask_kernel_l1(_vp(w), n_kernels, kd, kh, kw, self._assoc(), _vp(l1), _lib.stream_ptr()),
+                       "kernel_l1")
             _lib.check(lib.e2e_mask_kth(_vp(l1), n_kernels, rank, _vp(thr), None, _lib.stream_ptr()), "mask_kth")
             _lib.check(lib.e2e_mask_kill(_vp(l1), _vp(thr), _vp(mask), n_kernels, k_size,
                                          C.c_void_p(kill_counts.data_ptr() + 8 * i), _lib.stream_ptr()), "mask_kill")
@@ -479,7 +490,8 @@ class Masking(object):
         thr = torch.empty(1, dtype=torch.float32, device=dev)
         cnt = torch.zeros(2, dtype=torch.int32, device=dev)
         kd, kh, kw = (int(s) for s in weight.shape[-3:])
-        _lib.check(lib.e2e_mask_kernel_l1(_vp(weight.data), n_kernels, kd, kh, kw, _vp(l1), _lib.stream_ptr()), "kernel_l1")
+        _lib.check(lib.e2e_mask_kernel_l1(_vp(weight.data), n_kernels, kd, kh, kw, self._assoc(), _vp(l1), _lib.stream_ptr()),
+                   "kernel_l1")
         _lib.check(lib.e2e_mask_kth(_vp(l1), n_kernels, rank, _vp(thr), None, _lib.stream_ptr()), "mask_kth")
         _lib.check(lib.e2e_mask_kill(_vp(l1), _vp(thr), _vp(mask), n_kernels, k_size, _vp(cnt), _lib.stream_ptr()), "mask_kill")
         return mask, prune_num

@@ -181,6 +181,8 @@ class TrainStep(object):
             self.mask.apply_mask()
         self.graph_launches = _lib.launch_count() - n0       # kernels of libe2enet_b200.so inside one replay
         self._graph = graph                                   # (capture records, it does not execute)
+        from . import ops
+        self._graph_keepalive = ops.pack_registry_keepalive(self.device)   # memory the graph's pack launch points at
         return self
 
     def _graph_step(self, data, targets):

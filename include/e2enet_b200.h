@@ -87,12 +87,22 @@ typedef struct {
   int32_t impl;                      /* 0: mma.sync gather kernel   1: tcgen05/TMA kernel (halo / 1-tap forms) */
   int32_t col_bounds;                /* bit 0 / 1 / 2: a column block's destination depth / row / column can fall
                                         outside the destination grid and must be checked (7 is always safe) */
+  /* InstanceNorm statistics fused into the epilogue (tcgen05 path, out_mode 0 only; may be null): per-slot partial
+   * sums of the bf16-rounded result, stats[slot][b][{sum, sum of squares}][stats_ctot] fp32, channel index =
+   * destination channel; slots = e2e_gather_gemm_stats_slots() (one per CTA x epilogue warp; every slot is
+   * written completely, no atomics: bit-reproducible).  Reduce with e2e_in_stats_final().  Replaces the separate
+   * statistics pass over the conv output of ConvDropoutNormNonlin (unetpp_d.py:108-110). */
+  float* stats;
+  int32_t stats_ctot;
 } e2e_gemm_t;
 
 int e2e_gather_gemm(const e2e_gemm_t* p, void* stream);
 /* p[0..n): column chunks of one GEMM -- identical except wpacked / cols / Npad (a result wider than
  * 256 columns is split by the host plan); one kernel launch on the tcgen05 path */
 int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* stream);
+/* slots the launch e2e_gather_gemm_multi(p, n) would write into p->stats; 0 when that launch cannot fuse the
+ * statistics (mma.sync path, fp32 output): then run e2e_in_stats on the result instead */
+int e2e_gather_gemm_stats_slots(const e2e_gemm_t* p, int32_t n);
 
 /*
  * dwp[e/2][t][e%2][n][j] += sum_o grad[b, n/8, o, n%8] * src[...][(o*is + iv + cent[e].off + tap[t].off), j]
@@ -147,10 +157,19 @@ int e2e_unpack_wgrad(const float* dwp, const int32_t* rowoff, const int32_t* cen
 int e2e_nc_to_c8(const float* x, void* y, int32_t B, int32_t C, int64_t V, void* stream);     /* fp32 NCDHW -> bf16 C8 (C padded to 8) */
 int e2e_c8_to_nc(const void* x, float* y, int32_t B, int32_t C, int64_t V, void* stream);     /* bf16 C8 -> fp32 NCDHW */
 
+/* stand-alone depth shift on a plain NCDHW tensor of 2- or 4-byte elements (torch_shift.forward, unetpp_d.py:45-59):
+ * y[b,c,d,:] = x[b,c,d - sign*s_c,:] with zero fill, s_c = c / ceil(C/shift_size) - shift_size/2; sign = -1 is the
+ * gradient.  (Inside the shift-conv the shift is folded into the operand fetch; this serves direct module calls.) */
+int e2e_shift_depth(const void* x, void* y, int32_t elem_bytes, int32_t B, int32_t C, int32_t D, int64_t HW,
+                    int32_t shift_size, int32_t sign, void* stream);
+
 /* ---------------------------------------------------------------- InstanceNorm + LeakyReLU */
 /* per (b, c): mean and rstd of raw over V voxels; partial: scratch fp32 [B*Cb][nchunk][16] */
 int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, float eps, float* partial, int32_t nchunk,
                  float* mean, float* rstd, void* stream);
+/* mean / rstd from the per-slot partials a fused conv epilogue wrote (e2e_gemm_t.stats): fixed-order fp64 reduce */
+int e2e_in_stats_final(const float* stats, int32_t n_slots, int32_t B, int32_t C, int64_t V, float eps, float* mean,
+                       float* rstd, void* stream);
 int e2e_in_apply(const void* raw, const float* mean, const float* rstd, const float* gamma, const float* beta,
                  float slope, int32_t B, int32_t Cb, int64_t V, void* out, void* stream);
 /* backward: sums[b][c] = {sum dz, sum dz*xhat}; then draw, dgamma, dbeta, dbias */
@@ -182,8 +201,11 @@ int e2e_add_inplace(void* y, const void* x, int64_t n_elems, void* stream);
 /* multi-tensor apply_mask: w[i] *= m[i]; mom[i] *= m[i] (mom may be null); ptr tables are device arrays */
 int e2e_mask_apply_multi(float* const* w, float* const* mom, const float* const* mask, const int64_t* numel,
                          int32_t n_tensors, int64_t max_numel, void* stream);
-/* kernel L1: l1[a*C1+b] = nested fp32 sums over (kd,kh,kw) of |w| with the reference's association */
-int e2e_mask_kernel_l1(const float* w, int32_t n_kernels, int32_t kd, int32_t kh, int32_t kw, float* l1, void* stream);
+/* kernel L1: l1[a*C1+b] = nested fp32 sums over (kd,kh,kw <= 4) of |w| with the reference's association:
+ * assoc 0 = torch CPU (left to right), assoc 1 = torch CUDA reduce order ((a0+a2)+a1 for 3 values) -- the reference's
+ * Masking computes it on the GPU, so 1 is what reproduces its prune sets bit for bit */
+int e2e_mask_kernel_l1(const float* w, int32_t n_kernels, int32_t kd, int32_t kh, int32_t kw, int32_t assoc, float* l1,
+                       void* stream);
 /* k-th smallest (0-based rank) of l1[0..n): exact radix select; result -> *thr (device) */
 int e2e_mask_kth(const float* l1, int32_t n, int32_t rank, float* thr, uint32_t* scratch, void* stream);
 /* mask[kernel,:] = 0 for l1 <= *thr; counts[0] = kernels alive after; counts[1] = dead kernels after */

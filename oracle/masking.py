@@ -29,15 +29,28 @@ def is_masked_name(name: str) -> bool:
     return sel and ('bias' not in name) and ('instnorm' not in name)
 
 
-def kernel_l1(w: np.ndarray) -> np.ndarray:
-    """sum(sum(sum(|w|, -1), -1), -1) in fp32 with left-to-right association at every
-    level (core_channel.py:653-655; association verified against CPU torch)."""
+def kernel_l1(w: np.ndarray, assoc: str = "cpu") -> np.ndarray:
+    """sum(sum(sum(|w|, -1), -1), -1) in fp32 (core_channel.py:653-655) with the association of the torch
+    build the reference runs on:
+      "cpu"  -- left to right at every level (verified against CPU torch; the committed goldens);
+      "cuda" -- torch's CUDA reduce kernel strides last_pow2(n) threads over the reduced axis and combines them
+                with a shuffle tree: (a0 + a2) + a1 for n = 3, (a0 + a2) + (a1 + a3) for n = 4 (measured on
+                B200 / torch 2.11 by tests/test_gpu_oracle_fullsize.py).  The reference's Masking
+                hard-codes .cuda(), so this is the order of a real run."""
     a = np.abs(w.astype(np.float32, copy=False))
+    f32 = np.float32
 
     def fold(t):
+        n = t.shape[-1]
+        if assoc == "cuda" and n == 3:
+            return ((t[..., 0] + t[..., 2]).astype(f32) + t[..., 1]).astype(f32)
+        if assoc == "cuda" and n == 4:
+            return ((t[..., 0] + t[..., 2]).astype(f32) + (t[..., 1] + t[..., 3]).astype(f32)).astype(f32)
+        if assoc not in ("cpu", "cuda") or n > 4 and assoc == "cuda":
+            raise ValueError("kernel_l1: association %r for %d values is not pinned" % (assoc, n))
         acc = t[..., 0].copy()
-        for k in range(1, t.shape[-1]):
-            acc = (acc + t[..., k]).astype(np.float32)
+        for k in range(1, n):
+            acc = (acc + t[..., k]).astype(f32)
         return acc
 
     return fold(fold(fold(a)))
@@ -70,12 +83,12 @@ def apply_mask(weights: Dict[str, np.ndarray], masks: Dict[str, np.ndarray],
             momentum[name] *= m
 
 
-def kernel_death(mask: np.ndarray, w: np.ndarray, death_rate: float):
+def kernel_death(mask: np.ndarray, w: np.ndarray, death_rate: float, assoc: str = "cpu"):
     """core_channel.py:647-666.  Returns (new_mask (in place), prune_num)."""
     k_size = int(np.prod(w.shape[-3:]))
     nnz = float(mask.sum(dtype=np.float64))                         # mask.sum().item() is exact (< 2^24)
     nzero = mask.size - nnz
-    l1 = kernel_l1(w)
+    l1 = kernel_l1(w, assoc)
     prune_num = math.ceil(death_rate * nnz / k_size)
     num_zeros = math.ceil(nzero / k_size)
     value = np.sort(l1.reshape(-1), kind="stable")
@@ -102,14 +115,14 @@ def kernel_growth(mask: np.ndarray, num_growth: int, rng=random) -> np.ndarray:
     return out
 
 
-def prune_regrow(weights, masks, death_rate: float, momentum=None, rng=random):
+def prune_regrow(weights, masks, death_rate: float, momentum=None, rng=random, assoc: str = "cpu"):
     """truncate_weights (core_channel.py:556-611): death for ALL tensors, then growth for
     ALL tensors (one rng.sample per tensor, in order), then apply_mask.
     Returns dict(num_death, num_remove, pruned_masks)."""
     num_death, num_remove, pruned = {}, {}, {}
     for name in masks:
         nnz0 = float(masks[name].sum(dtype=np.float64))
-        m, pn = kernel_death(masks[name], weights[name], death_rate)
+        m, pn = kernel_death(masks[name], weights[name], death_rate, assoc)
         num_death[name] = pn
         num_remove[name] = int(nnz0 - float(m.sum(dtype=np.float64)))
         pruned[name] = m.copy()

@@ -146,3 +146,62 @@ def test_tcgen05_kw_stacked_forward(src, cout, spatial, B):
     torch.cuda.synchronize()
     assert not torch.isnan(b_.float()).any()
     assert rel(b_, a) < ULP, rel(b_, a)
+
+
+@pytest.mark.parametrize("src,cout,stride,spatial,B,use3", [
+    ([48, 48], 48, (1, 1, 1), (3, 9, 70), 2, True),        # kw-stacked narrow kernel, ragged tiles
+    ([48, 48], 48, (1, 1, 1), (5, 37, 45), 3, False),      # halo form, m = 4, partial tiles, B = 3
+    ([96, 96, 48], 96, (1, 1, 1), (5, 12, 16), 2, False),  # halo form, m = 2, three 32-column chunks
+    ([320, 320, 192], 320, (1, 1, 1), (4, 5, 5), 2, False),  # Cout 320 -> two column chunks in one launch
+    ([1], 48, (1, 1, 1), (6, 16, 16), 2, False),           # network input layer
+    ([48], 96, (1, 2, 2), (6, 16, 16), 2, False),          # strided encoder conv: point form
+    ([192], 320, (2, 2, 2), (4, 10, 12), 1, False),        # strided, two column chunks, odd output grid
+])
+def test_fused_epilogue_instancenorm_statistics(src, cout, stride, spatial, B, use3):
+    """InstanceNorm statistics reduced in the conv epilogue (e2e_gemm_t.stats + e2e_in_stats_final) vs the
+    separate statistics pass over the stored tensor (e2e_in_stats) and vs torch on the stored values; the fused
+    path has no atomics, so two runs must agree bit for bit."""
+    import ctypes as C
+    from e2enet_medical_b200 import _lib, ops
+    from e2enet_medical_b200.plans import build_shiftconv_plan
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(4)
+    cin = sum(src)
+    plan = build_shiftconv_plan(src, cout, stride)
+    D, H, W = spatial
+    Do, Ho, Wo = plan.out_grid(D, H, W)
+    bf = lambda t: t.bfloat16().float()
+    xs8 = [ops.nc_to_c8(bf(torch.from_numpy((rs.standard_normal((B, c) + spatial) + 0.3).astype(np.float32))).to(dev))
+           for c in src]
+    w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
+    Cb, V = cout // 8, Do * Ho * Wo
+    plans = [plan.fwd3] if use3 else plan.fwd_chunks
+    assert plans[0] is not None
+    p = lambda t: C.c_void_p(t.data_ptr())
+    res = []
+    for rep in range(2):
+        raw = torch.full((B, Cb, Do, Ho, Wo, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+        stats = ops.run_gemm_chunks(plans, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], 1,
+                                    want_stats=True)
+        assert stats is not None and stats.shape[1:] == (B, 2, cout), "the tcgen05 launch must fuse the statistics"
+        mean = torch.empty(B * cout, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        _lib.check(lib.e2e_in_stats_final(p(stats), stats.shape[0], B, cout, V, 1e-5, p(mean), p(rstd), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        res.append((raw, mean, rstd))
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2]), "fused statistics are not reproducible"
+    raw, mean, rstd = res[0]
+    nch = ops._nchunk(V, B * Cb)
+    partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+    mean2 = torch.empty_like(mean)
+    rstd2 = torch.empty_like(mean)
+    _lib.check(lib.e2e_in_stats(p(raw), B, Cb, V, 1e-5, p(partial), nch, p(mean2), p(rstd2), _lib.stream_ptr()))
+    y = ops.c8_to_nc(raw, cout).double()
+    m_ref = y.mean((2, 3, 4)).flatten()
+    r_ref = (1.0 / torch.sqrt(y.var((2, 3, 4), unbiased=False) + 1e-5)).flatten()
+    torch.cuda.synchronize()
+    scale = float(y.abs().max())
+    assert float((mean.double() - m_ref).abs().max()) < 1e-5 * scale
+    assert float(((rstd.double() - r_ref) / r_ref).abs().max()) < 1e-4
+    assert float((mean - mean2).abs().max()) < 1e-5 * scale and float(((rstd - rstd2) / rstd2).abs().max()) < 1e-4
