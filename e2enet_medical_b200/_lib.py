@@ -54,6 +54,7 @@ class GemmParams(C.Structure):
         ("col_bounds", C.c_int32),
         ("stats", C.c_void_p),
         ("stats_ctot", C.c_int32),
+        ("accumulate", C.c_int32),
     ]
 
 
@@ -84,6 +85,10 @@ class PackJob(C.Structure):
                 ("pad_", C.c_int32), ("out", C.c_void_p), ("item_begin", C.c_int64)]
 
 
+class SgdTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("mom", C.c_void_p), ("mask", C.c_void_p), ("numel", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/e2enet_b200.h
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
@@ -93,6 +98,7 @@ SIGNATURES = {
     "e2e_gather_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
     "e2e_gather_gemm_multi": (C.c_int, [C.POINTER(GemmParams), _I32, _VP]),
     "e2e_gather_gemm_stats_slots": (C.c_int, [C.POINTER(GemmParams), _I32]),
+    "e2e_gather_gemm_on_tcgen05": (C.c_int, [C.POINTER(GemmParams), _I32]),
     "e2e_in_stats_final": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _F, _VP, _VP, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
     "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
@@ -119,10 +125,15 @@ SIGNATURES = {
     "e2e_mask_dead_list": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "e2e_mask_grow": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "e2e_mask_counts": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
+    "e2e_sgd_partial_count": (C.c_int, [_I32, _I64]),
+    "e2e_sgd_clip_coef": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _VP, _VP]),
+    "e2e_sgd_update": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _I32, _VP]),
     "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP]),
     "e2e_softmax_stats_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I64, _VP, _VP]),
     "e2e_window_accumulate": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                         _I32, _I32, _F, _I32, _I32, _VP]),
+    "e2e_window_head_accumulate": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                             _I32, _I32, _I32, _F, _I32, _VP]),
     "e2e_window_finalize": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
 }
 

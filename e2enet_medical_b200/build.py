@@ -2,7 +2,8 @@
 
     python -m e2enet_medical_b200.build [--force]
 
-The .so is git-ignored but travels to the GPU box with the repo snapshot.
+The .so and the _build/ objects + ptxas logs are git-ignored (.gitignore) but travel to the GPU box with the
+repo snapshot.
 """
 from __future__ import annotations
 
@@ -19,7 +20,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libe2enet_b200.so")
 
-SOURCES = ["api.cu", "gather_gemm.cu", "conv_tc.cu", "elementwise.cu", "masking.cu", "window.cu", "loss.cu"]
+SOURCES = ["api.cu", "gather_gemm.cu", "conv_tc.cu", "elementwise.cu", "masking.cu", "window.cu", "loss.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DE2E_B200=1", "-I" + INCLUDE,
               "-Xptxas", "-v"]

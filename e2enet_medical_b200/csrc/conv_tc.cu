@@ -66,11 +66,12 @@ struct TcParams {
   int npad[TC_MAX_CHUNKS];
   void* dst[E2E_MAX_SRC];
   int dst_cb[E2E_MAX_SRC];
-  // InstanceNorm statistics of the (bf16-rounded) result, reduced in the epilogue: every epilogue warp owns the
-  // slot  stats[((blockIdx.x * epi_warps + w) * B + b) * 2 + {0: sum, 1: sum of squares}][stats_ctot]
+  // InstanceNorm statistics of the (bf16-rounded) result, reduced in the epilogue: every CTA owns the slot
+  // stats[(blockIdx.x * B + b) * 2 + {0: sum, 1: sum of squares}][stats_ctot]
   float* stats;
   int stats_ctot;                  // channels per row of `stats` (destination channel = col.blk * 8 + e)
   int stats_smem_off;              // byte offset of the per-warp accumulators [epi_warps][2][Npad] in dynamic smem
+  int accum;                       // the result is ADDED to the destination (gradient fan-in of an activation)
 };
 
 struct alignas(64) TcMaps {
@@ -254,17 +255,22 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 struct ColInfo {            // one 8-column block of the result, decoded once per CTA
   int32_t off;              // voxel offset of (blk, od, oh, ow) inside one sample of the destination
   int32_t bstride;          // voxels per sample of that destination (dst_cb * Dd * Hd * Wd)
-  int16_t od, oh, ow;
+  int16_t blk;              // destination channel block (statistics are indexed by destination channel)
+  int8_t od, oh, ow;        // small offsets: |od| <= 4 (shift-folded dgrad), oh / ow < 8 (transposed-conv taps)
   int8_t dst;               // -1: dead block
   uint8_t chmask;
-  int32_t blk;              // destination channel block (statistics are indexed by destination channel)
+  uint8_t pad_;
 };
+static_assert(sizeof(ColInfo) == 16, "ColInfo is read as one 16-byte shared-memory vector");
 
 constexpr int EPI_WARPS = 16;            // upper bound; the launch picks 8 or 16 (blockDim.x = 64 + 32 * warps)
 constexpr int TC_THREADS2 = 64 + 32 * EPI_WARPS;
 
-template <bool HALO, int MS>      // MS: 8-voxel-wide sub-tiles (accumulators) per tile
-__global__ void __launch_bounds__(TC_THREADS2, 1)
+// MS: 8-voxel-wide sub-tiles (accumulators) per tile.  MODE selects the epilogue: 0 plain store, 1 store +
+// InstanceNorm statistics (always 8 epilogue warps: the smaller block leaves 204 registers per thread for the
+// column-sum butterflies), 2 accumulate into the destination (gradient fan-in)
+template <bool HALO, int MS, int MODE>
+__global__ void __launch_bounds__(MODE == 1 ? 64 + 32 * 8 : TC_THREADS2, 1)
 conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMaps maps) {
   constexpr int NT = HALO ? 9 : 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -296,8 +302,9 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     const int plane = p.Ddst * p.Hd * p.Wd;
     ci.dst = (int8_t)dst;
     ci.chmask = (uint8_t)c.chmask;
-    ci.od = (int16_t)c.od; ci.oh = (int16_t)c.oh; ci.ow = (int16_t)c.ow;
-    ci.blk = c.blk;
+    ci.od = (int8_t)c.od; ci.oh = (int8_t)c.oh; ci.ow = (int8_t)c.ow;
+    ci.blk = (int16_t)c.blk;
+    ci.pad_ = 0;
     ci.off = dst >= 0 ? c.blk * plane + (c.od * p.Hd + c.oh) * p.Wd + c.ow : 0;
     ci.bstride = dst >= 0 ? p.dst_cb[dst] * plane : 0;
     s_cols[i] = ci;
@@ -470,30 +477,58 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     // InstanceNorm statistics: this warp's accumulators [2][Npad] in shared memory, flushed to its own global
     // slot whenever the (sample, column chunk) of the work items changes (both are monotonic per CTA or alternate
     // with a short period) -- no atomics anywhere, so the statistics are bit-reproducible
-    const bool do_stats = p.stats != nullptr;
-    float* wstat = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off)) + (warp - 2) * 2 * Npad;
-    float* gslot = do_stats ? p.stats + (size_t)(blockIdx.x * epi_warps + (warp - 2)) * p.B * 2 * p.stats_ctot : nullptr;
+    constexpr bool do_stats = MODE == 1;
+    constexpr bool do_accum = MODE == 2;
+    float* wstat_all = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off));
+    float* wstat = wstat_all + (warp - 2) * 2 * Npad;
+    float* gslot = do_stats ? p.stats + (size_t)blockIdx.x * p.B * 2 * p.stats_ctot : nullptr;
+    const int et = (int)threadIdx.x - 64, ethreads = epi_warps * 32;      // index among the epilogue threads
     int sb = -1, sch = -1;
+    // register path: with one column chunk per launch and (warps per quadrant) % (32-column chunks) == 0 a warp
+    // meets the same 32 columns in every work item, so each thread keeps running sums of its own rows and the
+    // lanes are combined only at a flush (no shuffles per tile)
+    const int nchunk0 = (p.npad[0] + 31) >> 5;
+    const bool reg_stats = do_stats && p.n_chunks == 1 && ((epi_warps >> 2) % nchunk0) == 0;
+    const int reg_c0 = (grp % nchunk0) << 5;
+    float rs[do_stats ? 32 : 1], rq[do_stats ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (do_stats ? 32 : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    // flush: executed by ALL epilogue warps at the same points of the (uniform) work sequence.  The per-warp
+    // accumulators are summed in a fixed order and added to this CTA's global slot; named barrier 1 orders it.
     auto flush_stats = [&](int fb, int fch) {
       const int fn = p.npad[fch];
       const ColInfo* fc = s_cols + fch * 32;
-      __syncwarp();
-      for (int c = lane; c < fn; c += 32) {
-        const ColInfo col = fc[c >> 3];
-        if (col.dst >= 0) {
-          float* g = gslot + (size_t)fb * 2 * p.stats_ctot + col.blk * 8 + (c & 7);
-          g[0] += wstat[c];
-          g[p.stats_ctot] += wstat[Npad + c];
+      if constexpr (do_stats) {
+        if (reg_stats) {
+          const float s1 = warp_colsum32(rs, lane);       // destroys rs / rq: re-zeroed below
+          const float s2 = warp_colsum32(rq, lane);
+          if (reg_c0 + lane < fn) {
+            wstat[reg_c0 + lane] += s1;
+            wstat[Npad + reg_c0 + lane] += s2;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
         }
-        wstat[c] = 0.f;
-        wstat[Npad + c] = 0.f;
       }
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
+      for (int idx = et; idx < 2 * Npad; idx += ethreads) {
+        const int k = idx >= Npad ? 1 : 0, c = idx - k * Npad;
+        float sum = 0.f;
+        for (int w = 0; w < epi_warps; ++w) {
+          sum += wstat_all[w * 2 * Npad + idx];
+          wstat_all[w * 2 * Npad + idx] = 0.f;
+        }
+        if (c < fn) {
+          const ColInfo col = fc[c >> 3];
+          if (col.dst >= 0) gslot[((size_t)fb * 2 + k) * p.stats_ctot + col.blk * 8 + (c & 7)] += sum;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
     };
     if (do_stats) {
-      for (int i = lane; i < p.B * 2 * p.stats_ctot; i += 32) gslot[i] = 0.f;
+      for (int i = et; i < p.B * 2 * p.stats_ctot; i += ethreads) gslot[i] = 0.f;
       for (int c = lane; c < 2 * Npad; c += 32) wstat[c] = 0.f;
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
     }
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
       int t = work / p.n_chunks;
@@ -524,45 +559,87 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         const bool two = c0 + 16 < npc;
         tc_ld16(acc0 + j * Npad + c0, v);
         if (two) tc_ld16(acc0 + j * Npad + c0 + 16, v + 16);
+        // destination of column block u of this chunk (nullptr: nothing to store)
+        auto dst_of = [&](int u) -> bf16* {
+          const ColInfo col = ccols[(c0 >> 3) + u];
+          if (!inb || col.dst < 0) return nullptr;
+          if (need_bounds) {
+            if ((need_bounds & 1) && (unsigned)(ds + col.od) >= (unsigned)p.Ddst) return nullptr;
+            if ((need_bounds & 2) && (unsigned)(hs + col.oh) >= (unsigned)p.Hd) return nullptr;
+            if ((need_bounds & 4) && (unsigned)(ws + col.ow) >= (unsigned)p.Wd) return nullptr;
+          }
+          return reinterpret_cast<bf16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
+        };
+        // accumulate mode: the values already stored at the destinations are fetched BEFORE the TMEM wait so that
+        // their latency overlaps it (issued back to back: no store in between that they could alias)
+        bf16* dps[4] = {nullptr, nullptr, nullptr, nullptr};
+        uint4 olds[4];
+        if constexpr (do_accum) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            olds[u] = make_uint4(0, 0, 0, 0);
+            if (u >= 2 && !two) continue;
+            dps[u] = dst_of(u);
+            if (dps[u]) olds[u] = *reinterpret_cast<const uint4*>(dps[u]);
+          }
+        }
         tc_wait_ld();
-        if (do_stats) {
-          // sums of the values exactly as stored (bf16-rounded), rows outside the grid excluded
-          float t1[32];
+        uint4 pk[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t1[i] = (inb && (i < 16 || two)) ? bf16_round(__uint_as_float(v[i])) : 0.f;
-          float t2[32];
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) t2[i] = t1[i] * t1[i];
-          const float s1 = warp_colsum32(t1, lane);
-          const float s2 = warp_colsum32(t2, lane);
-          if (c0 + lane < npc) {
-            wstat[c0 + lane] += s1;
-            wstat[Npad + c0 + lane] += s2;
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[u * 8 + e]);
+          if constexpr (do_accum) {
+            // gradient fan-in: another consumer of this activation already stored its contribution here
+            const uint4 old = olds[u];
+            f[0] += bf16_lo(old.x); f[1] += bf16_hi(old.x); f[2] += bf16_lo(old.y); f[3] += bf16_hi(old.y);
+            f[4] += bf16_lo(old.z); f[5] += bf16_hi(old.z); f[6] += bf16_lo(old.w); f[7] += bf16_hi(old.w);
+          }
+          pk[u] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+        }
+        if constexpr (do_stats) {
+          // sums of the values exactly as stored (the packed bf16), rows outside the grid excluded
+          float t1[32], t2[32];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool on = inb && (u < 2 || two);
+            const uint32_t wv[4] = {pk[u].x, pk[u].y, pk[u].z, pk[u].w};
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+              const float lo = on ? bf16_lo(wv[hh]) : 0.f, hi = on ? bf16_hi(wv[hh]) : 0.f;
+              t1[u * 8 + 2 * hh] = lo; t1[u * 8 + 2 * hh + 1] = hi;
+              t2[u * 8 + 2 * hh] = lo * lo; t2[u * 8 + 2 * hh + 1] = hi * hi;
+            }
+          }
+          if (reg_stats) {
+            // this warp always sees the same 32 columns: running sums per thread, lanes combined at the flush
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { rs[i] += t1[i]; rq[i] += t2[i]; }
+          } else {
+            const float s1 = warp_colsum32(t1, lane);
+            const float s2 = warp_colsum32(t2, lane);
+            if (c0 + lane < npc) {
+              wstat[c0 + lane] += s1;
+              wstat[Npad + c0 + lane] += s2;
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (u >= 2 && !two) break;
-          const ColInfo col = ccols[(c0 >> 3) + u];
-          if (!inb || col.dst < 0) continue;
-          if (need_bounds) {
-            if ((need_bounds & 1) && (unsigned)(ds + col.od) >= (unsigned)p.Ddst) continue;
-            if ((need_bounds & 2) && (unsigned)(hs + col.oh) >= (unsigned)p.Hd) continue;
-            if ((need_bounds & 4) && (unsigned)(ws + col.ow) >= (unsigned)p.Wd) continue;
-          }
-          bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
-          const uint32_t* vv = v + u * 8;
-          uint4 o = make_uint4(pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])),
-                               pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3])),
-                               pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])),
-                               pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7])));
-          if (col.chmask == 0xff) {
+          bf16* dp;
+          if constexpr (do_accum) dp = dps[u]; else dp = dst_of(u);
+          if (dp == nullptr) continue;
+          const uint4 o = pk[u];
+          const int cm = ccols[(c0 >> 3) + u].chmask;
+          if (cm == 0xff) {
             *reinterpret_cast<uint4*>(dp) = o;
           } else {
             // shift groups are contiguous channel ranges: store the selected channels in the widest
             // aligned pieces (8 / 4 / 2 bytes)
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
-            const int cm = col.chmask;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               const int m4 = (cm >> (4 * h2)) & 0xf;
@@ -655,7 +732,7 @@ struct S3Params {
   const e2e_centry_t* cents;
   const bf16* wpacked;
   bf16* dst;
-  float* stats;                     // see TcParams::stats (slot = blockIdx.x * S3_EPI_WARPS + epilogue warp)
+  float* stats;                     // see TcParams::stats (slot = blockIdx.x)
   int stats_ctot;
   int stats_smem_off;               // per-warp accumulators [S3_EPI_WARPS][2][Np]
 };
@@ -801,27 +878,50 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     const int grp = (warp - 2) >> 2;
     const int nblk = Np >> 3;
     uint32_t mcount = 0;
+    // InstanceNorm statistics: every thread keeps the running sums of ITS voxels' values for the (at most 3) channel
+    // blocks its warp handles in registers -- no shuffles per tile -- and the lanes / warps are combined only when
+    // the sample changes and at the end (host guarantees nblk <= 6 when statistics are requested)
     const bool do_stats = p.stats != nullptr;
-    float* wstat = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off)) + (warp - 2) * 2 * Np;
-    float* gslot = do_stats ? p.stats + (size_t)(blockIdx.x * S3_EPI_WARPS + (warp - 2)) * p.B * 2 * p.stats_ctot : nullptr;
+    float* wstat_all = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off));
+    float* wstat = wstat_all + (warp - 2) * 2 * Np;
+    float* gslot = do_stats ? p.stats + (size_t)blockIdx.x * p.B * 2 * p.stats_ctot : nullptr;
+    const int et = (int)threadIdx.x - 64;
+    constexpr int ethreads = S3_EPI_WARPS * 32;
+    float rs[3][8], rq[3][8];
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { rs[u][e] = 0.f; rq[u][e] = 0.f; }
     int sb = -1;
     auto flush_stats = [&](int fb) {
-      __syncwarp();
-      for (int c = lane; c < Np; c += 32) {
-        float* g = gslot + (size_t)fb * 2 * p.stats_ctot + c;
-        if (c < p.stats_ctot) {
-          g[0] += wstat[c];
-          g[p.stats_ctot] += wstat[Np + c];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int cb = grp + u * (S3_EPI_WARPS / 4);
+        const float s1 = warp_colsum8(rs[u], lane);
+        const float s2 = warp_colsum8(rq[u], lane);
+        if (cb < nblk && lane < 8) {
+          wstat[cb * 8 + lane] = s1;
+          wstat[Np + cb * 8 + lane] = s2;
         }
-        wstat[c] = 0.f;
-        wstat[Np + c] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { rs[u][e] = 0.f; rq[u][e] = 0.f; }
       }
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(ethreads) : "memory");
+      for (int idx = et; idx < 2 * Np; idx += ethreads) {
+        const int k = idx >= Np ? 1 : 0, c = idx - k * Np;
+        float sum = 0.f;
+        for (int w = 0; w < S3_EPI_WARPS; ++w) {
+          sum += wstat_all[w * 2 * Np + idx];
+          wstat_all[w * 2 * Np + idx] = 0.f;
+        }
+        if (c < p.stats_ctot) gslot[((size_t)fb * 2 + k) * p.stats_ctot + c] += sum;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(ethreads) : "memory");
     };
     if (do_stats) {
-      for (int i = lane; i < p.B * 2 * p.stats_ctot; i += 32) gslot[i] = 0.f;
+      for (int i = et; i < p.B * 2 * p.stats_ctot; i += ethreads) gslot[i] = 0.f;
       for (int c = lane; c < 2 * Np; c += 32) wstat[c] = 0.f;
-      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(ethreads) : "memory");
     }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int t = tile;
@@ -867,22 +967,20 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
             o[e] = left + __uint_as_float(v[u][1][e]) + right;
           }
           if (ok) {
+            const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                        pack_bf16x2(o[6], o[7]));
             bf16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
-            *reinterpret_cast<uint4*>(dp) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                       pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          }
-          if (do_stats) {
-            float t1[8], t2[8];
+            *reinterpret_cast<uint4*>(dp) = pk;
+            if (do_stats) {                       // sums of the values exactly as stored (the packed bf16)
+              const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              t1[e] = ok ? bf16_round(o[e]) : 0.f;
-              t2[e] = t1[e] * t1[e];
-            }
-            const float s1 = warp_colsum8(t1, lane);
-            const float s2 = warp_colsum8(t2, lane);
-            if (lane < 8) {
-              wstat[cb * 8 + lane] += s1;
-              wstat[Np + cb * 8 + lane] += s2;
+              for (int hh = 0; hh < 4; ++hh) {
+                const float lo = bf16_lo(wv[hh]), hi = bf16_hi(wv[hh]);
+                rs[u][2 * hh] += lo;
+                rs[u][2 * hh + 1] += hi;
+                rq[u][2 * hh] = __fmaf_rn(lo, lo, rq[u][2 * hh]);
+                rq[u][2 * hh + 1] = __fmaf_rn(hi, hi, rq[u][2 * hh + 1]);
+              }
             }
           }
         }
@@ -960,7 +1058,12 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   {
     int grid0 = e2e_num_sms();
     if (grid0 > p.n_tiles) grid0 = p.n_tiles;
-    if (slots_out) { *slots_out = grid0 * S3_EPI_WARPS; return E2E_OK; }
+    const bool can_stats = (p.Np >> 3) <= 3 * (S3_EPI_WARPS / 4);       // register accumulators: <= 3 blocks per warp
+    if (slots_out) { *slots_out = can_stats ? grid0 : 0; return E2E_OK; }
+    if (g->stats && !can_stats) {
+      e2e_set_error("conv_tc3: fused statistics support at most %d output channels", 8 * 3 * (S3_EPI_WARPS / 4));
+      return E2E_ERR_UNSUPPORTED;
+    }
   }
   p.stats = g->stats;
   p.stats_ctot = g->stats_ctot;
@@ -1040,6 +1143,10 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
     return E2E_ERR_CUDA;
   }
   if (form == 3) {
+    if (g->accumulate) {
+      e2e_set_error("conv_tc_fwd: the kw-stacked forward form does not accumulate");
+      return E2E_ERR_UNSUPPORTED;
+    }
     if (n != 1) {
       e2e_set_error("conv_tc_fwd: the kw-stacked form takes a single column chunk");
       return E2E_ERR_UNSUPPORTED;
@@ -1166,19 +1273,23 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
   p.stats = g->stats;
   p.stats_ctot = g->stats_ctot;
   p.stats_smem_off = p.b_region_bytes + p.stages * p.stage_bytes;
+  p.accum = g->accumulate ? 1 : 0;
   typedef void (*kern_t)(const TcParams, const TcMaps);
-  static const kern_t kerns[2][4] = {
-      {conv_tc_kernel<false, 1>, conv_tc_kernel<false, 2>, conv_tc_kernel<false, 3>, conv_tc_kernel<false, 4>},
-      {conv_tc_kernel<true, 1>, conv_tc_kernel<true, 2>, conv_tc_kernel<true, 3>, conv_tc_kernel<true, 4>}};
+#define E2E_TC_ROW(H, MODE) {conv_tc_kernel<H, 1, MODE>, conv_tc_kernel<H, 2, MODE>, conv_tc_kernel<H, 3, MODE>, conv_tc_kernel<H, 4, MODE>}
+  static const kern_t kerns[3][2][4] = {{E2E_TC_ROW(false, 0), E2E_TC_ROW(true, 0)},
+                                        {E2E_TC_ROW(false, 1), E2E_TC_ROW(true, 1)},
+                                        {E2E_TC_ROW(false, 2), E2E_TC_ROW(true, 2)}};
+#undef E2E_TC_ROW
   static E2eDevOnce attr_once;
   if (attr_once.first()) {
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 4; ++b) {
-        cudaFuncAttributes fa;
-        E2E_CUDA(cudaFuncGetAttributes(&fa, kerns[a][b]));
-        E2E_CUDA(cudaFuncSetAttribute(kerns[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024 - (int)fa.sharedSizeBytes));
-      }
+    for (int md = 0; md < 3; ++md)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b) {
+          cudaFuncAttributes fa;
+          E2E_CUDA(cudaFuncGetAttributes(&fa, kerns[md][a][b]));
+          E2E_CUDA(cudaFuncSetAttribute(kerns[md][a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024 - (int)fa.sharedSizeBytes));
+        }
   }
   if (!p.b_res && grid > p.n_tiles * p.n_chunks) grid = p.n_tiles * p.n_chunks;
   // 16 epilogue warps when a tile has many accumulator columns per MMA (short K loops: data gradients
@@ -1191,8 +1302,13 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
     if (force == 8 || force == 16) epi = force;
   }
   if (want_stats) epi = 8;                 // the statistics accumulators are sized for 8 epilogue warps
-  if (slots_out) { *slots_out = grid * epi; return E2E_OK; }
-  kerns[halo ? 1 : 0][m - 1]<<<grid, 64 + 32 * epi, smem_bytes, st>>>(p, maps);
+  if (slots_out) { *slots_out = grid; return E2E_OK; }
+  if (g->stats && g->accumulate) {
+    e2e_set_error("conv_tc_fwd: fused statistics and accumulate cannot be combined");
+    return E2E_ERR_UNSUPPORTED;
+  }
+  const int mode = g->stats ? 1 : (g->accumulate ? 2 : 0);
+  kerns[mode][halo ? 1 : 0][m - 1]<<<grid, 64 + 32 * epi, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc_fwd");
   return E2E_OK;
 }

@@ -136,27 +136,36 @@ __global__ void in_stats_final_kernel(const float* __restrict__ partial, int pla
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// statistics from the per-slot partials a fused conv epilogue wrote: stats[slot][b][{sum, sumsq}][C].  One WARP per
-// (b, c), lanes stride over the slots in a fixed order (deterministic), fp64 accumulation.
-__global__ void in_stats_from_slots_kernel(const float* __restrict__ stats, int n_slots, int B, int C, long long V, float eps,
-                                           float* __restrict__ mean, float* __restrict__ rstd) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= B * C) return;
-  const int b = i / C, c = i - b * C;
+// statistics from the per-slot partials a fused conv epilogue wrote: stats[slot][b][{sum, sumsq}][C] (one slot per
+// CTA of the conv launch).  grid (ceil(C / 32), B), 32 warps: lane = channel (coalesced rows), warp w takes slots
+// w, w + 32, ...; the 32 partial sums are combined in a fixed order in fp64 (deterministic).
+__global__ void __launch_bounds__(1024) in_stats_from_slots_kernel(const float* __restrict__ stats, int n_slots, int B, int C,
+                                                                  long long V, float eps, float* __restrict__ mean,
+                                                                  float* __restrict__ rstd) {
+  __shared__ double red[32][2][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.y, c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int k = lane; k < n_slots; k += 32) {
-    const float* row = stats + ((long long)(k * B + b) * 2) * C + c;
-    s += row[0];
-    q += row[C];
+  if (c < C) {
+#pragma unroll 4
+    for (int k = w; k < n_slots; k += 32) {
+      const float* row = stats + ((long long)(k * B + b) * 2) * C + c;
+      s += (double)row[0];
+      q += (double)row[C];
+    }
   }
-  s = warp_sum_d(s);
-  q = warp_sum_d(q);
-  if (lane) return;
+  red[w][0][lane] = s;
+  red[w][1][lane] = q;
+  __syncthreads();
+  if (w != 0 || c >= C) return;
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { s += red[i][0][lane]; q += red[i][1][lane]; }
   const double m = s / (double)V;
   double var = q / (double)V - m * m;
   if (var < 0.0) var = 0.0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  mean[b * C + c] = (float)m;
+  rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // grid (nchunk, B*Cb)
@@ -664,8 +673,7 @@ extern "C" int e2e_in_stats(const void* raw, int32_t B, int32_t Cb, int64_t V, f
 extern "C" int e2e_in_stats_final(const float* stats, int32_t n_slots, int32_t B, int32_t C, int64_t V, float eps,
                                   float* mean, float* rstd, void* stream) {
   E2E_ARG(stats && mean && rstd && n_slots > 0 && B > 0 && C > 0 && V > 0, "in_stats_final: bad arguments");
-  const int n = B * C * 32;
-  in_stats_from_slots_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, n_slots, B, C, V, eps, mean, rstd);
+  in_stats_from_slots_kernel<<<dim3((C + 31) / 32, B), 1024, 0, (cudaStream_t)stream>>>(stats, n_slots, B, C, V, eps, mean, rstd);
   E2E_LAUNCHED("in_stats_final");
   return E2E_OK;
 }

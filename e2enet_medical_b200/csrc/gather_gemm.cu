@@ -515,10 +515,15 @@ extern "C" int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* strea
   return E2E_OK;
 }
 
-extern "C" int e2e_gather_gemm_stats_slots(const e2e_gemm_t* p, int32_t n) {
+extern "C" int e2e_gather_gemm_on_tcgen05(const e2e_gemm_t* p, int32_t n) {
   if (p == nullptr || n < 1 || n > 12 || p->out_mode != 0) return 0;
   for (int i = 0; i < n; ++i)
     if (p[i].impl != 1 || !e2e_conv_tc_supported(p + i) || e2e_conv_tc_supported(p + i) != e2e_conv_tc_supported(p)) return 0;
+  return 1;
+}
+
+extern "C" int e2e_gather_gemm_stats_slots(const e2e_gemm_t* p, int32_t n) {
+  if (!e2e_gather_gemm_on_tcgen05(p, n)) return 0;
   if ((long long)p->B * p->Do * p->Ho * p->Wo <= 0) return 0;
   return e2e_conv_tc_stats_slots(p, n);
 }
@@ -535,6 +540,7 @@ static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   if (M <= 0) return E2E_OK;
   if (allow_tc && p->impl == 1 && e2e_conv_tc_supported(p)) return e2e_conv_tc_fwd(p, 1, st);
   E2E_ARG(p->stats == nullptr, "gather_gemm: fused statistics need the tcgen05 path (query e2e_gather_gemm_stats_slots first)");
+  E2E_ARG(p->accumulate == 0, "gather_gemm: accumulate needs the tcgen05 path (query e2e_gather_gemm_on_tcgen05 first)");
   if (p->n_taps == 3) {
     e2e_set_error("gather_gemm: a kw-stacked plan (3 taps, N = 3 x Cout) is only executable by the tcgen05 kernel");
     return E2E_ERR_UNSUPPORTED;

@@ -59,6 +59,81 @@ __global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __r
   }
 }
 
+// ------------------------------------------------------------------ fused 1x1x1 seg head + softmax + accumulate
+// The last layer of the network at inference is Conv3d(C, ncls, 1) on the full-resolution feature map
+// (unetpp_d.py:394-401,480-488), followed by softmax_helper, the un-mirroring, the Gaussian weighting and the
+// `+=` into the accumulators (neural_network.py:529-563, 390-393).  With ncls <= 32 outputs the head is a
+// 2*C*ncls-FLOP-per-voxel dot product: far too narrow for a tensor-core tile and cheap enough for the CUDA cores
+// to hide under the memory traffic, so it is folded into the accumulate pass: the fp32 logits (ncls * 4 B per
+// voxel written by a head kernel and read back here) never exist.  x: bf16 C8 [Cb][px][py][pz][8] of ONE tile;
+// w: fp32 [ncls][C] (rounded to bf16 here, like the packed operand of the GEMM head); one thread per voxel.
+template <int NC>
+__global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4* __restrict__ x, int Cb, const float* __restrict__ w,
+                                                                     int C, const float* __restrict__ gauss, float* __restrict__ agg,
+                                                                     float* __restrict__ wsum, int ncls, int px, int py, int pz,
+                                                                     int X, int Y, int Z, int x0, int y0, int z0, int flip,
+                                                                     float scale, int add_weight) {
+  extern __shared__ float w_s[];                 // [Cb * 8][NC]: w_s[k * NC + c] = bf16(w[c][k]) (0 beyond C / ncls)
+  for (int i = threadIdx.x; i < Cb * 8 * NC; i += blockDim.x) {
+    const int k = i / NC, c = i - k * NC;
+    w_s[i] = (k < C && c < ncls) ? __bfloat162float(__float2bfloat16_rn(w[c * C + k])) : 0.f;
+  }
+  __syncthreads();
+  const long long P = (long long)px * py * pz;
+  const long long V = (long long)X * Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % pz);
+    const long long t = i / pz;
+    const int j = (int)(t % py), ii = (int)(t / py);
+    const int si = (flip & 1) ? px - 1 - ii : ii;
+    const int sj = (flip & 2) ? py - 1 - j : j;
+    const int sk = (flip & 4) ? pz - 1 - k : k;
+    const long long s = ((long long)si * py + sj) * pz + sk;
+    float v[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) v[c] = 0.f;
+    for (int cb = 0; cb < Cb; ++cb) {
+      const uint4 q = ld_nc_16(x + (long long)cb * P + s);
+      const float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
+                          bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4* wr = reinterpret_cast<const float4*>(w_s + (cb * 8 + e) * NC);
+#pragma unroll
+        for (int c4 = 0; c4 < NC / 4; ++c4) {
+          const float4 ww = wr[c4];
+          v[4 * c4 + 0] = __fmaf_rn(f[e], ww.x, v[4 * c4 + 0]);
+          v[4 * c4 + 1] = __fmaf_rn(f[e], ww.y, v[4 * c4 + 1]);
+          v[4 * c4 + 2] = __fmaf_rn(f[e], ww.z, v[4 * c4 + 2]);
+          v[4 * c4 + 3] = __fmaf_rn(f[e], ww.w, v[4 * c4 + 3]);
+        }
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < ncls) mx = fmaxf(mx, v[c]);
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      v[c] = (c < ncls) ? expf(v[c] - mx) : 0.f;
+      sum += v[c];
+    }
+    const float inv = 1.0f / sum;
+    const float g = gauss ? gauss[i] : 1.f;
+    const long long dst = ((long long)(x0 + ii) * Y + (y0 + j)) * Z + (z0 + k);
+    float a[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) a[c] = (c < ncls) ? agg[c * V + dst] : 0.f;
+    const float w0 = add_weight ? wsum[dst] : 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c < ncls) agg[c * V + dst] = a[c] + ((v[c] * inv) * scale) * g;
+    if (add_weight) wsum[dst] = w0 + g;
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict__ agg, const float* __restrict__ wsum, int ncls,
                                                               long long V, long long* __restrict__ seg) {
@@ -103,6 +178,32 @@ extern "C" int e2e_window_accumulate(const float* logits, const float* gauss, fl
   else
     window_accumulate_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(logits, gauss, agg, wsum, ncls, px, py, pz, X, Y, Z, x0, y0, z0, flip, scale, add_weight, apply_softmax);
   E2E_LAUNCHED("window_accumulate");
+  return E2E_OK;
+}
+
+extern "C" int e2e_window_head_accumulate(const void* x, int32_t Cb, const float* w, int32_t C, const float* gauss, float* agg,
+                                          float* wsum, int32_t ncls, int32_t px, int32_t py, int32_t pz, int32_t X, int32_t Y,
+                                          int32_t Z, int32_t x0, int32_t y0, int32_t z0, int32_t flip, float scale,
+                                          int32_t add_weight, void* stream) {
+  E2E_ARG(x && w && agg && wsum, "window_head_accumulate: null pointer");
+  E2E_ARG(ncls >= 1 && ncls <= MAXC, "window_head_accumulate: ncls %d outside [1,%d]", ncls, MAXC);
+  E2E_ARG(Cb >= 1 && C >= 1 && C <= 8 * Cb && Cb <= 40, "window_head_accumulate: bad channel counts (C %d, Cb %d)", C, Cb);
+  E2E_ARG(x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + px <= X && y0 + py <= Y && z0 + pz <= Z,
+          "window_head_accumulate: tile (%d,%d,%d)+(%d,%d,%d) outside volume (%d,%d,%d)", x0, y0, z0, px, py, pz, X, Y, Z);
+  const long long P = (long long)px * py * pz;
+  long long blocks = (P + 255) / 256;
+  const long long cap = (long long)e2e_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint4* xp = (const uint4*)x;
+#define E2E_WHA(NC)                                                                                                       \
+  window_head_accumulate_kernel<NC><<<(unsigned)blocks, 256, (size_t)Cb * 8 * NC * 4, st>>>(                               \
+      xp, Cb, w, C, gauss, agg, wsum, ncls, px, py, pz, X, Y, Z, x0, y0, z0, flip, scale, add_weight)
+  if (ncls <= 4) E2E_WHA(4);
+  else if (ncls <= 16) E2E_WHA(16);
+  else E2E_WHA(32);
+#undef E2E_WHA
+  E2E_LAUNCHED("window_head_accumulate");
   return E2E_OK;
 }
 

@@ -266,14 +266,31 @@ class SegmentationNetwork(NeuralNetwork):
         else:
             combos, scale = [()], 1.0
         fused = self._uses_softmax()
+        # the network's 1x1x1 head folded into the accumulate kernel (no fp32 logits tensor): available when the
+        # drop-in network would return seg_outputs[0] alone and the inference non-linearity is softmax
+        head_fused = (fused and getattr(self, "fuse_head_into_window", True) and hasattr(self, "e2e_head_fusable")
+                      and self.e2e_head_fusable())
         for n, m in enumerate(combos):
             t = torch.flip(tile, tuple(a + 2 for a in m)) if m else tile
+            flip = sum(1 << a for a in m)
+            if head_fused:
+                feat, hw = self.e2e_head_features(t)
+                assert feat.dtype == torch.bfloat16 and feat.is_contiguous() and tuple(feat.shape[2:5]) == (px, py, pz)
+                hw = hw.float().contiguous()
+                Cb = feat.shape[1]
+                per = feat[0].numel() * 2
+                for i, org in enumerate(origins):
+                    _lib.check(lib.e2e_window_head_accumulate(
+                        C.c_void_p(feat.data_ptr() + i * per), Cb, C.c_void_p(hw.data_ptr()), hw.shape[1],
+                        C.c_void_p(gauss.data_ptr() if gauss is not None else 0), C.c_void_p(agg.data_ptr()),
+                        C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z, int(org[0]), int(org[1]), int(org[2]), flip,
+                        scale, 1 if n == 0 else 0, _lib.stream_ptr()), "window_head_accumulate")
+                continue
             out = self(t)
             if not fused:
                 out = self.inference_apply_nonlin(out)
             out = out.float().contiguous()
             assert out.shape[1] == ncls
-            flip = sum(1 << a for a in m)
             per = out[0].numel() * 4
             for i, org in enumerate(origins):
                 _lib.check(lib.e2e_window_accumulate(
@@ -291,18 +308,38 @@ class SegmentationNetwork(NeuralNetwork):
                                            C.c_void_p(seg.data_ptr()), _lib.stream_ptr()), "window_finalize")
         return seg
 
+    def _host_buffer(self, shape, dtype, tag: str) -> torch.Tensor:
+        """a pinned host tensor for a result.  Buffers are pooled per (tag, shape, dtype) and handed out again ONLY
+        when nothing outside the pool references them any more (the NumPy array a previous call returned, or any
+        view of it, keeps its buffer's reference count up), so results never alias across calls -- the reference's
+        fold loop `softmax += predict(...)[1]` (inference/predict.py:288-292) stays correct -- while the steady
+        state (caller drops the previous result) moves 5.6 GB of labels + softmax at PCIe speed instead of
+        pageable-memory speed.  `self.pinned_output_buffers = False` restores fresh pageable arrays."""
+        def in_use(b):
+            # an ndarray made by Tensor.numpy() (and every view of it) holds a reference to the tensor's STORAGE;
+            # 2 = the pooled tensor itself + the temporary storage wrapper of this query
+            try:
+                return torch._C._storage_Use_Count(b.untyped_storage()._cdata) > 2
+            except Exception:                     # private API missing: never reuse (always safe)
+                return True
+        pool = self.__dict__.setdefault("_pinned_pool", {})
+        key = (tag, tuple(shape), dtype)
+        for k in [k for k in pool if k[0] == tag and k != key]:      # shapes changed: drop the idle old buffers
+            pool[k] = [b for b in pool[k] if in_use(b)]
+        bufs = pool.setdefault(key, [])
+        for b in bufs:
+            if not in_use(b):
+                return b
+        bufs[:] = [b for b in bufs if in_use(b)][-2:]                # do not hoard: remember at most two lent buffers
+        b = torch.empty(tuple(shape), dtype=dtype, pin_memory=torch.cuda.is_available())
+        bufs.append(b)
+        return b
+
     def _to_host(self, t: torch.Tensor, tag: str) -> np.ndarray:
-        """device -> NumPy.  With `self.pinned_output_buffers = True` the result lives in a pinned host
-        buffer that is REUSED by the next predict_3D call (copy it if you keep it): the 5.6 GB of
-        labels + softmax of a 300x512x512 / 16-class volume then move at PCIe speed instead of
-        pageable-memory speed.  Default: a fresh pageable array per call, like the reference."""
-        if not getattr(self, "pinned_output_buffers", False):
+        """device -> NumPy through a pooled pinned buffer (see _host_buffer)"""
+        if not getattr(self, "pinned_output_buffers", True):
             return t.cpu().numpy()
-        cache = self.__dict__.setdefault("_pinned_out", {})
-        buf = cache.get(tag)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-            buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            cache[tag] = buf
+        buf = self._host_buffer(t.shape, t.dtype, tag)
         buf.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return buf.numpy()

@@ -399,9 +399,40 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
         return ops.SegHead.apply(self._splans[k], mod.weight, x.tensor)
 
     # ------------------------------------------------------------------ forward (reference :447-488)
+    def e2e_head_features(self, x):
+        """inference hook of the sliding window (neural_network.SegmentationNetwork._accumulate_tile): the C8
+        feature map x0_5 that feeds seg_outputs[0] and that head's weight -- the 1x1x1 head itself is folded into
+        the softmax + accumulate kernel (e2e_window_head_accumulate), so the fp32 logits of a tile never exist.
+        Only valid when the network would return seg_outputs[0] alone (do_ds off) with an identity final_nonlin."""
+        node = self._grid(x)
+        mod = self.seg_outputs[0]
+        return node[(0, 5)].tensor, mod.weight.detach().reshape(mod.out_channels, mod.in_channels).contiguous()
+
+    def e2e_head_fusable(self) -> bool:
+        if self._deep_supervision and self.do_ds:
+            return False
+        try:
+            probe = torch.zeros(2)
+            return self.final_nonlin(probe) is probe           # identity (the trainer passes lambda x: x, :299)
+        except Exception:
+            return False
+
     def forward(self, x):
+        node = self._grid(x)
+        if not (self._deep_supervision and self.do_ds):
+            # the reference computes all four heads and returns the last (:480-488); the other three
+            # have no effect on the result, so inference skips them
+            return self.final_nonlin(self._seg(0, node[(0, 5)]))
+        seg_outputs = [self.final_nonlin(self._seg(3, node[(3, 2)])), self.final_nonlin(self._seg(2, node[(2, 3)])),
+                       self.final_nonlin(self._seg(1, node[(1, 4)])), self.final_nonlin(self._seg(0, node[(0, 5)]))]
+        return list([seg_outputs[-1]] + [i(j) for i, j in zip(list(self.upscale_logits_ops)[::-1],
+                                                               seg_outputs[:-1][::-1])])
+
+    def _grid(self, x):
+        """the fusion grid (reference :447-478): returns {(scale i, depth j): C8 activation}"""
         if not x.is_cuda:
             raise RuntimeError("Generic_UNetPlusPlus (B200): input must be a CUDA tensor; there is no CPU fallback")
+        ops.fanin_reset()               # gradient fan-in buffers of a backward pass that never completed
         node = {}
         h = C8(ops.ToC8.apply(x), [x.shape[1]])
         for s in range(6):
@@ -414,14 +445,7 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
                 if i > 0:
                     parts.append(self._pool(getattr(self, "down%d" % z)[idx], node[(i - 1, j - 1)]))
                 node[(i, j)] = getattr(self, "loc%d" % z)[idx](C8.cat(parts))
-        if not (self._deep_supervision and self.do_ds):
-            # the reference computes all four heads and returns the last (:480-488); the other three
-            # have no effect on the result, so inference skips them
-            return self.final_nonlin(self._seg(0, node[(0, 5)]))
-        seg_outputs = [self.final_nonlin(self._seg(3, node[(3, 2)])), self.final_nonlin(self._seg(2, node[(2, 3)])),
-                       self.final_nonlin(self._seg(1, node[(1, 4)])), self.final_nonlin(self._seg(0, node[(0, 5)]))]
-        return list([seg_outputs[-1]] + [i(j) for i, j in zip(list(self.upscale_logits_ops)[::-1],
-                                                               seg_outputs[:-1][::-1])])
+        return node
 
     @staticmethod
     def compute_approx_vram_consumption(patch_size, num_pool_per_axis, base_num_features, max_num_features,

@@ -17,7 +17,13 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True}
+CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True}
+# A/B switches for measurements (tools/, bench.py): E2E_FUSE_STATS=0 / E2E_FUSE_FANIN=0 / E2E_FUSE_POOL=0 / E2E_STACK3=0
+import os as _os
+for _k, _e in (("fuse_stats", "E2E_FUSE_STATS"), ("fuse_fanin", "E2E_FUSE_FANIN"), ("fuse_pool", "E2E_FUSE_POOL"),
+               ("stack3", "E2E_STACK3")):
+    if _os.environ.get(_e) is not None:
+        CONFIG[_k] = _os.environ[_e] not in ("0", "false", "False")
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
@@ -54,6 +60,77 @@ def _p(t: Optional[torch.Tensor]):
 def _need_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _lib.E2EError("%s: tensor is on %s; the E2ENet B200 ops run on CUDA only (no CPU fallback)" % (what, t.device))
+
+
+# ---------------------------------------------------------------------------------------- gradient fan-in
+# An activation of the fusion grid has up to three consumers (the same-scale fusion conv, a transposed conv, a
+# seg head; unetpp_d.py:453-483).  Autograd would add their data gradients with one bf16 add launch per extra
+# consumer (28 per step, 1.4 ms).  Instead the FIRST consumer whose backward runs stores its gradient into a fresh
+# buffer and hands it to autograd; later consumers ADD theirs into the same buffer inside the data-gradient
+# epilogue (e2e_gemm_t.accumulate) and return no gradient.  The producer's backward retires the entry.
+_FANIN = {}            # data_ptr of the C8 activation -> gradient buffer of the backward pass in flight
+
+
+def fanin_reset():
+    _FANIN.clear()
+
+
+def _fanin_retire(ptr):
+    if ptr is not None:
+        _FANIN.pop(ptr, None)
+
+
+def _fanin_dst(src: torch.Tensor, zero: bool):
+    """(buffer, accumulate?) for the data gradient of C8 activation `src`"""
+    if not CONFIG.get("fuse_fanin", True):
+        return (torch.zeros_like(src) if zero else torch.empty_like(src)), False
+    key = src.data_ptr()
+    buf = _FANIN.get(key)
+    if buf is not None and buf.shape == src.shape:
+        return buf, True
+    buf = torch.zeros_like(src) if zero else torch.empty_like(src)
+    _FANIN[key] = buf
+    return buf, False
+
+
+def _dgrad_into(groups, weight, mask, srcs_of_gemm, src_grid, iter_grid_of, B, targets, dst_grid, impl, needs_zero):
+    """runs the data-gradient GEMM(s) `groups` for the activations `targets`; returns one gradient per target (None
+    where the contribution was accumulated into a buffer autograd already holds)."""
+    lib = _lib.load()
+    dsts, accs = [], []
+    for t in targets:
+        d, a = _fanin_dst(t, needs_zero)
+        dsts.append(d)
+        accs.append(a)
+    if any(accs) and not all(accs):
+        # mixed: give the not-yet-started targets a zeroed buffer and accumulate everywhere
+        for i, (t, a) in enumerate(zip(targets, accs)):
+            if not a:
+                dsts[i].zero_()
+    acc = any(accs)
+    dst_cb = [t.shape[1] for t in targets]
+    temps = None
+    for group in groups:
+        it = iter_grid_of(group[0])
+        if min(it) <= 0:
+            continue
+        if acc:
+            # accumulate needs the tcgen05 epilogue; otherwise fall back to a temporary + add
+            arr = (_lib.GemmParams * len(group))()
+            for i, pl in enumerate(group):
+                _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl)
+            if impl == 1 and int(lib.e2e_gather_gemm_on_tcgen05(arr, len(group))):
+                run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl, accumulate=True)
+            else:
+                if temps is None:
+                    temps = [torch.zeros_like(t) for t in targets]
+                run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, temps, dst_grid, dst_cb, impl)
+        else:
+            run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl)
+    if temps is not None:
+        for d, t in zip(dsts, temps):
+            _lib.check(lib.e2e_add_inplace(_p(d), _p(t), d.numel(), _lib.stream_ptr()), "add_inplace")
+    return [None if a else d for d, a in zip(dsts, accs)]
 
 
 def c8_shape(x: torch.Tensor):
@@ -172,7 +249,7 @@ def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor]
 
 def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optional[torch.Tensor],
                     srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, dsts: Sequence[torch.Tensor], dst_grid,
-                    dst_cb: Sequence[int], impl: int = 0, want_stats: bool = False):
+                    dst_cb: Sequence[int], impl: int = 0, want_stats: bool = False, accumulate: bool = False):
     """the column chunks of one GEMM (plans differ in columns / packed weights only): one launch.
     want_stats: ask the tcgen05 epilogue for the InstanceNorm partial sums of the (single, C8) destination;
     returns (stats tensor [slots][B][2][C], slots) or None when that launch cannot fuse them."""
@@ -182,6 +259,7 @@ def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optio
     flops = 0.0
     for i, pl in enumerate(plans):
         _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl)
+        arr[i].accumulate = 1 if accumulate else 0
         flops += _plan_flops(pl, B * iter_grid[0] * iter_grid[1] * iter_grid[2])
     stats = None
     if want_stats and impl == 1 and CONFIG.get("fuse_stats", True):
@@ -234,9 +312,19 @@ def _fill_gemm(p, plan: GemmPlan, wpacked: torch.Tensor, srcs, src_grid, iter_gr
     return p
 
 
+def _grad_slot(param: torch.Tensor):
+    """(arena, fresh view of the parameter's slot in the flat gradient arena) -- or (None, None) when the parameter
+    has no arena or already holds a gradient (then autograd must ACCUMULATE, and the arena slot may be that very
+    gradient: writing into it first would double it)."""
+    arena = getattr(param, "_e2e_grad_arena", None)
+    if arena is None or param.grad is not None or not arena.has(param):
+        return None, None
+    return arena, arena.view(param)
+
+
 def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, grad: torch.Tensor,
-              weight_shape, impl: int = 0) -> torch.Tensor:
-    """returns the fp32 weight gradient in the reference's parameter layout."""
+              weight_shape, impl: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """returns the fp32 weight gradient in the reference's parameter layout (written into `out` if given)."""
     lib = _lib.load()
     device = grad.device
     dev = plan.dev(device)
@@ -262,7 +350,8 @@ def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid,
     p.impl = impl
     with _Timed("wgrad", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
         _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
-    gw = torch.empty(weight_shape, dtype=torch.float32, device=device)      # unpack writes every weight once
+    gw = out if out is not None else torch.empty(weight_shape, dtype=torch.float32, device=device)   # unpack writes every weight once
+    assert tuple(gw.shape) == tuple(weight_shape) and gw.dtype == torch.float32 and gw.is_contiguous()
     _lib.check(lib.e2e_unpack_wgrad(_p(dwp), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]), plan.n_cent,
                                     plan.n_taps, plan.Npad, _p(gw), _lib.stream_ptr()), "unpack_wgrad")
     return gw
@@ -300,10 +389,13 @@ class ToC8(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         ctx.channels = x.shape[1]
-        return nc_to_c8(x)
+        y = nc_to_c8(x)
+        ctx.out_ptr = y.data_ptr()
+        return y
 
     @staticmethod
     def backward(ctx, dy):
+        _fanin_retire(ctx.out_ptr)
         return c8_to_nc(dy.contiguous(), ctx.channels)
 
 
@@ -386,6 +478,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         y = torch.empty_like(raw)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         ctx.plan, ctx.slope, ctx.mask, ctx.grid = plan, slope, mask, (B, D, H, W, Do, Ho, Wo)
+        ctx.bias = bias                 # not a saved tensor: only its identity (gradient slot) is needed
         ctx.pool_k = None
         if pool_k is not None:
             kd, kh, kw = (int(v) for v in pool_k)
@@ -394,18 +487,23 @@ class ShiftConvINLReLU(torch.autograd.Function):
             _lib.check(lib.e2e_in_apply_pool(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, Do, Ho, Wo,
                                              kd, kh, kw, _p(y), _p(yp), _p(am), _lib.stream_ptr()), "in_apply_pool")
             ctx.pool_k = (kd, kh, kw)
+            ctx.out_ptrs = (y.data_ptr(), yp.data_ptr())
             ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, am, *srcs)
             return y, yp
         _lib.check(lib.e2e_in_apply(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, V, _p(y),
                                     _lib.stream_ptr()), "in_apply")
+        ctx.out_ptrs = (y.data_ptr(),)
         ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, *srcs)
         return y
 
     @staticmethod
     def backward(ctx, dy, dyp=None):
         lib = _lib.load()
+        for ptr in ctx.out_ptrs:
+            _fanin_retire(ptr)
         plan: ShiftConvPlan = ctx.plan
         weight, gamma, beta, raw, mean, rstd = ctx.saved_tensors[:6]
+        bias = ctx.bias
         am = None
         if ctx.pool_k is not None:
             am = ctx.saved_tensors[6]
@@ -422,9 +520,16 @@ class ShiftConvINLReLU(torch.autograd.Function):
         partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
         sums = torch.empty(B * Cb * 16, dtype=torch.float32, device=dev)
         draw = torch.empty_like(raw)
-        dgamma = torch.empty(plan.cout, dtype=torch.float32, device=dev)
-        dbeta = torch.empty_like(dgamma)
-        dbias = torch.empty_like(dgamma)
+        # small-parameter gradients go straight into the flat gradient arena when the trainer installed one
+        slots = {}
+        def small(prm, needed=True):
+            a, v = _grad_slot(prm) if (prm is not None and needed and prm.dtype == torch.float32) else (None, None)
+            if a is not None:
+                slots[id(prm)] = (a, prm)
+                return v
+            return torch.empty(plan.cout, dtype=torch.float32, device=dev)
+        dgamma, dbeta = small(gamma), small(beta)
+        dbias = small(bias, ctx.needs_input_grad[3])
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         if am is not None and dyp is not None:
             kd, kh, kw = ctx.pool_k
@@ -438,20 +543,23 @@ class ShiftConvINLReLU(torch.autograd.Function):
                                       _p(partial), nch, _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
                                       _lib.stream_ptr()), "in_bwd")
         # weight gradient (dense, also at masked positions: SURVEY H3)
+        for a, prm in slots.values():
+            a.mark_ready(prm)
         gw = None
         if ctx.needs_input_grad[2]:
-            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl)
+            arena, slot = _grad_slot(weight)
+            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot)
+            if arena is not None:
+                arena.mark_ready(weight)
         # data gradients of every source
         need = [ctx.needs_input_grad[8 + i] for i in range(len(srcs))]
         dsrcs: List[Optional[torch.Tensor]] = [None] * len(srcs)
         if any(need):
-            outs = [(torch.zeros_like(s) if plan.dgrad_needs_zero else torch.empty_like(s)) for s in srcs]
-            for group in plan.dgrad_groups:          # column chunks of one GEMM go out as one launch
-                it = plan.dgrad_iter_grid(group[0], D, H, W)
-                if min(it) <= 0:
-                    continue
-                run_gemm_chunks(group, weight, ctx.mask, [draw], (Do, Ho, Wo), it, B, outs, (D, H, W),
-                                [s.shape[1] for s in srcs], impl)
+            # column chunks of one GEMM go out as one launch; gradients of activations that already received a
+            # contribution from another consumer are accumulated in the epilogue (see _FANIN)
+            outs = _dgrad_into(plan.dgrad_groups, weight, ctx.mask, [draw], (Do, Ho, Wo),
+                               lambda var: plan.dgrad_iter_grid(var, D, H, W), B, list(srcs), (D, H, W), impl,
+                               plan.dgrad_needs_zero)
             dsrcs = [o if n else None for o, n in zip(outs, need)]
         return (None, None, gw, dbias.to(weight.dtype) if ctx.needs_input_grad[3] else None,
                 dgamma.to(gamma.dtype), dbeta.to(beta.dtype), None, None, *dsrcs)
@@ -470,11 +578,13 @@ class TConv(torch.autograd.Function):
         run_gemm_chunks(plan.fwd, weight, mask, [x], (D, H, W), (D, H, W), B, [y], (D * kd, H * kh, W * kw),
                         [plan.cout // 8], impl)
         ctx.plan, ctx.mask = plan, mask
+        ctx.out_ptr = y.data_ptr()
         ctx.save_for_backward(weight, x)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        _fanin_retire(ctx.out_ptr)
         plan: TConvPlan = ctx.plan
         weight, x = ctx.saved_tensors
         B, Cb, D, H, W = c8_shape(x)
@@ -484,10 +594,13 @@ class TConv(torch.autograd.Function):
         impl = CONFIG["impl"]
         gw = dx = None
         if ctx.needs_input_grad[1]:
-            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl)
+            arena, slot = _grad_slot(weight)
+            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot)
+            if arena is not None:
+                arena.mark_ready(weight)
         if ctx.needs_input_grad[3]:
-            dx = torch.empty_like(x)
-            run_gemm_chunks(plan.dgrad, weight, ctx.mask, [dy], fine, (D, H, W), B, [dx], (D, H, W), [Cb], impl)
+            dx = _dgrad_into([plan.dgrad], weight, ctx.mask, [dy], fine, lambda var: (D, H, W), B, [x], (D, H, W), impl,
+                             False)[0]
         return None, gw, None, dx
 
 
@@ -504,11 +617,13 @@ class MaxPool(torch.autograd.Function):
         _lib.check(_lib.load().e2e_maxpool_fwd(_p(x), _p(y), _p(am), B * Cb, D, H, W, kd, kh, kw, _lib.stream_ptr()),
                    "maxpool_fwd")
         ctx.k, ctx.shape = (kd, kh, kw), (B, Cb, D, H, W)
+        ctx.out_ptr = y.data_ptr()
         ctx.save_for_backward(am)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        _fanin_retire(ctx.out_ptr)
         (am,) = ctx.saved_tensors
         B, Cb, D, H, W = ctx.shape
         kd, kh, kw = ctx.k
@@ -541,11 +656,13 @@ class SegHead(torch.autograd.Function):
         impl = CONFIG["impl"]
         gw = dx = None
         if ctx.needs_input_grad[1]:
-            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl)
+            arena, slot = _grad_slot(weight)
+            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl, out=slot)
+            if arena is not None:
+                arena.mark_ready(weight)
         if ctx.needs_input_grad[2]:
-            wp = pack_weights(plan.dgrad, weight, None)
-            dx = torch.empty_like(x)
-            run_gemm(plan.dgrad, wp, [g], (D, H, W), (D, H, W), B, [dx], (D, H, W), [Cb], impl)
+            dx = _dgrad_into([[plan.dgrad]], weight, None, [g], (D, H, W), lambda var: (D, H, W), B, [x], (D, H, W), impl,
+                             False)[0]
         return None, gw, dx
 
 

@@ -100,11 +100,18 @@ class SparseArgs(argparse.Namespace):
 
 
 class TrainStep(object):
-    """one data-parallel replica of the reference's training iteration on synthetic data."""
+    """one data-parallel replica of the reference's training iteration on synthetic data.
+
+    fused_optimizer=True (default): clip_grad_norm_ + Nesterov SGD + apply_mask run as the three multi-tensor
+    launches of optim.FusedSGD, weight gradients are written by the backward kernels straight into one flat
+    gradient arena (laid out in gradient-ready order), and under data parallelism that arena is all-reduced in
+    `n_buckets` buckets on a communication stream while the rest of the backward still runs.
+    fused_optimizer=False: stock torch.optim.SGD + clip_grad_norm_ + Masking.apply_mask and one flat all-reduce
+    after the backward, exactly the calls the unchanged reference trainer makes around the drop-in modules."""
 
     def __init__(self, in_ch=1, num_classes=14, pools=None, patch=(64, 160, 160), density=0.2, death_rate=0.5,
                  update_frequency=1200, device="cuda", world_size=1, seed=0, base=48, total_steps=250000,
-                 fused_loss=True):
+                 fused_loss=True, fused_optimizer=True, n_buckets=4, process_group=None):
         from .sparselearning.core_channel import CosineDecay, Masking
         import random
         pools = POOLS["btcv"] if pools is None else pools
@@ -112,8 +119,15 @@ class TrainStep(object):
         self.device = torch.device(device)
         self.pools, self.patch, self.in_ch, self.num_classes = pools, tuple(patch), in_ch, num_classes
         self.network = build_network(in_ch, num_classes, pools, patch, base).to(self.device)
-        self.optimizer = torch.optim.SGD(self.network.parameters(), 1e-2, weight_decay=3e-5, momentum=0.99,
-                                         nesterov=True)
+        self.fused_optimizer = bool(fused_optimizer)
+        self.group = process_group
+        if self.fused_optimizer:
+            from .optim import FusedSGD
+            self.optimizer = FusedSGD(self.network.parameters(), 1e-2, momentum=0.99, weight_decay=3e-5, nesterov=True,
+                                      max_norm=12.0, grad_scale=1.0 / max(1, world_size))
+        else:
+            self.optimizer = torch.optim.SGD(self.network.parameters(), 1e-2, weight_decay=3e-5, momentum=0.99,
+                                             nesterov=True)
         args = SparseArgs()
         args.update_frequency = update_frequency
         random.seed(seed)
@@ -121,8 +135,12 @@ class TrainStep(object):
                             death_rate_decay=CosineDecay(death_rate, total_steps), growth_mode='random',
                             redistribution_mode='none', args=args)
         self.mask.add_module(self.network, sparse_init='uniform', density=density)
+        if self.fused_optimizer:
+            self.optimizer.set_masks_from(self.mask)
         self.world_size = world_size
-        self._flat = None
+        self.n_buckets = n_buckets
+        self.arena = None               # built after the first backward (gradient-ready order is recorded there)
+        self._comm = None
         self._graph = None
         # the trainer's loss (nnUNetTrainer_simple.py:100,200-215): fused statistics kernels, or plain torch
         if fused_loss:
@@ -136,23 +154,82 @@ class TrainStep(object):
         """data-parallel gradient mean over NCCL (one flat bucket; grads are ~95 MB fp32)."""
         allreduce_mean_grads(list(self.network.parameters()), self.world_size)
 
+    # ------------------------------------------------------------------ gradient arena + bucketed all-reduce
+    def _record_ready_order(self, data, targets):
+        """one plain iteration (no arena) whose only extra job is to record the order in which the parameters
+        receive their gradients; the arena is laid out in that order so that its buckets complete front to back"""
+        order, hooks = [], []
+        for p in self.network.parameters():
+            hooks.append(p.register_post_accumulate_grad_hook(lambda q, order=order: order.append(q)))
+        self.optimizer.zero_grad(set_to_none=True)
+        self.loss(self.network(data), targets).backward()
+        for h in hooks:
+            h.remove()
+        seen = set(id(q) for q in order)
+        order += [p for p in self.network.parameters() if id(p) not in seen]
+        self.optimizer.zero_grad(set_to_none=True)
+        return order
+
+    def _build_arena(self, data, targets):
+        from .optim import GradArena, attach_arena
+        self.arena = GradArena(self._record_ready_order(data, targets), n_buckets=self.n_buckets)
+        attach_arena(self.arena)
+        if self.world_size > 1:
+            self._comm = torch.cuda.Stream(device=self.device)
+            self.arena.on_bucket_ready = self._allreduce_bucket
+
+    def _allreduce_bucket(self, b: int):
+        """bucket b of the arena is complete on the compute stream: sum it over the ranks on the communication
+        stream (NCCL over NVLink / NVSwitch) while the backward continues; the mean's 1/world is FusedSGD's grad_scale"""
+        import torch.distributed as dist
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ev)
+            dist.all_reduce(self.arena.bucket(b), group=self.group)
+        self._reduced.add(b)
+
     def _device_step(self, data, targets):
         """everything of one iteration that runs on the device (no host synchronisation)"""
-        self.optimizer.zero_grad()
+        if not self.fused_optimizer:
+            self.optimizer.zero_grad()
+            output = self.network(data)
+            l = self.loss(output, targets)
+            l.backward()
+            if self.world_size > 1:
+                self._allreduce_grads()
+            torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+            self.optimizer.step()
+            return l.detach()
+        if self.arena is None:
+            self._build_arena(data, targets)
+        self.optimizer.zero_grad(set_to_none=True)
+        self._reduced = set()
+        self.arena.begin_step()
         output = self.network(data)
         l = self.loss(output, targets)
         l.backward()
         if self.world_size > 1:
-            self._allreduce_grads()
-        torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
-        self.optimizer.step()
+            for b in range(self.arena.n_buckets):        # buckets whose completion the hooks did not see
+                if b not in self._reduced:
+                    self._allreduce_bucket(b)
+            torch.cuda.current_stream().wait_stream(self._comm)
+        if not self._arena_checked:
+            for p in self.network.parameters():
+                if p.grad is None or p.grad.data_ptr() != self.arena.view(p).data_ptr():
+                    raise RuntimeError("TrainStep: a gradient did not land in the arena (autograd copied it); the "
+                                       "bucketed all-reduce would miss it")
+            self._arena_checked = True
+        self.optimizer.step()                 # clip + Nesterov SGD + apply_mask, three launches
         return l.detach()
+
+    _arena_checked = False
 
     def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
         if self._graph is not None:
             return self._graph_step(data, targets)
         l = self._device_step(data, targets)
-        self.mask.step()
+        self.mask.step(_mask_already_applied=self.fused_optimizer)
         return l
 
     # ------------------------------------------------------------------ whole-step CUDA graph
@@ -160,7 +237,10 @@ class TrainStep(object):
         """captures one training iteration (forward, loss, backward, gradient all-reduce, clip, SGD,
         apply_mask: ~750 kernel launches) into ONE CUDA graph.  Later `step()` calls copy the batch into
         the static input buffers and replay it; Masking's host bookkeeping and the rare prune / regrow
-        update stay eager.  Shapes must not change afterwards."""
+        update stay eager.  Shapes must not change afterwards.  The `warmup` iterations that precede the capture
+        are REAL training iterations on the given batch (weights, momentum, Masking.steps and the death-rate schedule
+        advance); hyper-parameters are read from FusedSGD's device array, so param_groups changes (poly-LR) take
+        effect on replay (with fused_optimizer=False torch's SGD bakes lr into the graph: re-capture after changing it)."""
         assert self._graph is None
         self._static_data = data.clone()
         self._static_targets = [t.clone() for t in targets]
@@ -169,7 +249,7 @@ class TrainStep(object):
         with torch.cuda.stream(side):
             for _ in range(max(warmup, 2)):            # lazy state: momentum buffers, plans, tensor maps, pack registry
                 self._device_step(self._static_data, self._static_targets)
-                self.mask.step()
+                self.mask.step(_mask_already_applied=self.fused_optimizer)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
@@ -178,7 +258,8 @@ class TrainStep(object):
         n0 = _lib.launch_count()
         with torch.cuda.graph(graph):
             self._static_loss = self._device_step(self._static_data, self._static_targets)
-            self.mask.apply_mask()
+            if not self.fused_optimizer:
+                self.mask.apply_mask()
         self.graph_launches = _lib.launch_count() - n0       # kernels of libe2enet_b200.so inside one replay
         self._graph = graph                                   # (capture records, it does not execute)
         from . import ops
@@ -188,12 +269,15 @@ class TrainStep(object):
     def _graph_step(self, data, targets):
         if data.data_ptr() != self._static_data.data_ptr():
             self._static_data.copy_(data, non_blocking=True)
-            for s_, t in zip(self._static_targets, targets):
+        for s_, t in zip(self._static_targets, targets):
+            if t.data_ptr() != s_.data_ptr():
                 s_.copy_(t, non_blocking=True)
+        if self.fused_optimizer:
+            self.optimizer.sync_hyper()       # learning-rate / momentum / weight-decay changes reach the replayed step
         self._graph.replay()
         # the replay changed weights (SGD, apply_mask) behind torch's version counters: any EAGER use of the
         # network after this (validation, inference) must repack its operands
         from . import ops
         ops.bump_weight_epoch()
         self.mask.step(_mask_already_applied=True)            # host bookkeeping; prune / regrow when due
-        return self._static_loss
+        return self._static_loss.clone()                      # the static buffer is overwritten by the next replay

@@ -89,11 +89,15 @@ typedef struct {
                                         outside the destination grid and must be checked (7 is always safe) */
   /* InstanceNorm statistics fused into the epilogue (tcgen05 path, out_mode 0 only; may be null): per-slot partial
    * sums of the bf16-rounded result, stats[slot][b][{sum, sum of squares}][stats_ctot] fp32, channel index =
-   * destination channel; slots = e2e_gather_gemm_stats_slots() (one per CTA x epilogue warp; every slot is
+   * destination channel; slots = e2e_gather_gemm_stats_slots() (one per CTA of the launch; every slot is
    * written completely, no atomics: bit-reproducible).  Reduce with e2e_in_stats_final().  Replaces the separate
    * statistics pass over the conv output of ConvDropoutNormNonlin (unetpp_d.py:108-110). */
   float* stats;
   int32_t stats_ctot;
+  /* tcgen05 path, out_mode 0 only: the result is ADDED to what the destination already holds (bf16(fp32(old) +
+   * fp32 accumulator)): the gradient fan-in of an activation with several consumers (the fusion grid,
+   * unetpp_d.py:453-478) is summed in the data-gradient epilogue instead of a separate add pass */
+  int32_t accumulate;
 } e2e_gemm_t;
 
 int e2e_gather_gemm(const e2e_gemm_t* p, void* stream);
@@ -103,6 +107,8 @@ int e2e_gather_gemm_multi(const e2e_gemm_t* p, int32_t n, void* stream);
 /* slots the launch e2e_gather_gemm_multi(p, n) would write into p->stats; 0 when that launch cannot fuse the
  * statistics (mma.sync path, fp32 output): then run e2e_in_stats on the result instead */
 int e2e_gather_gemm_stats_slots(const e2e_gemm_t* p, int32_t n);
+/* 1 when e2e_gather_gemm_multi(p, n) is served by a tcgen05 kernel (then `stats` / `accumulate` are honoured) */
+int e2e_gather_gemm_on_tcgen05(const e2e_gemm_t* p, int32_t n);
 
 /*
  * dwp[e/2][t][e%2][n][j] += sum_o grad[b, n/8, o, n%8] * src[...][(o*is + iv + cent[e].off + tap[t].off), j]
@@ -219,6 +225,31 @@ int e2e_mask_grow(float* mask, const int32_t* dead, const int32_t* pick, int32_t
 /* nnz[0] = #(mask != 0); fired |= mask; nnz[1] = #(fired != 0) */
 int e2e_mask_counts(const float* mask, uint8_t* fired, int64_t numel, int32_t* nnz, void* stream);
 
+/* ---------------------------------------------------------------- fused optimizer step */
+/*
+ * clip_grad_norm_ + Nesterov SGD + weight decay + Masking.apply_mask over pointer tables
+ * (nnUNetTrainer_simple.py:367-371,560-564; core_channel.py:427-434).  `tensors` is a DEVICE array; hyper is a
+ * DEVICE float[5] = {lr, momentum, weight_decay, max_norm (<= 0: no clipping), grad_scale (multiplies every
+ * gradient first, e.g. 1/world_size or a GradScaler's inverse scale)} so captured graphs follow LR schedules.
+ *   e2e_sgd_clip_coef: norm_coef[0] = ||grad_scale * g||_2 over all tensors, [1] = min(1, max_norm / (norm + 1e-6)),
+ *                      [2] = 1 if the norm is not finite; partial: scratch of e2e_sgd_partial_count() floats.
+ *   e2e_sgd_update:    g' = g * grad_scale * coef + wd * p;  buf = momentum * buf + g';
+ *                      p = (p - lr * (nesterov ? g' + momentum * buf : buf)) * mask;  buf *= mask   (mask may be null);
+ *                      skipped entirely when norm_coef[2] != 0.  Gradients are left unscaled in memory.
+ */
+typedef struct {
+  float* p;
+  const float* g;
+  float* mom;                      /* momentum buffer (zero-initialised before the first step) */
+  const float* mask;               /* DSFF mask of this tensor or null */
+  int64_t numel;
+} e2e_sgd_tensor_t;
+int e2e_sgd_partial_count(int32_t n_tensors, int64_t max_numel);
+int e2e_sgd_clip_coef(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t max_numel, const float* hyper,
+                      float* partial, float* norm_coef, void* stream);
+int e2e_sgd_update(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t max_numel, const float* hyper,
+                   const float* norm_coef, int32_t nesterov, void* stream);
+
 /* ---------------------------------------------------------------- deep-supervision loss statistics */
 /*
  * logits fp32 [B][C][V], target fp32 [B][V] (class index as float, like the reference's target[:, 0]):
@@ -243,6 +274,14 @@ int e2e_window_accumulate(const float* logits, const float* gauss, float* agg, f
                           int32_t px, int32_t py, int32_t pz, int32_t X, int32_t Y, int32_t Z,
                           int32_t x0, int32_t y0, int32_t z0, int32_t flip, float scale, int32_t add_weight,
                           int32_t apply_softmax, void* stream);
+/* the same with the network's last layer folded in: x = bf16 C8 [Cb][px][py][pz][8] feature map of one tile,
+ * w = fp32 [ncls][C] weight of the 1x1x1 seg head (unetpp_d.py:394-401; rounded to bf16 like the GEMM operand):
+ * logits = w . x per voxel on the CUDA cores, then softmax / un-flip / scale / gauss / += as above.  The fp32
+ * logits tensor of the tile is never written or read. */
+int e2e_window_head_accumulate(const void* x, int32_t Cb, const float* w, int32_t C, const float* gauss, float* agg,
+                               float* wsum, int32_t ncls, int32_t px, int32_t py, int32_t pz, int32_t X, int32_t Y,
+                               int32_t Z, int32_t x0, int32_t y0, int32_t z0, int32_t flip, float scale,
+                               int32_t add_weight, void* stream);
 /* agg /= wsum (in place, cropped region), seg = argmax over classes (first max wins) */
 int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
                         int64_t* seg, void* stream);

@@ -317,3 +317,34 @@ def test_shiftconv_plans_random_geometries():
             got = pi.from_c8(o, c)
             assert not np.isnan(got).any(), (src, cout, stride)
             np.testing.assert_allclose(got, t.grad.numpy(), atol=1e-9, err_msg=str((src, cout, stride)))
+
+
+def test_grad_arena_layout_and_bucket_callbacks():
+    """optim.GradArena (host logic of the bucketed data-parallel all-reduce): slots are disjoint, aligned and in
+    the given (gradient-ready) order; a bucket's callback fires exactly when its last parameter is marked."""
+    import torch
+    from e2enet_medical_b200.optim import GradArena
+    ps = [torch.nn.Parameter(torch.zeros(s)) for s in ((48, 96, 1, 3, 3), (48,), (48,), (96, 48, 1, 2, 2), (14, 48, 1, 1, 1), (7,))]
+    arena = GradArena(ps, n_buckets=3, align=64)
+    offs = [arena.offset[id(p)] for p in ps]
+    assert offs == sorted(offs) and all(o % 64 == 0 for o in offs)
+    for a, b, p in zip(offs, offs[1:] + [arena.total], ps):
+        assert b - a >= p.numel()
+    assert arena.bucket_range[0][0] == 0 and arena.bucket_range[-1][1] == arena.total
+    for (l0, h0), (l1, h1) in zip(arena.bucket_range, arena.bucket_range[1:]):
+        assert h0 == l1
+    v = arena.view(ps[3])
+    v.fill_(2.0)
+    assert float(arena.flat.sum()) == 2.0 * ps[3].numel() and v.shape == ps[3].shape
+    assert arena.view(ps[3]) is not v                          # a fresh tensor object per call (AccumulateGrad adopts it)
+    fired = []
+    arena.on_bucket_ready = fired.append
+    arena.begin_step()
+    for p in reversed(ps):                                     # any marking order: a bucket fires with its last member
+        before = len(fired)
+        arena.mark_ready(p)
+        b = arena.bucket_of[id(p)]
+        members = [q for q in ps if arena.bucket_of[id(q)] == b]
+        done = all(id(q) not in arena._pending[b] for q in members)
+        assert (len(fired) > before) == done
+    assert sorted(fired) == list(range(arena.n_buckets))
