@@ -76,6 +76,10 @@ class WgradParams(C.Structure):
         ("Npad", C.c_int32),
         ("dwp", C.c_void_p),
         ("impl", C.c_int32),
+        ("grad_out", C.c_void_p),
+        ("rowoff", C.c_void_p),
+        ("centoff", C.c_void_p),
+        ("tapoff", C.c_void_p),
     ]
 
 
@@ -101,6 +105,7 @@ SIGNATURES = {
     "e2e_gather_gemm_on_tcgen05": (C.c_int, [C.POINTER(GemmParams), _I32]),
     "e2e_in_stats_final": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _F, _VP, _VP, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
+    "e2e_gather_wgrad_direct_ok": (C.c_int, [C.POINTER(WgradParams)]),
     "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_pack_weights_multi": (C.c_int, [_VP, _I32, _I64, _VP]),
     "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
@@ -128,7 +133,8 @@ SIGNATURES = {
     "e2e_sgd_partial_count": (C.c_int, [_I32, _I64]),
     "e2e_sgd_clip_coef": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _VP, _VP]),
     "e2e_sgd_update": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _I32, _VP]),
-    "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP]),
+    "e2e_softmax_stats_partial_count": (C.c_int, [_I32, _I32, _I64]),
+    "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP, _VP]),
     "e2e_softmax_stats_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I64, _VP, _VP]),
     "e2e_window_accumulate": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                         _I32, _I32, _F, _I32, _I32, _VP]),

@@ -71,7 +71,7 @@ struct TcParams {
   float* stats;
   int stats_ctot;                  // channels per row of `stats` (destination channel = col.blk * 8 + e)
   int stats_smem_off;              // byte offset of the per-warp accumulators [epi_warps][2][Npad] in dynamic smem
-  int accum;                       // the result is ADDED to the destination (gradient fan-in of an activation)
+  int accum;                       // bit i: the result is ADDED to destination i (gradient fan-in of an activation)
 };
 
 struct alignas(64) TcMaps {
@@ -580,7 +580,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             olds[u] = make_uint4(0, 0, 0, 0);
             if (u >= 2 && !two) continue;
             dps[u] = dst_of(u);
-            if (dps[u]) olds[u] = *reinterpret_cast<const uint4*>(dps[u]);
+            if (dps[u] && ((p.accum >> ccols[(c0 >> 3) + u].dst) & 1)) olds[u] = *reinterpret_cast<const uint4*>(dps[u]);
           }
         }
         tc_wait_ld();
@@ -1273,7 +1273,7 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
   p.stats = g->stats;
   p.stats_ctot = g->stats_ctot;
   p.stats_smem_off = p.b_region_bytes + p.stages * p.stage_bytes;
-  p.accum = g->accumulate ? 1 : 0;
+  p.accum = g->accumulate & ((1 << E2E_MAX_SRC) - 1);
   typedef void (*kern_t)(const TcParams, const TcMaps);
 #define E2E_TC_ROW(H, MODE) {conv_tc_kernel<H, 1, MODE>, conv_tc_kernel<H, 2, MODE>, conv_tc_kernel<H, 3, MODE>, conv_tc_kernel<H, 4, MODE>}
   static const kern_t kerns[3][2][4] = {{E2E_TC_ROW(false, 0), E2E_TC_ROW(true, 0)},
@@ -1347,6 +1347,12 @@ struct WgParams {
   const e2e_centry_t* cents;
   const e2e_tap_t* taps;
   float* dwp;
+  // direct mode: the flush adds into the gradient in the PARAMETER layout (grad[rowoff[n] + centoff[e*8+j] + tapoff[t]],
+  // the scatter e2e_unpack_wgrad would do) instead of the packed scratch
+  float* gout;
+  const int32_t* rowoff;
+  const int32_t* centoff;
+  const int32_t* tapoff;
 };
 
 struct alignas(64) WgMaps {
@@ -1500,16 +1506,26 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
       for (int gi = 0; gi < ng; ++gi) {
         const int e = e0 + gi * 16 + el;
         const bool valid = gi * 16 + el < ne;
+        const int co = (p.gout && valid) ? __ldg(p.centoff + e * 8 + j) : -1;
         for (int tl = 0; tl < nt; ++tl) {
           const int t = t0 + tl;
           // dwp index of (entry e, tap t): slab = ((e/2)*n_taps + t)*2 + e%2
           float* base = p.dwp + ((size_t)(((e >> 1) * p.n_taps + t) * 2 + (e & 1)) * p.Npad + n0) * 8 + j;
+          const int to = p.gout ? __ldg(p.tapoff + t) : 0;
           const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((gi * nt + tl) * Nc);
           for (int c = 0; c < ncol; c += 16) {
             uint32_t v[16];
             tc_ld16(acc + c, v);
             tc_wait_ld();
-            if (valid) {
+            if (p.gout) {
+              if (co >= 0) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const int ro = __ldg(p.rowoff + n0 + c + u);
+                  if (ro >= 0) atomicAdd(p.gout + (size_t)(ro + co + to), __uint_as_float(v[u]));
+                }
+              }
+            } else if (valid) {
 #pragma unroll
               for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
             }
@@ -1551,6 +1567,10 @@ struct WgsParams {
   const e2e_centry_t* cents;
   const e2e_tap_t* taps;
   float* dwp;
+  float* gout;                      // direct mode, see WgParams
+  const int32_t* rowoff;
+  const int32_t* centoff;
+  const int32_t* tapoff;
 };
 
 constexpr int GS_TH = 8;                    // tile rows
@@ -1670,16 +1690,26 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
       tc_fence_after();
       const int e = e0 + el;
       const bool valid = el < ne;
+      const int co = (p.gout && valid) ? __ldg(p.centoff + e * 8 + j) : -1;
       for (int kh = 0; kh < 3; ++kh) {
         for (int kw = 0; kw < 3; ++kw) {
           const int t = s_tap_of[kh * 3 + kw];
           float* base = p.dwp + ((size_t)(((e >> 1) * 9 + t) * 2 + (e & 1)) * Npad) * 8 + j;
+          const int to = p.gout ? __ldg(p.tapoff + t) : 0;
           const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kh * N3 + kw * Npad);
           for (int c = 0; c < Npad; c += 16) {
             uint32_t v[16];
             tc_ld16(acc + c, v);
             tc_wait_ld();
-            if (valid) {
+            if (p.gout) {
+              if (co >= 0) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const int ro = __ldg(p.rowoff + c + u);
+                  if (ro >= 0) atomicAdd(p.gout + (size_t)(ro + co + to), __uint_as_float(v[u]));
+                }
+              }
+            } else if (valid) {
 #pragma unroll
               for (int u = 0; u < 16; ++u) atomicAdd(base + (size_t)(c + u) * 8, __uint_as_float(v[u]));
             }
@@ -1735,6 +1765,7 @@ static int wgrad_gshift_launch(const e2e_wgrad_t* g, PFN_cuTensorMapEncodeTiled_
   splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.splits = splits;
   p.cents = g->cents; p.taps = g->taps; p.dwp = g->dwp; p.grad_cb = g->grad_cb;
+  p.gout = g->grad_out; p.rowoff = g->rowoff; p.centoff = g->centoff; p.tapoff = g->tapoff;
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
@@ -1846,6 +1877,7 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
   splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.splits = splits;
   p.cents = g->cents; p.taps = g->taps; p.dwp = g->dwp; p.grad_cb = g->grad_cb;
+  p.gout = g->grad_out; p.rowoff = g->rowoff; p.centoff = g->centoff; p.tapoff = g->tapoff;
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
   const int n_xmaps = g->n_src < E2E_MAX_SRC - 1 ? E2E_MAX_SRC - 1 : E2E_MAX_SRC;

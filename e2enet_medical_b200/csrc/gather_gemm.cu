@@ -554,6 +554,10 @@ static int gather_gemm_one(const e2e_gemm_t* p, void* stream, bool allow_tc) {
   return launch_gemm<1>(p, st);
 }
 
+extern "C" int e2e_gather_wgrad_direct_ok(const e2e_wgrad_t* p) {
+  return (p != nullptr && p->impl == 1 && e2e_wgrad_tc_supported(p)) ? 1 : 0;
+}
+
 extern "C" int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream) {
   E2E_ARG(p != nullptr, "gather_wgrad: null params");
   E2E_ARG(p->n_cent > 0 && (p->n_cent & 1) == 0, "gather_wgrad: n_cent must be even and > 0");
@@ -562,7 +566,12 @@ extern "C" int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long M = (long long)p->B * p->Do * p->Ho * p->Wo;
   if (M <= 0) return E2E_OK;
+  if (p->grad_out != nullptr)
+    E2E_ARG(p->rowoff && p->centoff && p->tapoff, "gather_wgrad: direct mode needs the rowoff / centoff / tapoff tables");
+  else
+    E2E_ARG(p->dwp != nullptr, "gather_wgrad: null dwp");
   if (p->impl == 1 && e2e_wgrad_tc_supported(p)) return e2e_wgrad_tc(p, st);
+  E2E_ARG(p->grad_out == nullptr, "gather_wgrad: direct mode needs the tcgen05 path (query e2e_gather_wgrad_direct_ok first)");
   const int N = p->Npad;
   if (N <= 16) return launch_wgrad<1>(p, st);
   if (N <= 32) return launch_wgrad<2>(p, st);

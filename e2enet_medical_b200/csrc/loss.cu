@@ -15,15 +15,15 @@
 
 namespace {
 
+// grid (chunks_per_b, B).  No atomics anywhere: every block writes its 3*C + 1 partial sums to
+// partial[b][chunk][3*C + 1] (warps combined in a fixed order), a second kernel sums the chunks in a fixed order.
+// A run-to-run difference of one ulp in these sums is amplified by the bf16 backward pass of the ~40 layers behind
+// it into ~1 % differences of the deepest weight gradients, so the loss statistics must be bit-reproducible.
 template <int NC>
 __global__ void __launch_bounds__(256) softmax_stats_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                                 int C, long long V, int chunks_per_b,
-                                                                float* __restrict__ stats /* [B][C][3] */,
-                                                                float* __restrict__ ce_sum) {
-  // grid: (chunks_per_b, B); block-level partial sums in shared memory, then one atomic per value
-  __shared__ float s_acc[3 * NC + 1];
-  for (int i = threadIdx.x; i < 3 * NC + 1; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
+                                                                float* __restrict__ partial) {
+  __shared__ float s_w[8][3 * NC + 1];
   const int b = blockIdx.y;
   const long long per = (V + chunks_per_b - 1) / chunks_per_b;
   const long long lo = (long long)blockIdx.x * per, hi = min(V, lo + per);
@@ -59,23 +59,46 @@ __global__ void __launch_bounds__(256) softmax_stats_fwd_kernel(const float* __r
     }
     ce += logf(sum) + mx - zy;                     // -log softmax(z)[y]
   }
-  // warp reduce, then shared-memory atomics (few per warp), then one global atomic per value
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     if (c >= C) break;
     const float a = warp_sum(sp[c]), t = warp_sum(tpv[c]), s = warp_sum(sy[c]);
-    if (lane == 0) {
-      atomicAdd(&s_acc[3 * c + 0], a);
-      atomicAdd(&s_acc[3 * c + 1], t);
-      atomicAdd(&s_acc[3 * c + 2], s);
-    }
+    if (lane == 0) { s_w[warp][3 * c + 0] = a; s_w[warp][3 * c + 1] = t; s_w[warp][3 * c + 2] = s; }
   }
   ce = warp_sum(ce);
-  if (lane == 0) atomicAdd(&s_acc[3 * NC], ce);
+  if (lane == 0) s_w[warp][3 * NC] = ce;
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(&stats[(long long)b * C * 3 + i], s_acc[i]);
-  if (threadIdx.x == 0) atomicAdd(ce_sum, s_acc[3 * NC]);
+  float* out = partial + ((long long)b * chunks_per_b + blockIdx.x) * (3 * C + 1);
+  for (int i = threadIdx.x; i < 3 * C + 1; i += blockDim.x) {
+    const int k = i < 3 * C ? i : 3 * NC;
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += s_w[w][k];
+    out[i] = acc;
+  }
+}
+
+// one warp per (b, value): lanes stride over the chunks, fp64, fixed order; stats / ce_sum are ADDED to (once,
+// by one thread per value: the caller zeroes them, and different launches never overlap on a stream)
+__global__ void softmax_stats_final_kernel(const float* __restrict__ partial, int B, int C, int chunks_per_b,
+                                           float* __restrict__ stats, float* __restrict__ ce_sum) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nv = 3 * C + 1;
+  if (i >= nv) return;
+  double ce_all = 0.0;
+  for (int b = 0; b < B; ++b) {
+    double s = 0.0;
+    for (int k = lane; k < chunks_per_b; k += 32) s += (double)partial[((long long)b * chunks_per_b + k) * nv + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (i < 3 * C) {
+      if (lane == 0) stats[(long long)b * C * 3 + i] += (float)s;
+    } else {
+      ce_all += s;
+    }
+  }
+  if (i == 3 * C && lane == 0) ce_sum[0] += (float)ce_all;
 }
 
 template <int NC>
@@ -137,16 +160,24 @@ inline int chunks_for(long long V, int B) {
 
 }  // namespace
 
+extern "C" int e2e_softmax_stats_partial_count(int32_t B, int32_t C, int64_t V) {
+  if (B <= 0 || C <= 0 || V <= 0) return 0;
+  return chunks_for(V, B) * B * (3 * C + 1);
+}
+
 extern "C" int e2e_softmax_stats_fwd(const float* logits, const float* target, int32_t B, int32_t C, int64_t V,
-                                     float* stats, float* ce_sum, void* stream) {
-  E2E_ARG(logits && target && stats && ce_sum && B > 0 && C > 0 && V > 0, "softmax_stats_fwd: bad arguments");
+                                     float* partial, float* stats, float* ce_sum, void* stream) {
+  E2E_ARG(logits && target && partial && stats && ce_sum && B > 0 && C > 0 && V > 0, "softmax_stats_fwd: bad arguments");
   E2E_ARG(C <= 32, "softmax_stats_fwd: at most 32 classes (got %d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(chunks_for(V, B), B);
-  if (C <= 4) softmax_stats_fwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
-  else if (C <= 16) softmax_stats_fwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
-  else softmax_stats_fwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, stats, ce_sum);
+  if (C <= 4) softmax_stats_fwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, partial);
+  else if (C <= 16) softmax_stats_fwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, partial);
+  else softmax_stats_fwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, C, V, grid.x, partial);
   E2E_LAUNCHED("softmax_stats_fwd");
+  const int nv = 3 * C + 1;
+  softmax_stats_final_kernel<<<(nv * 32 + 127) / 128, 128, 0, st>>>(partial, B, C, grid.x, stats, ce_sum);
+  E2E_LAUNCHED("softmax_stats_final");
   return E2E_OK;
 }
 

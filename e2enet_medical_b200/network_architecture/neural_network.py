@@ -112,7 +112,9 @@ class SegmentationNetwork(NeuralNetwork):
         the other ranks return (None, None); result_on="slab": slab ownership (option B) -- ranks
         predict contiguous x-major tile ranges into accumulators that cover only their own x-extent,
         exchange just the overlap planes with their neighbours and return the (seg, softmax) of the
-        x-slab they own (`self._last_slab` = (x_lo, x_hi) in un-padded coordinates)."""
+        x-slab they own (`self._last_slab` = (x_lo, x_hi) in un-padded coordinates); result_on="gather": slab
+        ownership, then the finalised slabs travel GPU -> GPU to rank 0, which returns the FULL (seg, softmax) like
+        the reference (the other ranks return (None, None)); every rank uploads only the x-planes its tiles read."""
         self._tile_shard = None if world_size <= 1 else (int(rank), int(world_size), group, result_on)
 
     @staticmethod
@@ -250,10 +252,15 @@ class SegmentationNetwork(NeuralNetwork):
     def _uses_softmax(self) -> bool:
         return getattr(self.inference_apply_nonlin, "__name__", "") == "softmax_helper"
 
-    def _accumulate_tile(self, tile: torch.Tensor, mirror_axes, do_mirroring, gauss, agg, wsum, origin):
-        """tile: (n,c,px,py,pz) CUDA fp32, n tiles batched through one forward (InstanceNorm is per
-        sample, so batching tiles is exact); origin: one (x0,y0,z0) or a list of n.  Fuses softmax,
-        un-mirroring, 1/num_mirrors, Gaussian and the += into agg / wsum (reference :529-563, :392-393)."""
+    def _accumulate_tile(self, tile: torch.Tensor, mirror_axes, do_mirroring, gauss, agg, wsum, origin,
+                         result_scale: float = 1.0, add_weight: bool = True):
+        """tile: (n,c,px,py,pz) CUDA fp32; origin: one (x0,y0,z0) or a list of n.  Every (tile, mirror variant) pair
+        is one SAMPLE of a forward pass -- InstanceNorm is per sample, so batching is exact -- and the pairs are
+        packed `self.tile_batch` at a time into the batch (= GEMM M) dimension: 8 mirrored copies of a single tile
+        run as one forward of batch 8 instead of eight of batch 1.  Per sample one fused
+        kernel does seg head (when foldable) + softmax + un-mirroring + 1/num_mirrors + Gaussian + `+=` into agg /
+        wsum (reference :529-563, :392-393).  result_scale / add_weight: fold ensembling (1/n_folds; the weight
+        volume is accumulated by the first fold only)."""
         lib = _lib.load()
         origins = [origin] if isinstance(origin[0], (int, np.integer)) else list(origin)
         assert len(origins) == tile.shape[0]
@@ -265,39 +272,47 @@ class SegmentationNetwork(NeuralNetwork):
             scale = 1.0 / (2 ** len(mirror_axes))
         else:
             combos, scale = [()], 1.0
+        scale *= result_scale
         fused = self._uses_softmax()
         # the network's 1x1x1 head folded into the accumulate kernel (no fp32 logits tensor): available when the
         # drop-in network would return seg_outputs[0] alone and the inference non-linearity is softmax
         head_fused = (fused and getattr(self, "fuse_head_into_window", True) and hasattr(self, "e2e_head_fusable")
                       and self.e2e_head_fusable())
-        for n, m in enumerate(combos):
-            t = torch.flip(tile, tuple(a + 2 for a in m)) if m else tile
-            flip = sum(1 << a for a in m)
+        jobs = [(i, n, m) for i in range(tile.shape[0]) for n, m in enumerate(combos)]      # mirror order of the reference
+        nb = max(1, int(getattr(self, "tile_batch", 4)))
+        gp = C.c_void_p(gauss.data_ptr() if gauss is not None else 0)
+        for j0 in range(0, len(jobs), nb):
+            grp = jobs[j0:j0 + nb]
+            if len(grp) == tile.shape[0] and all(not m for _, _, m in grp):
+                t = tile                                    # no mirroring: the batch is the tile batch itself
+            else:
+                t = torch.stack([torch.flip(tile[i], tuple(a + 1 for a in m)) if m else tile[i] for i, _, m in grp])
             if head_fused:
                 feat, hw = self.e2e_head_features(t)
                 assert feat.dtype == torch.bfloat16 and feat.is_contiguous() and tuple(feat.shape[2:5]) == (px, py, pz)
                 hw = hw.float().contiguous()
-                Cb = feat.shape[1]
-                per = feat[0].numel() * 2
-                for i, org in enumerate(origins):
+                Cb, per = feat.shape[1], feat[0].numel() * 2
+            else:
+                out = self(t)
+                if not fused:
+                    out = self.inference_apply_nonlin(out)
+                out = out.float().contiguous()
+                assert out.shape[1] == ncls
+                per = out[0].numel() * 4
+            for k, (i, n, m) in enumerate(grp):
+                org = origins[i]
+                flip = sum(1 << a for a in m)
+                addw = 1 if (n == 0 and add_weight) else 0
+                if head_fused:
                     _lib.check(lib.e2e_window_head_accumulate(
-                        C.c_void_p(feat.data_ptr() + i * per), Cb, C.c_void_p(hw.data_ptr()), hw.shape[1],
-                        C.c_void_p(gauss.data_ptr() if gauss is not None else 0), C.c_void_p(agg.data_ptr()),
-                        C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z, int(org[0]), int(org[1]), int(org[2]), flip,
-                        scale, 1 if n == 0 else 0, _lib.stream_ptr()), "window_head_accumulate")
-                continue
-            out = self(t)
-            if not fused:
-                out = self.inference_apply_nonlin(out)
-            out = out.float().contiguous()
-            assert out.shape[1] == ncls
-            per = out[0].numel() * 4
-            for i, org in enumerate(origins):
-                _lib.check(lib.e2e_window_accumulate(
-                    C.c_void_p(out.data_ptr() + i * per), C.c_void_p(gauss.data_ptr() if gauss is not None else 0),
-                    C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z,
-                    int(org[0]), int(org[1]), int(org[2]), flip, scale, 1 if n == 0 else 0, 1 if fused else 0,
-                    _lib.stream_ptr()), "window_accumulate")
+                        C.c_void_p(feat.data_ptr() + k * per), Cb, C.c_void_p(hw.data_ptr()), hw.shape[1], gp,
+                        C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()), ncls, px, py, pz, X, Y, Z,
+                        int(org[0]), int(org[1]), int(org[2]), flip, scale, addw, _lib.stream_ptr()), "window_head_accumulate")
+                else:
+                    _lib.check(lib.e2e_window_accumulate(
+                        C.c_void_p(out.data_ptr() + k * per), gp, C.c_void_p(agg.data_ptr()), C.c_void_p(wsum.data_ptr()),
+                        ncls, px, py, pz, X, Y, Z, int(org[0]), int(org[1]), int(org[2]), flip, scale, addw,
+                        1 if fused else 0, _lib.stream_ptr()), "window_accumulate")
 
     def _finalize(self, agg, wsum):
         lib = _lib.load()
@@ -333,6 +348,7 @@ class SegmentationNetwork(NeuralNetwork):
         bufs[:] = [b for b in bufs if in_use(b)][-2:]                # do not hoard: remember at most two lent buffers
         b = torch.empty(tuple(shape), dtype=dtype, pin_memory=torch.cuda.is_available())
         bufs.append(b)
+        self._pinned_allocs = getattr(self, "_pinned_allocs", 0) + 1      # diagnostic: should stop growing in steady state
         return b
 
     def _to_host(self, t: torch.Tensor, tag: str) -> np.ndarray:
@@ -357,6 +373,15 @@ class SegmentationNetwork(NeuralNetwork):
         assert len(x.shape) == 4, "x must be (c, x, y, z)"
         assert patch_size is not None, "patch_size cannot be None for tiled prediction"
         dev = self._device()
+        import time as _time
+        prof = bool(getattr(self, "profile_phases", False))     # diagnostic: synchronise after every phase and time it
+        marks = [("start", _time.perf_counter())]
+
+        def mark(name):
+            if prof:
+                torch.cuda.synchronize()
+                marks.append((name, _time.perf_counter()))
+                self._last_host_phases = {b[0]: (b[1] - a[1]) * 1e3 for a, b in zip(marks, marks[1:])}
         data, slicer = pad_nd_image(x, patch_size, pad_border_mode, pad_kwargs, True, None)
         data_shape = data.shape
         steps = self._compute_steps_for_sliding_window(patch_size, data_shape[1:], step_size)
@@ -371,32 +396,43 @@ class SegmentationNetwork(NeuralNetwork):
                 self._patch_size_for_gaussian_3d = patch_size
             gauss = torch.from_numpy(self._gaussian_3d).to(dev, non_blocking=True).contiguous()
 
-        vol = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).to(dev, non_blocking=True)
         tiles = [(a, b, c) for a in steps[0] for b in steps[1] for c in steps[2]]
         shard = self._tile_shard
         slab = None
         xoff, xext = 0, data_shape[1]
-        if shard is not None and shard[3] == "slab":
+        if shard is not None and shard[3] in ("slab", "gather"):
             cut, bx, hi = self._slab_plan(tiles, patch_size[0], data_shape[1], shard[1])
             slab = (bx, hi)
             tiles = tiles[cut[shard[0]]:cut[shard[0] + 1]]
             xoff, xext = bx[shard[0]], max(hi[shard[0]], bx[shard[0] + 1]) - bx[shard[0]]
         elif shard is not None:
             tiles = self._shard_tiles(tiles, shard[0], shard[1])
-        # accumulators cover x in [xoff, xoff + xext) (the whole padded volume unless slab mode)
+        # host -> device: only the x-planes this rank's tiles read (the whole padded volume unless slab ownership)
+        vol = torch.from_numpy(np.ascontiguousarray(data[:, xoff:xoff + xext], dtype=np.float32)).to(dev, non_blocking=True)
+        self._last_h2d_bytes = int(vol.numel() * 4)
+        mark("pad_and_upload_ms")
+        # accumulators cover x in [xoff, xoff + xext)
         agg = torch.zeros((self.num_classes, xext) + tuple(data_shape[2:]), dtype=torch.float32, device=dev)
         wsum = torch.zeros((xext,) + tuple(data_shape[2:]), dtype=torch.float32, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         nb = max(1, int(getattr(self, "tile_batch", 4)))      # tiles per forward (exact: per-sample norm)
-        for i0 in range(0, len(tiles), nb):
-            grp = tiles[i0:i0 + nb]
-            tile = torch.stack([vol[:, a:a + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]]
-                                for (a, b, c) in grp])
-            self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum,
-                                  [(a - xoff, b, c) for (a, b, c) in grp])
+        # fold ensembling on the device (inference/predict.py:282-296: softmax = mean over the folds' softmax): every
+        # fold's weights are loaded in turn and accumulate into the SAME accumulators with scale 1/n_folds; the weight
+        # volume is identical for all folds, so it is accumulated once and a single finalise yields the mean
+        folds = getattr(self, "_ensemble_params", None) or [None]
+        for fi, params in enumerate(folds):
+            if params is not None:
+                self.load_state_dict(params)
+            for i0 in range(0, len(tiles), nb):
+                grp = tiles[i0:i0 + nb]
+                tile = torch.stack([vol[:, a - xoff:a - xoff + patch_size[0], b:b + patch_size[1], c:c + patch_size[2]]
+                                    for (a, b, c) in grp])
+                self._accumulate_tile(tile, mirror_axes, do_mirroring, gauss, agg, wsum,
+                                      [(a - xoff, b, c) for (a, b, c) in grp], 1.0 / len(folds), fi == 0)
         ev_t = torch.cuda.Event(enable_timing=True)
         ev_t.record()
+        mark("tile_loop_ms")
         self._last_phase_events = (ev0, ev_t)
         if slab is not None:
             bx, hi = slab
@@ -417,14 +453,19 @@ class SegmentationNetwork(NeuralNetwork):
                 self._last_num_tiles, self._last_tile_loop_ms = num_tiles, ev0.elapsed_time(ev1)
                 return None, None
 
-        if agg.shape[1] == 0:                                 # slab mode: this rank owns no planes
-            ev1.record()
-            torch.cuda.current_stream().synchronize()
-            self._last_num_tiles, self._last_tile_loop_ms, self._last_slab = num_tiles, ev0.elapsed_time(ev1), (0, 0)
-            return None, None
-        seg = self._finalize(agg, wsum)                       # agg now holds agg / wsum
+        gather = shard is not None and shard[3] == "gather"
+        seg = None
+        if agg.shape[1] > 0:
+            seg = self._finalize(agg, wsum)                   # agg now holds agg / wsum
         ev1.record()
+        mark("exchange_and_finalize_ms")
         self._last_tile_events, self._last_num_tiles = (ev0, ev1), num_tiles
+        if gather:
+            return self._gather_slabs(seg, agg, slab[0], shard, data_shape, slicer, regions_class_order, ev0, ev1, verbose)
+        if agg.shape[1] == 0:                                 # slab mode: this rank owns no planes
+            torch.cuda.current_stream().synchronize()
+            self._last_tile_loop_ms, self._last_slab = ev0.elapsed_time(ev1), (0, 0)
+            return None, None
         sp = list(slicer[1:])
         if slab is not None:
             # un-pad: intersect the owned planes [xoff, xoff + own) with the un-padded x-range
@@ -445,9 +486,89 @@ class SegmentationNetwork(NeuralNetwork):
                 predicted_segmentation[class_probabilities[i] > 0.5] = c
         if verbose:
             print("prediction done")
+        mark("results_to_host_ms")
         # device time of tile loop + reduce + finalise of the last call (events are complete: the D2H copies synchronised)
         self._last_tile_loop_ms = ev0.elapsed_time(ev1)
         return predicted_segmentation, class_probabilities
+
+    def _gather_slabs(self, seg, probs, bx, shard, data_shape, slicer, regions_class_order, ev0, ev1, verbose):
+        """result_on="gather": every rank owns the finalised labels / probabilities of its x-slab on its GPU; they
+        travel GPU -> GPU (NCCL point-to-point over NVLink / NVSwitch, labels as uint8) to rank 0, which assembles
+        the FULL (seg, softmax) in pooled pinned host buffers and returns exactly what the reference's predict_3D
+        returns (neural_network.py:396-426); the other ranks return (None, None)."""
+        import torch.distributed as dist
+        rank, world, group = shard[0], shard[1], shard[2]
+        dev = probs.device
+        ncls = self.num_classes
+        Y, Z = data_shape[2], data_shape[3]
+        small = ncls <= 255
+        if rank != 0:
+            ops_ = []
+            if probs.shape[1] > 0:
+                lab = seg.to(torch.uint8) if small else seg
+                ops_ = [dist.P2POp(dist.isend, probs, 0, group), dist.P2POp(dist.isend, lab, 0, group)]
+                for req in dist.batch_isend_irecv(ops_):
+                    req.wait()
+            torch.cuda.current_stream().synchronize()
+            self._last_tile_loop_ms = ev0.elapsed_time(ev1)
+            self._last_slab = (bx[rank], bx[rank + 1])
+            return None, None
+        pieces, ops_ = [], []
+        for r in range(1, world):
+            own = bx[r + 1] - bx[r]
+            if own <= 0:
+                continue
+            pr = torch.empty((ncls, own, Y, Z), dtype=torch.float32, device=dev)
+            lb = torch.empty((own, Y, Z), dtype=torch.uint8 if small else torch.int64, device=dev)
+            pieces.append((bx[r], own, pr, lb))
+            ops_ += [dist.P2POp(dist.irecv, pr, r, group), dist.P2POp(dist.irecv, lb, r, group)]
+        reqs = dist.batch_isend_irecv(ops_) if ops_ else []
+        X = data_shape[1]
+        probs_h = self._host_buffer((ncls, X, Y, Z), torch.float32, "probs") if getattr(self, "pinned_output_buffers", True) \
+            else torch.empty((ncls, X, Y, Z), dtype=torch.float32)
+        seg_h = self._host_buffer((X, Y, Z), torch.int64, "seg") if getattr(self, "pinned_output_buffers", True) \
+            else torch.empty((X, Y, Z), dtype=torch.int64)
+
+        def deliver(lo, own, pr, lb):
+            for c in range(ncls):                             # probs_h[c, lo:lo+own] is contiguous on the host
+                probs_h[c, lo:lo + own].copy_(pr[c], non_blocking=True)
+            seg_h[lo:lo + own].copy_(lb.to(torch.int64), non_blocking=True)
+
+        if probs.shape[1] > 0:
+            deliver(bx[0], probs.shape[1], probs, seg)        # own slab first: overlaps with the incoming transfers
+        for req in reqs:
+            req.wait()
+        for lo, own, pr, lb in pieces:
+            deliver(lo, own, pr, lb)
+        torch.cuda.current_stream().synchronize()
+        self._last_tile_loop_ms = ev0.elapsed_time(ev1)
+        self._last_slab = (0, X)
+        sp = tuple(slicer[1:])
+        class_probabilities = probs_h.numpy()[(slice(None),) + sp]
+        if regions_class_order is None:
+            predicted_segmentation = seg_h.numpy()[sp]
+        else:
+            predicted_segmentation = np.zeros(class_probabilities.shape[1:], dtype=np.float32)
+            for i, c in enumerate(regions_class_order):
+                predicted_segmentation[class_probabilities[i] > 0.5] = c
+        if verbose:
+            print("prediction done")
+        return predicted_segmentation, class_probabilities
+
+    # ------------------------------------------------------------------ fold ensembling (SURVEY 8(f) rank 3)
+    def predict_3D_ensemble(self, x: np.ndarray, fold_params, *args, **kwargs):
+        """the fold loop of inference/predict.py:282-296 on the device: `softmax = mean_f predict_3D(x; params_f)[1]`
+        and its argmax.  fold_params: state_dicts (as `load_checkpoint_ram` feeds them, nnUNetTrainer_simple.py:
+        1211-1255); remaining arguments as predict_3D.  All folds accumulate into one set of device accumulators,
+        one finalise, ONE device -> host transfer instead of one per fold; the network ends holding the last fold."""
+        fold_params = list(fold_params)
+        if not fold_params:
+            raise ValueError("predict_3D_ensemble: no fold parameters")
+        self._ensemble_params = fold_params
+        try:
+            return self.predict_3D(x, *args, **kwargs)
+        finally:
+            self._ensemble_params = None
 
     def _internal_predict_3D_3Dconv(self, x: np.ndarray, min_size: Tuple[int, ...], do_mirroring: bool,
                                     mirror_axes: tuple = (0, 1, 2), regions_class_order: tuple = None,

@@ -384,13 +384,14 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
                 raise NotImplementedError("transposed conv must have kernel == stride and no bias")
             self._tplans[key] = build_tconv_plan(mod.in_channels, mod.out_channels, mod.kernel_size)
         y = ops.TConv.apply(self._tplans[key], mod.weight, getattr(mod, "e2e_weight_mask", None), x.tensor)
+        ops.debug_tap(y, "tconv_out:%d" % (key % 100000))
         return C8(y, [mod.out_channels])
 
     def _pool(self, mod: nn.MaxPool3d, x: C8) -> C8:
         k = _triple(mod.kernel_size)
         if x.pooled is not None and tuple(x.pooled[1]) == k:
             return C8(x.pooled[0], x.channels)         # produced by the block's fused norm + pool pass
-        return C8(ops.MaxPool.apply(x.tensor, k), x.channels)
+        return C8(ops.debug_tap(ops.MaxPool.apply(x.tensor, k), "pool_out:%s" % (tuple(x.tensor.shape[2:5]),)), x.channels)
 
     def _seg(self, k: int, x: C8):
         mod = self.seg_outputs[k]
@@ -438,6 +439,7 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
         for s in range(6):
             h = self.conv_blocks_context[s](h)
             node[(s, 0)] = h
+            ops.debug_tap(h.parts[0], "node:%d_0" % s)
         for j in range(1, 6):
             for i in range(5 - j, -1, -1):
                 z, idx = 5 - i - j, j - 1
@@ -445,6 +447,7 @@ class Generic_UNetPlusPlus(SegmentationNetwork):
                 if i > 0:
                     parts.append(self._pool(getattr(self, "down%d" % z)[idx], node[(i - 1, j - 1)]))
                 node[(i, j)] = getattr(self, "loc%d" % z)[idx](C8.cat(parts))
+                ops.debug_tap(node[(i, j)].parts[0], "node:%d_%d" % (i, j))
         return node
 
     @staticmethod

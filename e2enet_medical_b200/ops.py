@@ -17,16 +17,24 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True}
+CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True, "wgrad_direct": False}
 # A/B switches for measurements (tools/, bench.py): E2E_FUSE_STATS=0 / E2E_FUSE_FANIN=0 / E2E_FUSE_POOL=0 / E2E_STACK3=0
 import os as _os
 for _k, _e in (("fuse_stats", "E2E_FUSE_STATS"), ("fuse_fanin", "E2E_FUSE_FANIN"), ("fuse_pool", "E2E_FUSE_POOL"),
-               ("stack3", "E2E_STACK3")):
+               ("stack3", "E2E_STACK3"), ("wgrad_direct", "E2E_WGRAD_DIRECT")):
     if _os.environ.get(_e) is not None:
         CONFIG[_k] = _os.environ[_e] not in ("0", "false", "False")
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
 # (kind, start_event, end_event, algorithmic dense FLOPs = 2*M*N*K over real rows/cols only)
 PROFILE = {"enabled": False, "records": []}
+# debugging aid (tools/debug_grads3.py): when a dict, the network records the gradient arriving at every activation
+DEBUG_GRADS = None
+
+
+def debug_tap(t: torch.Tensor, name: str):
+    if DEBUG_GRADS is not None and t.requires_grad:
+        t.register_hook(lambda g, name=name: DEBUG_GRADS.__setitem__(name, g.detach().clone()))
+    return t
 
 
 def _plan_flops(plan: GemmPlan, M: int) -> float:
@@ -102,34 +110,32 @@ def _dgrad_into(groups, weight, mask, srcs_of_gemm, src_grid, iter_grid_of, B, t
         d, a = _fanin_dst(t, needs_zero)
         dsts.append(d)
         accs.append(a)
-    if any(accs) and not all(accs):
-        # mixed: give the not-yet-started targets a zeroed buffer and accumulate everywhere
-        for i, (t, a) in enumerate(zip(targets, accs)):
-            if not a:
-                dsts[i].zero_()
-    acc = any(accs)
+    accmask = sum(1 << i for i, a in enumerate(accs) if a)       # per-destination: accumulate or overwrite
     dst_cb = [t.shape[1] for t in targets]
     temps = None
     for group in groups:
         it = iter_grid_of(group[0])
         if min(it) <= 0:
             continue
-        if acc:
-            # accumulate needs the tcgen05 epilogue; otherwise fall back to a temporary + add
+        if accmask:
+            # accumulate needs the tcgen05 epilogue; otherwise the accumulating targets get a temporary + add
             arr = (_lib.GemmParams * len(group))()
             for i, pl in enumerate(group):
                 _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl)
             if impl == 1 and int(lib.e2e_gather_gemm_on_tcgen05(arr, len(group))):
-                run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl, accumulate=True)
+                run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl,
+                                accumulate=accmask)
             else:
                 if temps is None:
-                    temps = [torch.zeros_like(t) for t in targets]
+                    temps = [(torch.zeros_like(t) if needs_zero else torch.empty_like(t)) if a else d
+                             for t, a, d in zip(targets, accs, dsts)]
                 run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, temps, dst_grid, dst_cb, impl)
         else:
             run_gemm_chunks(group, weight, mask, srcs_of_gemm, src_grid, it, B, dsts, dst_grid, dst_cb, impl)
     if temps is not None:
-        for d, t in zip(dsts, temps):
-            _lib.check(lib.e2e_add_inplace(_p(d), _p(t), d.numel(), _lib.stream_ptr()), "add_inplace")
+        for d, t, a in zip(dsts, temps, accs):
+            if a:
+                _lib.check(lib.e2e_add_inplace(_p(d), _p(t), d.numel(), _lib.stream_ptr()), "add_inplace")
     return [None if a else d for d, a in zip(dsts, accs)]
 
 
@@ -249,7 +255,7 @@ def run_gemm(plan: GemmPlan, wpacked: torch.Tensor, srcs: Sequence[torch.Tensor]
 
 def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optional[torch.Tensor],
                     srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, dsts: Sequence[torch.Tensor], dst_grid,
-                    dst_cb: Sequence[int], impl: int = 0, want_stats: bool = False, accumulate: bool = False):
+                    dst_cb: Sequence[int], impl: int = 0, want_stats: bool = False, accumulate: int = 0):
     """the column chunks of one GEMM (plans differ in columns / packed weights only): one launch.
     want_stats: ask the tcgen05 epilogue for the InstanceNorm partial sums of the (single, C8) destination;
     returns (stats tensor [slots][B][2][C], slots) or None when that launch cannot fuse them."""
@@ -259,7 +265,7 @@ def run_gemm_chunks(plans: Sequence[GemmPlan], weight: torch.Tensor, mask: Optio
     flops = 0.0
     for i, pl in enumerate(plans):
         _fill_gemm(arr[i], pl, pack_weights(pl, weight, mask), srcs, src_grid, iter_grid, B, dsts, dst_grid, dst_cb, impl)
-        arr[i].accumulate = 1 if accumulate else 0
+        arr[i].accumulate = int(accumulate)
         flops += _plan_flops(pl, B * iter_grid[0] * iter_grid[1] * iter_grid[2])
     stats = None
     if want_stats and impl == 1 and CONFIG.get("fuse_stats", True):
@@ -323,12 +329,11 @@ def _grad_slot(param: torch.Tensor):
 
 
 def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, grad: torch.Tensor,
-              weight_shape, impl: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              weight_shape, impl: int = 0, out: Optional[torch.Tensor] = None, out_is_zero: bool = False) -> torch.Tensor:
     """returns the fp32 weight gradient in the reference's parameter layout (written into `out` if given)."""
     lib = _lib.load()
     device = grad.device
     dev = plan.dev(device)
-    dwp = torch.zeros(plan.packed_numel, dtype=torch.float32, device=device)
     p = _lib.WgradParams()
     p.B = B
     p.Di, p.Hi, p.Wi = src_grid
@@ -346,9 +351,28 @@ def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid,
     p.grad = grad.data_ptr()
     p.grad_cb = grad.shape[1]
     p.Npad = plan.Npad
-    p.dwp = dwp.data_ptr()
     p.impl = impl
-    with _Timed("wgrad", _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])):
+    flops = _plan_flops(plan, B * iter_grid[0] * iter_grid[1] * iter_grid[2])
+    if impl == 1 and CONFIG.get("wgrad_direct", False) and int(lib.e2e_gather_wgrad_direct_ok(C.byref(p))):
+        # (A/B switch, default off) the tcgen05 kernels add their split-K results straight into the gradient in the
+        # parameter layout: no packed scratch, no unpack pass -- but the scattered fp32 atomics (stride 9 floats
+        # between lanes instead of 8 contiguous floats) cost more L2 atomic transactions than the unpack pass saves.
+        # The destination must start at zero: arena slots are zeroed once per step by GradArena.begin_step (passed
+        # as `out` with out_is_zero), anything else is zeroed here.
+        if out is not None and out_is_zero:
+            gw = out
+        else:
+            gw = out if out is not None else torch.empty(weight_shape, dtype=torch.float32, device=device)
+            gw.zero_()
+        assert tuple(gw.shape) == tuple(weight_shape) and gw.dtype == torch.float32 and gw.is_contiguous()
+        p.grad_out = gw.data_ptr()
+        p.rowoff, p.centoff, p.tapoff = (dev[k].data_ptr() for k in ("rowoff", "centoff", "tapoff"))
+        with _Timed("wgrad", flops):
+            _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
+        return gw
+    dwp = torch.zeros(plan.packed_numel, dtype=torch.float32, device=device)
+    p.dwp = dwp.data_ptr()
+    with _Timed("wgrad", flops):
         _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
     gw = out if out is not None else torch.empty(weight_shape, dtype=torch.float32, device=device)   # unpack writes every weight once
     assert tuple(gw.shape) == tuple(weight_shape) and gw.dtype == torch.float32 and gw.is_contiguous()
@@ -548,7 +572,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         gw = None
         if ctx.needs_input_grad[2]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot)
+            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
             if arena is not None:
                 arena.mark_ready(weight)
         # data gradients of every source
@@ -595,7 +619,7 @@ class TConv(torch.autograd.Function):
         gw = dx = None
         if ctx.needs_input_grad[1]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot)
+            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
             if arena is not None:
                 arena.mark_ready(weight)
         if ctx.needs_input_grad[3]:
@@ -657,7 +681,7 @@ class SegHead(torch.autograd.Function):
         gw = dx = None
         if ctx.needs_input_grad[1]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl, out=slot)
+            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
             if arena is not None:
                 arena.mark_ready(weight)
         if ctx.needs_input_grad[2]:
@@ -685,7 +709,8 @@ class SoftmaxStats(torch.autograd.Function):
                              % (tuple(target.shape), tuple(logits.shape)))
         stats = torch.zeros((B, Cc, 3), dtype=torch.float32, device=x.device)
         ce = torch.zeros((), dtype=torch.float32, device=x.device)
-        _lib.check(lib.e2e_softmax_stats_fwd(_p(x), _p(t), B, Cc, V, _p(stats), _p(ce), _lib.stream_ptr()),
+        partial = torch.empty(max(1, int(lib.e2e_softmax_stats_partial_count(B, Cc, V))), dtype=torch.float32, device=x.device)
+        _lib.check(lib.e2e_softmax_stats_fwd(_p(x), _p(t), B, Cc, V, _p(partial), _p(stats), _p(ce), _lib.stream_ptr()),
                    "softmax_stats_fwd")
         ctx.save_for_backward(x, t)
         sp, tp, sy = stats[..., 0].clone(), stats[..., 1].clone(), stats[..., 2].clone()

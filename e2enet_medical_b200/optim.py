@@ -57,6 +57,7 @@ class GradArena(object):
                 self.bucket_last.append(id(p))
                 lo, b = end, b + 1
         self.n_buckets = len(self.bucket_range)
+        self.zeroed_this_step = False       # begin_step() zeroed the whole buffer and nothing has been added since
         self._pending = None                # per-step: set of parameter ids of each bucket still missing
         self.on_bucket_ready = None         # callback(bucket index) -- installed by the data-parallel trainer
 
@@ -70,6 +71,10 @@ class GradArena(object):
         return id(p) in self.offset
 
     def begin_step(self):
+        """start of an iteration: zero the arena (the tcgen05 weight-gradient kernels ADD their split-K results into
+        their slots) and re-arm the bucket bookkeeping"""
+        self.flat.zero_()
+        self.zeroed_this_step = True
         self._pending = [set() for _ in range(self.n_buckets)]
         for p in self.params:
             self._pending[self.bucket_of[id(p)]].add(id(p))

@@ -228,7 +228,11 @@ class TrainStep(object):
     def step(self, data: torch.Tensor, targets: Sequence[torch.Tensor]) -> torch.Tensor:
         if self._graph is not None:
             return self._graph_step(data, targets)
+        staged = self._take_staged(data)
+        if staged is not None:
+            data, targets = staged
         l = self._device_step(data, targets)
+        self._release_stage()
         self.mask.step(_mask_already_applied=self.fused_optimizer)
         return l
 
@@ -266,12 +270,64 @@ class TrainStep(object):
         self._graph_keepalive = ops.pack_registry_keepalive(self.device)   # memory the graph's pack launch points at
         return self
 
+    # ------------------------------------------------------------------ input prefetch (host -> device overlap)
+    def prefetch(self, data: torch.Tensor, targets: Sequence[torch.Tensor]):
+        """starts the host -> device copy of the NEXT batch (pinned host tensors) on a copy stream while the current
+        iteration computes; the next `step(data, targets)` with these same host tensors then only waits for that
+        copy and moves the staged batch into the graph's static inputs with a device-side copy (30 MB: ~10 us)
+        instead of a serialised PCIe transfer (~0.6 ms).  Two staging sets alternate, so a copy never waits for
+        the iteration that is still computing."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stages, self._stage_idx = [None, None], 0
+        k = self._stage_idx
+        self._stage_idx ^= 1
+        st = self._stages[k]
+        if st is None or st["data"].shape != data.shape:
+            st = {"data": torch.empty(data.shape, dtype=data.dtype, device=self.device),
+                  "targets": [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in targets], "free": None}
+            self._stages[k] = st
+        if st["free"] is not None:
+            self._copy_stream.wait_event(st["free"])       # the iteration that last read this set has finished
+        with torch.cuda.stream(self._copy_stream):
+            st["data"].copy_(data, non_blocking=True)
+            for s_, t in zip(st["targets"], targets):
+                s_.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (data.data_ptr(), ev, st)
+
+    _copy_stream = None
+    _staged = None
+    _stage_in_use = None
+
+    def _take_staged(self, data):
+        """(staged data, staged targets) if `data` is the host tensor a prefetch() was started for, else None"""
+        st = self._staged
+        if st is None or st[0] != data.data_ptr() or data.is_cuda:
+            return None
+        torch.cuda.current_stream().wait_event(st[1])
+        self._staged = None
+        self._stage_in_use = st[2]
+        return st[2]["data"], st[2]["targets"]
+
+    def _release_stage(self):
+        if self._stage_in_use is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._stage_in_use["free"] = ev
+            self._stage_in_use = None
+
     def _graph_step(self, data, targets):
+        staged = self._take_staged(data)
+        if staged is not None:
+            data, targets = staged
         if data.data_ptr() != self._static_data.data_ptr():
             self._static_data.copy_(data, non_blocking=True)
         for s_, t in zip(self._static_targets, targets):
             if t.data_ptr() != s_.data_ptr():
                 s_.copy_(t, non_blocking=True)
+        self._release_stage()                 # the staged batch now lives in the graph's static inputs
         if self.fused_optimizer:
             self.optimizer.sync_hyper()       # learning-rate / momentum / weight-decay changes reach the replayed step
         self._graph.replay()

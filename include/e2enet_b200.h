@@ -94,9 +94,10 @@ typedef struct {
    * statistics pass over the conv output of ConvDropoutNormNonlin (unetpp_d.py:108-110). */
   float* stats;
   int32_t stats_ctot;
-  /* tcgen05 path, out_mode 0 only: the result is ADDED to what the destination already holds (bf16(fp32(old) +
-   * fp32 accumulator)): the gradient fan-in of an activation with several consumers (the fusion grid,
-   * unetpp_d.py:453-478) is summed in the data-gradient epilogue instead of a separate add pass */
+  /* tcgen05 path, out_mode 0 only: bit i set = the result is ADDED to what destination i already holds
+   * (bf16(fp32(old) + fp32 accumulator)); the other destinations are overwritten.  The gradient fan-in of an
+   * activation with several consumers (the fusion grid, unetpp_d.py:453-478) is summed in the data-gradient
+   * epilogue instead of a separate add pass */
   int32_t accumulate;
 } e2e_gemm_t;
 
@@ -129,11 +130,20 @@ typedef struct {
   const void* grad;                  /* device bf16 C8 on the iteration grid */
   int32_t grad_cb;
   int32_t Npad;                      /* multiple of 16, <= 8*grad_cb rounded up */
-  float* dwp;                        /* device fp32 [n_cent/2][n_taps][2][Npad][8] */
+  float* dwp;                        /* device fp32 [n_cent/2][n_taps][2][Npad][8] (may be null in direct mode) */
   int32_t impl;
+  /* direct mode (tcgen05 path only, see e2e_gather_wgrad_direct_ok): when grad_out is non-null the kernel adds its
+   * result straight into the gradient in the reference's PARAMETER layout, grad_out[rowoff[n] + centoff[e*8+j] +
+   * tapoff[t]] (the scatter of e2e_unpack_wgrad; the caller zeroes grad_out first), and dwp is not touched */
+  float* grad_out;
+  const int32_t* rowoff;             /* device, Npad entries (negative: padded column) */
+  const int32_t* centoff;            /* device, n_cent*8 entries (negative: padded channel) */
+  const int32_t* tapoff;             /* device, n_taps entries */
 } e2e_wgrad_t;
 
 int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream);
+/* 1 when e2e_gather_wgrad(p) runs on a tcgen05 kernel and therefore honours grad_out */
+int e2e_gather_wgrad_direct_ok(const e2e_wgrad_t* p);
 
 /*
  * wpacked[e/2][t][e%2][n][j] = bf16( w[rowoff[n] + centoff[e*8+j] + tapoff[t]] * (mask ? mask[same] : 1) )
@@ -254,11 +264,14 @@ int e2e_sgd_update(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t m
 /*
  * logits fp32 [B][C][V], target fp32 [B][V] (class index as float, like the reference's target[:, 0]):
  * stats[b][c] = {sum_v p, sum_v p*[y==c], #{y==c}} and *ce_sum = sum -log p[y] are ACCUMULATED (caller
- * zeroes them).  Replaces the softmax / one-hot / tp-fp-fn / log-softmax / nll passes of
+ * zeroes them) through per-block partials reduced in a fixed order -- no atomics, bit-reproducible: a one-ulp
+ * difference here is amplified by the bf16 backward pass into ~1 % differences of the deepest weight gradients.
+ * Replaces the softmax / one-hot / tp-fp-fn / log-softmax / nll passes of
  * e2enet/training/loss_functions/dice_loss.py:100-190,302-359 and crossentropy.py:4-11.
  */
+int e2e_softmax_stats_partial_count(int32_t B, int32_t C, int64_t V);      /* floats of scratch `partial` */
 int e2e_softmax_stats_fwd(const float* logits, const float* target, int32_t B, int32_t C, int64_t V,
-                          float* stats, float* ce_sum, void* stream);
+                          float* partial, float* stats, float* ce_sum, void* stream);
 /* dlogits = p_k (g_k - sum_j p_j g_j) + gce (p_k - [y==k]),  g_j = gsp[b][j] + gtp[b][j] [y==j]; gce: device scalar */
 int e2e_softmax_stats_bwd(const float* logits, const float* target, const float* gsp, const float* gtp,
                           const float* gce, int32_t B, int32_t C, int64_t V, float* dlogits, void* stream);

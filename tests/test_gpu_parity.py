@@ -537,6 +537,46 @@ def test_window_vs_reference_golden(dev, golden_dir):
     np.testing.assert_allclose(out[0].cpu().numpy(), ref, rtol=2e-4, atol=2e-6)
 
 
+def test_window_fold_ensemble_and_result_buffers(dev, golden_dir):
+    """predict_3D_ensemble = the fold loop of inference/predict.py:282-296 (mean of the folds' softmax) on one set of
+    device accumulators, mirrored (the 8 variants of a tile run as one batched forward); and the pooled pinned result
+    buffers never alias across calls (the reference's `softmax += predict(...)[1]` pattern)."""
+    g = np.load(os.path.join(golden_dir, "window.npz"))
+    net = _make_toy(dev)
+    x, patch = g["a_x"], (32, 48, 32)
+    args = (True, (0, 1, 2), True, 0.5, patch, None, True, "constant", {'constant_values': 0}, False, False, False)
+    folds = []
+    for k in range(3):
+        sd = {n: v.clone() for n, v in net.state_dict().items()}
+        sd["w"] = sd["w"] * (1.0 + 0.3 * k)
+        sd["b"] = sd["b"] - 0.1 * k
+        folds.append(sd)
+    keep = []
+    for sd in folds:                                  # the reference's loop: one predict_3D per fold, results kept
+        net.load_state_dict(sd)
+        keep.append(net.predict_3D(x, *args)[1])
+    ptrs = {a.__array_interface__['data'][0] for a in keep}
+    assert len(ptrs) == 3, "results of successive calls must not share memory while they are alive"
+    want = (keep[0] + keep[1] + keep[2]) / 3
+    seg, prob = net.predict_3D_ensemble(x, folds, *args)
+    np.testing.assert_allclose(prob, want, rtol=2e-4, atol=2e-6)
+    assert (seg == want.argmax(0)).mean() >= 0.999
+    assert net._ensemble_params is None
+    for n, v in net.state_dict().items():
+        assert torch.equal(v.cpu(), folds[-1][n].cpu())
+    # reference semantics per tile batch are unchanged by the (tile, mirror) batching: tile_batch 1 vs 8
+    net.tile_batch = 1
+    p1 = net.predict_3D(x, *args)[1]
+    net.tile_batch = 8
+    p8 = net.predict_3D(x, *args)[1]
+    np.testing.assert_allclose(p1, p8, rtol=1e-5, atol=1e-7)
+    del keep, p1, p8                                  # released buffers are reused (no unbounded pinned growth)
+    n_before = sum(len(v) for v in net._pinned_pool.values())
+    for _ in range(3):
+        net.predict_3D(x, *args)
+    assert sum(len(v) for v in net._pinned_pool.values()) <= n_before
+
+
 def test_window_steps_known_answers(dev):
     from e2enet_medical_b200.network_architecture.neural_network import SegmentationNetwork as S
     f = S._compute_steps_for_sliding_window
@@ -720,6 +760,32 @@ def test_fused_sgd_matches_torch_clip_sgd_mask(dev):
         assert torch.equal(p.detach(), s_)
 
 
+def test_forward_backward_is_reproducible(dev):
+    """two forward + backward passes of the same network on the same batch: every activation gradient chain is
+    atomics-free (fused loss statistics, InstanceNorm reductions, fused epilogue statistics, gradient fan-in), so the
+    InstanceNorm parameter gradients are BIT-identical; only the split-K flush of the weight-gradient GEMMs adds
+    with fp32 atomics (order-dependent in the last bits)."""
+    from e2enet_medical_b200.training import POOLS, TrainStep, synthetic_batch
+    pools, patch = POOLS["btcv"], (32, 96, 96)          # deepest pool window does not tile its grid (2x3x3): unfused pool path
+    random.seed(0)
+    ts = TrainStep(1, 14, pools, patch, 0.2, 0.5, 1200, dev, 1, seed=0, fused_optimizer=False)
+    data, targets = synthetic_batch(2, 1, 14, patch, pools, seed=1)
+    x, tg = data.to(dev), [t.to(dev) for t in targets]
+    res = []
+    for _ in range(2):
+        ts.optimizer.zero_grad()
+        l = ts.loss(ts.network(x), tg)
+        l.backward()
+        res.append((float(l), OrderedDict((k, p.grad.detach().clone()) for k, p in ts.network.named_parameters())))
+    assert res[0][0] == res[1][0]
+    for k in res[0][1]:
+        a_, b_ = res[0][1][k], res[1][1][k]
+        if "instnorm" in k:
+            assert torch.equal(a_, b_), k
+        elif not k.endswith("conv.bias"):
+            assert rel2(a_, b_) < 1e-5, (k, rel2(a_, b_))
+
+
 def test_train_step_fused_optimizer_matches_stock_torch_loop(dev):
     """TrainStep with the fused optimizer + gradient arena vs the same iteration with stock torch SGD / clip_grad_norm_ /
     Masking.apply_mask: same losses and weights after 3 steps (identical kernels elsewhere, so only the optimizer's
@@ -741,9 +807,9 @@ def test_train_step_fused_optimizer_matches_stock_torch_loop(dev):
     assert all(p.grad.data_ptr() == ts0.arena.view(p).data_ptr() for p in ts0.network.parameters())
     # after ONE step both runs applied their optimizer to bit-identical gradients: only its fp32 rounding differs;
     # later steps amplify that through bf16 re-packing of the weights, so only the losses are compared there
-    assert l0[0] == l1[0]
+    assert l0[0] == l1[0]                      # forward + fused loss are bit-reproducible (no atomics)
     for k in w0:
         if not k.endswith("conv.bias"):
-            assert rel2(w0[k], w1[k]) < 1e-5, (k, rel2(w0[k], w1[k]))
+            assert rel2(w0[k], w1[k]) < 1e-4, (k, rel2(w0[k], w1[k]))
     for a_, b_ in zip(l0, l1):
         assert abs(a_ - b_) < 5e-3 * abs(b_), (l0, l1)

@@ -60,6 +60,14 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     (F.conv3d(onet.shift_depth(torch.cat(xs, 1)), wc, None, padding=(0, 1, 1)) * g).sum().backward()
     assert rel(gw1, wc.grad) < 2e-4, rel(gw1, wc.grad)
     assert rel(gw1, gw0) < 2e-4
+    # direct mode: the split-K flush adds into the parameter layout (no packed scratch / unpack pass)
+    ops.CONFIG["wgrad_direct"] = True
+    try:
+        gw2 = ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (D, H, W), B, g8, tuple(w.shape), 1)
+    finally:
+        ops.CONFIG["wgrad_direct"] = False
+    torch.cuda.synchronize()
+    assert rel(gw2, gw1) < 1e-5, rel(gw2, gw1)
     # data gradient variants (one per shift group) through the same kernel
     (ref * g).sum().backward()
     douts = [torch.full_like(s, float("nan")) for s in xs8]
