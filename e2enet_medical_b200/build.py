@@ -20,7 +20,7 @@ INCLUDE = os.path.join(ROOT, "include")
 BUILD = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libe2enet_b200.so")
 
-SOURCES = ["api.cu", "gather_gemm.cu", "conv_tc.cu", "elementwise.cu", "masking.cu", "window.cu", "loss.cu", "optim.cu"]
+SOURCES = ["api.cu", "gather_gemm.cu", "conv_tc.cu", "elementwise.cu", "masking.cu", "window.cu", "loss.cu", "optim.cu", "export.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-DE2E_B200=1", "-I" + INCLUDE,
               "-Xptxas", "-v"]

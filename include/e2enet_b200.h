@@ -299,6 +299,17 @@ int e2e_window_head_accumulate(const void* x, int32_t Cb, const float* w, int32_
 int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
                         int64_t* seg, void* stream);
 
+/* ---------------------------------------------------------------- export: resample + argmax */
+/*
+ * probs fp32 [C][X][Y][Z] -> resampled to (Xo, Yo, Zo) with the pixel-centre map in = (out + 0.5) * n_in / n_out - 0.5
+ * and edge clamping, per axis nearest (mode 0 = interpolation order 0) or linear (mode 1 = order 1); writes the
+ * resampled probabilities (out_probs, may be null) and / or their arg-max over classes as uint8 labels (first
+ * maximum wins, may be null).  Replaces resample_data_or_seg(is_seg=False) + argmax(0) of
+ * e2enet/inference/segmentation_export.py:84-115 / e2enet/preprocessing/preprocessing.py:113-202.
+ */
+int e2e_resample_argmax(const float* probs, int32_t C, int32_t X, int32_t Y, int32_t Z, int32_t Xo, int32_t Yo, int32_t Zo,
+                        int32_t mode_x, int32_t mode_y, int32_t mode_z, float* out_probs, uint8_t* labels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
