@@ -576,9 +576,13 @@ def inference_leg(dev, world, rank, args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt, dev_ms = float(t[0]), float(t[1])
     nvox = float(np.prod(vol_shape))
+    gather_how = getattr(net, "_last_gather", None)
+    seg_bytes = int(seg.nbytes + probs.nbytes) if seg is not None else 0
+    del seg, probs
+    net.release_shared_result_segments()
     return {"metric": "inference voxels/s", "value": nvox / (dev_ms / 1e3), "unit": "voxels/s",
             "e2e": {"value": nvox / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(net._last_h2d_bytes),
-                    "d2h_bytes_per_step": int(seg.nbytes + probs.nbytes) if seg is not None else 0},
+                    "d2h_bytes_per_step": seg_bytes},
             "ms_per_volume": dev_ms, "e2e_ms_per_volume": dt * 1e3, "tiles": n_tiles, "rank0_phases": phases,
             "rank0_host_phases_diagnostic_pass": host_phases,
             "tiles_per_s": n_tiles / (dev_ms / 1e3),
@@ -589,7 +593,8 @@ def inference_leg(dev, world, rank, args):
                                    "buffers that never alias across calls" % vol_shape, "tiles_sharded_over": world,
                        "exchange": "none" if world == 1 else
                        "slab ownership: every rank uploads only its x-planes, NCCL point-to-point exchange of the overlap "
-                       "planes between neighbouring ranks, finalised slabs gathered GPU->GPU to rank 0 (labels as uint8)"}}
+                       "planes between neighbouring ranks, finalised slabs delivered to rank 0's result arrays: " +
+                       str(gather_how)}}
 
 
 def main():

@@ -116,6 +116,9 @@ SIGNATURES = {
     "e2e_in_apply": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP]),
     "e2e_in_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _I32, _VP, _VP, _VP, _VP,
                              _VP, _VP]),
+    "e2e_in_bwd_scratch_floats": (C.c_int64, [_I32, _I32, _I64]),
+    "e2e_in_bwd_fused": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                   _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "e2e_in_apply_pool": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP,
                                     _VP, _VP]),
     "e2e_in_bwd_pool": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32,

@@ -518,6 +518,199 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __
     block_reduce_store<8>(acc, partial + ((long long)plane * nchunk + chunk) * 8);
 }
 
+// ------------------------------------------------------------------ plane-resident InstanceNorm backward
+// The two-kernel backward above reads dy and raw twice from HBM (5 tensor passes).  Here ONE kernel walks the (b, cb)
+// planes; a group of Gs co-resident CTAs owns a plane at a time: phase A reduces sum dz / sum dz*xhat over the plane
+// (dy and raw stream in from HBM and stay in the 126 MB L2: a full-resolution plane is 2 x 26 MB), a counter barrier
+// among the group's CTAs, every CTA forms the totals from the group's partials in a fixed order (deterministic), and
+// phase C re-reads ITS OWN slice -- now L2 hits -- to write draw: 3 HBM passes (dy, raw, draw) instead of 5.
+// Groups are sized so that the planes in flight fit the L2; all CTAs are co-resident (grid = 2 per SM), so the
+// spin-wait cannot deadlock.  POOL folds the pooled gradient in exactly like in_bwd_pool_kernel.
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool POOL, int KD, int KH, int KW>
+__global__ void __launch_bounds__(EW_THREADS, 2)
+in_bwd_plane_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ dyp, const uint2* __restrict__ amax,
+                    const uint4* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float slope, int Cb, PoolGeo g, long long V,
+                    int planes, int Gs, int ngroups, float* __restrict__ partial, float* __restrict__ partial2,
+                    int* __restrict__ counters, float* __restrict__ sums_out, uint4* __restrict__ draw) {
+  __shared__ float s_sums[16];
+  const int group = blockIdx.x / Gs, c = blockIdx.x - group * Gs;
+  if (group >= ngroups) return;
+  constexpr int n = KD * KH * KW;                       // window voxels per pooled voxel (1 when !POOL)
+  const long long Vw = POOL ? V / n : V;                // work items per plane: pooled voxels or voxels
+  const long long per = (Vw + Gs - 1) / Gs;
+  const long long lo = (long long)c * per, hi = min(Vw, lo + per);
+  const float invV = 1.0f / (float)V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int plane = group; plane < planes; plane += ngroups) {
+    const int cb = plane % Cb;
+    float mu[8], rs[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
+      ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
+    }
+    const uint4* xb = raw + (long long)plane * V;
+    const uint4* gb = dy ? dy + (long long)plane * V : nullptr;
+    uint4* ob = draw + (long long)plane * V;
+    float m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m1[j] = 0.f; m2[j] = 0.f; }
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float acc[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+      if (!POOL) {
+        for (long long v0 = lo + threadIdx.x; v0 < hi; v0 += UNR * EW_THREADS) {
+          uint4 xr[UNR], gr[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * EW_THREADS;
+            if (v < hi) { xr[u] = ld_nc_16(xb + v); gr[u] = ld_nc_16(gb + v); }
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const long long v = v0 + u * EW_THREADS;
+            if (v >= hi) break;
+            float x[8], gv[8], o[8];
+            unpack8(xr[u], x);
+            unpack8(gr[u], gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xh = (x[j] - mu[j]) * rs[j];
+              const float z = xh * ga[j] + be[j];
+              const float dz = z > 0.f ? gv[j] : gv[j] * slope;
+              if (pass == 0) { acc[j] += dz; acc[8 + j] += dz * xh; }
+              else o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+            }
+            if (pass) {
+              const uint4 pk = pack8(o);
+              ob[v] = pk;
+              float ro[8];
+              unpack8(pk, ro);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+            }
+          }
+        }
+      } else {
+        for (long long vo = lo + threadIdx.x; vo < hi; vo += EW_THREADS) {
+          int od, oh, ow;
+          pool_decode(vo, g, od, oh, ow);
+          const long long po = (long long)plane * Vw + vo;
+          const uint2 am = amax[po];
+          float gp[8];
+          unpack8(ld_nc_16(dyp + po), gp);
+          uint4 xr[n], gr[n];
+          long long src[n];
+#pragma unroll
+          for (int a = 0; a < KD; ++a)
+#pragma unroll
+            for (int b = 0; b < KH; ++b)
+#pragma unroll
+              for (int cc = 0; cc < KW; ++cc) {
+                const int i = (a * KH + b) * KW + cc;
+                src[i] = ((long long)(od * KD + a) * g.H + oh * KH + b) * g.W + ow * KW + cc;
+                xr[i] = ld_nc_16(xb + src[i]);
+                gr[i] = gb ? ld_nc_16(gb + src[i]) : make_uint4(0, 0, 0, 0);
+              }
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            float x[8], gv[8], o[8];
+            unpack8(xr[i], x);
+            unpack8(gr[i], gv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = ((j < 4 ? am.x : am.y) >> ((j & 3) * 8)) & 0xffu;
+              const float gt = gv[j] + (a == (uint32_t)i ? gp[j] : 0.f);
+              const float xh = (x[j] - mu[j]) * rs[j];
+              const float z = xh * ga[j] + be[j];
+              const float dz = z > 0.f ? gt : gt * slope;
+              if (pass == 0) { acc[j] += dz; acc[8 + j] += dz * xh; }
+              else o[j] = rs[j] * ga[j] * (dz - m1[j] - xh * m2[j]);
+            }
+            if (pass) {
+              const uint4 pk = pack8(o);
+              ob[src[i]] = pk;
+              float ro[8];
+              unpack8(pk, ro);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += ro[j];
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+        block_reduce_store<16>(acc, partial + ((long long)plane * Gs + c) * 16);
+        // group barrier: publish this CTA's partial, wait until all Gs CTAs of the group have published theirs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(&counters[plane], 1);
+          while (ld_acquire_i32(&counters[plane]) < Gs) __nanosleep(64);
+        }
+        __syncthreads();
+        // totals of the plane, fixed order: warp w forms values w and w + 8 (fp64, lanes stride over the group's CTAs)
+        for (int k = warp; k < 16; k += EW_THREADS / 32) {
+          double sm = 0.0;
+          for (int i = lane; i < Gs; i += 32) sm += (double)__ldcg(partial + ((long long)plane * Gs + i) * 16 + k);
+          sm = warp_sum_d(sm);
+          if (lane == 0) s_sums[k] = (float)sm;
+        }
+        __syncthreads();
+        if (c == 0 && threadIdx.x < 16) sums_out[plane * 16 + threadIdx.x] = s_sums[threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { m1[j] = s_sums[j] * invV; m2[j] = s_sums[8 + j] * invV; }
+        __syncthreads();
+      } else {
+        block_reduce_store<8>(acc, partial2 + ((long long)plane * Gs + c) * 8);
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// geometry of the plane-resident backward: CTAs per group, groups, grid
+struct PlaneGeo { int grid, Gs, ngroups; };
+// CTAs of in_bwd_plane_kernel that are guaranteed to be resident at the same time on the current device (the
+// kernel's group barrier spins, so the grid must never exceed this)
+static int plane_coresident_ctas() {
+  static int cached[E2E_MAX_DEVICES] = {0};
+  const int dev = e2e_cur_device();
+  if (!cached[dev]) {
+    int occ = 2, o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_plane_kernel<false, 1, 1, 1>, EW_THREADS, 0) == cudaSuccess && o < occ) occ = o;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_plane_kernel<true, 1, 2, 2>, EW_THREADS, 0) == cudaSuccess && o < occ) occ = o;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, in_bwd_plane_kernel<true, 2, 2, 2>, EW_THREADS, 0) == cudaSuccess && o < occ) occ = o;
+    if (occ < 1) occ = 1;
+    cached[dev] = occ * e2e_num_sms();
+  }
+  return cached[dev];
+}
+static PlaneGeo plane_geometry(int planes, long long V) {
+  PlaneGeo pg;
+  const int G = plane_coresident_ctas();                            // co-resident: __launch_bounds__(256, 2)
+  const long long plane_bytes = V * 16 * 2;                         // dy + raw of one plane
+  long long ng = (80ll << 20) / (plane_bytes > 0 ? plane_bytes : 1);   // planes in flight that fit the L2 comfortably
+  if (ng < 1) ng = 1;
+  if (ng > planes) ng = planes;
+  long long gs = G / ng;
+  const long long max_useful = (V + 511) / 512;                     // at least ~512 voxels per CTA
+  if (gs > max_useful) gs = max_useful;
+  if (gs < 1) gs = 1;
+  ng = G / gs;
+  if (ng > planes) ng = planes;
+  pg.Gs = (int)gs; pg.ngroups = (int)ng; pg.grid = (int)(gs * ng);
+  return pg;
+}
+
 // ------------------------------------------------------------------ MaxPool3d, kernel == stride
 __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                                  uint2* __restrict__ amax, int BCb, int D, int H, int W,
@@ -711,6 +904,52 @@ extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, co
                                                    slope, Cb, V, nchunk, (uint4*)draw, partial);
   E2E_LAUNCHED("in_bwd_apply");
   in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  E2E_LAUNCHED("in_bwd_param");
+  return E2E_OK;
+}
+
+extern "C" int64_t e2e_in_bwd_scratch_floats(int32_t B, int32_t Cb, int64_t V) {
+  if (B <= 0 || Cb <= 0 || V <= 0) return 0;
+  const int planes = B * Cb;
+  const PlaneGeo pg = plane_geometry(planes, V);
+  return (int64_t)planes * pg.Gs * 24 + planes + 64;               // partial (16) + partial2 (8) per CTA, counters
+}
+
+// dyp / argmax null: plain backward; otherwise the pooled gradient is folded in (window kd,kh,kw must be (1,2,2) or
+// (2,2,2) and divide the grid).  scratch: e2e_in_bwd_scratch_floats() floats.
+extern "C" int e2e_in_bwd_fused(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
+                                const float* rstd, const float* gamma, const float* beta, float slope, int32_t B, int32_t Cb,
+                                int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* scratch,
+                                float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  E2E_ARG(raw && mean && rstd && gamma && beta && scratch && sums && draw && dgamma && dbeta, "in_bwd_fused: null pointer");
+  E2E_ARG(B > 0 && Cb > 0 && D > 0 && H > 0 && W > 0, "in_bwd_fused: bad sizes");
+  const bool pool = dyp != nullptr;
+  E2E_ARG(pool || dy != nullptr, "in_bwd_fused: dy is required without a pooled gradient");
+  E2E_ARG(!pool || argmax != nullptr, "in_bwd_fused: pooled gradient without its arg-max");
+  const bool k122 = kd == 1 && kh == 2 && kw == 2, k222 = kd == 2 && kh == 2 && kw == 2;
+  if (pool && !((k122 || k222) && D % kd == 0 && H % kh == 0 && W % kw == 0)) {
+    e2e_set_error("in_bwd_fused: pool window (%d,%d,%d) is not instantiated for grid (%d,%d,%d)", kd, kh, kw, D, H, W);
+    return E2E_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int planes = B * Cb;
+  const long long V = (long long)D * H * W;
+  const PlaneGeo pg = plane_geometry(planes, V);
+  float* partial = scratch;
+  float* partial2 = scratch + (size_t)planes * pg.Gs * 16;
+  int* counters = reinterpret_cast<int*>(scratch + (size_t)planes * pg.Gs * 24);
+  E2E_CUDA(cudaMemsetAsync(counters, 0, sizeof(int) * planes, st));
+  const PoolGeo g{D, H, W, pool ? kd : 1, pool ? kh : 1, pool ? kw : 1};
+#define E2E_PLANE(POOL, A, Bq, Cq)                                                                                         \
+  in_bwd_plane_kernel<POOL, A, Bq, Cq><<<pg.grid, EW_THREADS, 0, st>>>(                                                    \
+      (const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, V, \
+      planes, pg.Gs, pg.ngroups, partial, partial2, counters, sums, (uint4*)draw)
+  if (!pool) E2E_PLANE(false, 1, 1, 1);
+  else if (k122) E2E_PLANE(true, 1, 2, 2);
+  else E2E_PLANE(true, 2, 2, 2);
+#undef E2E_PLANE
+  E2E_LAUNCHED("in_bwd_plane");
+  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial2, B, Cb, pg.Gs, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;
 }

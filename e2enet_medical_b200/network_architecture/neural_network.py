@@ -571,6 +571,28 @@ class SegmentationNetwork(NeuralNetwork):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         return seg_ if int(flag) == 1 else None
 
+    def release_shared_result_segments(self):
+        """unmaps (and, on the rank that created them, unlinks) the shared result segments of result_on="gather".
+        Arrays returned by earlier predict_3D calls on rank 0 become invalid: copy what you keep first."""
+        for segs in self.__dict__.get("_shm_pool", {}).values():
+            for s_ in segs:
+                try:
+                    torch.cuda.cudart().cudaHostUnregister(s_["probs"].data_ptr())
+                except Exception:
+                    pass
+                name, shm = s_["name"], s_["shm"]
+                s_["probs"] = s_["seg"] = None
+                try:
+                    shm.close()
+                except Exception:
+                    pass
+                if name.lstrip("/").startswith("e2e_b200_%d_" % __import__("os").getpid()):
+                    try:
+                        shm.unlink()
+                    except Exception:
+                        pass
+        self.__dict__["_shm_pool"] = {}
+
     def _gather_slabs(self, seg, probs, bx, shard, data_shape, slicer, regions_class_order, ev0, ev1, verbose):
         """result_on="gather": every rank owns the finalised labels / probabilities of its x-slab on its GPU; they
         travel GPU -> GPU (NCCL point-to-point over NVLink / NVSwitch, labels as uint8) to rank 0, which assembles

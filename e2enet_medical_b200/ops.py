@@ -17,11 +17,12 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
-CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True, "wgrad_direct": False}
+CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True, "wgrad_direct": False,
+          "in_bwd_plane": False}
 # A/B switches for measurements (tools/, bench.py): E2E_FUSE_STATS=0 / E2E_FUSE_FANIN=0 / E2E_FUSE_POOL=0 / E2E_STACK3=0
 import os as _os
 for _k, _e in (("fuse_stats", "E2E_FUSE_STATS"), ("fuse_fanin", "E2E_FUSE_FANIN"), ("fuse_pool", "E2E_FUSE_POOL"),
-               ("stack3", "E2E_STACK3"), ("wgrad_direct", "E2E_WGRAD_DIRECT")):
+               ("stack3", "E2E_STACK3"), ("wgrad_direct", "E2E_WGRAD_DIRECT"), ("in_bwd_plane", "E2E_IN_BWD_PLANE")):
     if _os.environ.get(_e) is not None:
         CONFIG[_k] = _os.environ[_e] not in ("0", "false", "False")
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
@@ -555,7 +556,19 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dgamma, dbeta = small(gamma), small(beta)
         dbias = small(bias, ctx.needs_input_grad[3])
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
-        if am is not None and dyp is not None:
+        pooled = am is not None and dyp is not None
+        if CONFIG.get("in_bwd_plane", False):
+            # (A/B switch, default off: measured 0.5 ms SLOWER per step -- the per-plane group barriers cost more than the
+            # L2 hits save) plane-resident backward: one kernel, dy / raw are read once from HBM, the second read hits L2
+            if dy is None and not pooled:
+                dy = torch.zeros_like(raw)
+            kd, kh, kw = ctx.pool_k if pooled else (1, 1, 1)
+            scratch = torch.empty(int(lib.e2e_in_bwd_scratch_floats(B, Cb, V)), dtype=torch.float32, device=dev)
+            _lib.check(lib.e2e_in_bwd_fused(_p(dy), _p(dyp.contiguous()) if pooled else _p(None), _p(am) if pooled else _p(None),
+                                            _p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), ctx.slope, B, Cb, Do, Ho, Wo, kd, kh,
+                                            kw, _p(scratch), _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
+                                            _lib.stream_ptr()), "in_bwd_fused")
+        elif pooled:
             kd, kh, kw = ctx.pool_k
             _lib.check(lib.e2e_in_bwd_pool(_p(dy), _p(dyp.contiguous()), _p(am), _p(raw), _p(mean), _p(rstd), _p(g32),
                                            _p(b32), ctx.slope, B, Cb, Do, Ho, Wo, kd, kh, kw, _p(partial), nch, _p(sums),
@@ -566,7 +579,6 @@ class ShiftConvINLReLU(torch.autograd.Function):
             _lib.check(lib.e2e_in_bwd(_p(dy), _p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), ctx.slope, B, Cb, V,
                                       _p(partial), nch, _p(sums), _p(draw), _p(dgamma), _p(dbeta), _p(dbias),
                                       _lib.stream_ptr()), "in_bwd")
-        # weight gradient (dense, also at masked positions: SURVEY H3)
         for a, prm in slots.values():
             a.mark_ready(prm)
         gw = None

@@ -205,6 +205,16 @@ int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* argmax, cons
                     int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* partial, int32_t nchunk,
                     float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
 
+/* plane-resident backward (one kernel, 3 HBM passes instead of 5): a group of co-resident CTAs owns one (b, cb) plane
+ * at a time, reduces sum dz / sum dz*xhat, synchronises on a counter, and re-reads its slice of dy / raw from the L2
+ * to write draw.  dyp / argmax null = plain backward, else the pooled gradient is folded in (window (1,2,2) or
+ * (2,2,2) dividing the grid).  scratch: e2e_in_bwd_scratch_floats(B, Cb, D*H*W) floats; results as e2e_in_bwd. */
+int64_t e2e_in_bwd_scratch_floats(int32_t B, int32_t Cb, int64_t V);
+int e2e_in_bwd_fused(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
+                     const float* rstd, const float* gamma, const float* beta, float slope, int32_t B, int32_t Cb,
+                     int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* scratch, float* sums,
+                     void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
+
 /* ---------------------------------------------------------------- MaxPool3d (kernel == stride) */
 int e2e_maxpool_fwd(const void* x, void* y, uint8_t* argmax, int32_t BCb, int32_t D, int32_t H, int32_t W,
                     int32_t kd, int32_t kh, int32_t kw, void* stream);
