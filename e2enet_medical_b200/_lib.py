@@ -86,7 +86,8 @@ class WgradParams(C.Structure):
 class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("mask", C.c_void_p), ("rowoff", C.c_void_p), ("centoff", C.c_void_p),
                 ("tapoff", C.c_void_p), ("n_cent", C.c_int32), ("n_taps", C.c_int32), ("Npad", C.c_int32),
-                ("pad_", C.c_int32), ("out", C.c_void_p), ("item_begin", C.c_int64)]
+                ("pad_", C.c_int32), ("out", C.c_void_p), ("item_begin", C.c_int64), ("emask", C.c_void_p),
+                ("rclass", C.c_void_p)]
 
 
 class SgdTensor(C.Structure):
@@ -106,7 +107,7 @@ SIGNATURES = {
     "e2e_in_stats_final": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _F, _VP, _VP, _VP]),
     "e2e_gather_wgrad": (C.c_int, [C.POINTER(WgradParams), _VP]),
     "e2e_gather_wgrad_direct_ok": (C.c_int, [C.POINTER(WgradParams)]),
-    "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_pack_weights": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_pack_weights_multi": (C.c_int, [_VP, _I32, _I64, _VP]),
     "e2e_unpack_wgrad": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _VP, _VP]),
     "e2e_nc_to_c8": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP]),

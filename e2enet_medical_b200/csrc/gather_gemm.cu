@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(THREADS, 1) gather_wgrad_kernel(const __grid_c
 // ------------------------------------------------------------------------------------ pack / unpack
 __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __restrict__ mask,
                                     const int32_t* __restrict__ rowoff, const int32_t* __restrict__ centoff,
-                                    const int32_t* __restrict__ tapoff, int n_cent, int n_taps, int Npad,
+                                    const int32_t* __restrict__ tapoff, const int32_t* __restrict__ emask,
+                                    const int32_t* __restrict__ rclass, int n_cent, int n_taps, int Npad,
                                     bf16* __restrict__ out) {
   // one thread per (ks, half, n): writes 8 bf16 (16 B)
   const long long total = (long long)n_cent * n_taps * Npad;
@@ -360,7 +361,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
     const int ks = (int)(sl >> 1);
     const int pr = ks / n_taps, t = ks - pr * n_taps;
     const int e = 2 * pr + hf;
-    const int ro = rowoff[n], to = tapoff[t];
+    int ro = rowoff[n];
+    const int to = tapoff[t];
+    if (emask && !((emask[e] >> (rclass ? rclass[n] : 0)) & 1)) ro = -1;     // entry does not feed this column class
     uint32_t o[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -399,7 +402,9 @@ __global__ void pack_weights_multi_kernel(const e2e_pack_job_t* __restrict__ job
     const int ks = (int)(sl >> 1);
     const int pr = ks / jb.n_taps, t = ks - pr * jb.n_taps;
     const int e = 2 * pr + hf;
-    const int ro = jb.rowoff[n], to = jb.tapoff[t];
+    int ro = jb.rowoff[n];
+    const int to = jb.tapoff[t];
+    if (jb.emask && !((jb.emask[e] >> (jb.rclass ? jb.rclass[n] : 0)) & 1)) ro = -1;
     uint32_t o[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -582,15 +587,15 @@ extern "C" int e2e_gather_wgrad(const e2e_wgrad_t* p, void* stream) {
 }
 
 extern "C" int e2e_pack_weights(const float* w, const float* mask, const int32_t* rowoff, const int32_t* centoff,
-                                const int32_t* tapoff, int32_t n_cent, int32_t n_taps, int32_t Npad, void* wpacked,
-                                void* stream) {
+                                const int32_t* tapoff, const int32_t* emask, const int32_t* rclass, int32_t n_cent,
+                                int32_t n_taps, int32_t Npad, void* wpacked, void* stream) {
   E2E_ARG(w && rowoff && centoff && tapoff && wpacked, "pack_weights: null pointer");
   const long long total = (long long)n_cent * n_taps * Npad;
   if (total <= 0) return E2E_OK;
   int blocks = (int)((total + 255) / 256);
   if (blocks > e2e_num_sms() * 16) blocks = e2e_num_sms() * 16;
   pack_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, mask, rowoff, centoff, tapoff, n_cent, n_taps, Npad, reinterpret_cast<bf16*>(wpacked));
+      w, mask, rowoff, centoff, tapoff, emask, rclass, n_cent, n_taps, Npad, reinterpret_cast<bf16*>(wpacked));
   E2E_LAUNCHED("pack_weights");
   return E2E_OK;
 }

@@ -43,7 +43,7 @@ def _plan_flops(plan: GemmPlan, M: int) -> float:
         import numpy as np
         plan._dev["_kn"] = (int((plan.centoff >= 0).sum()) * plan.n_taps, int((plan.rowoff >= 0).sum()))
     k, n = plan._dev["_kn"]
-    return 2.0 * M * k * n
+    return 2.0 * M * k * n * plan.useful          # useful: fraction of (entry, column) pairs that are not masked out
 
 
 class _Timed(object):
@@ -196,6 +196,8 @@ def _repack_all(device):
             j.rowoff, j.centoff, j.tapoff = (e.tables[k].data_ptr() for k in ("rowoff", "centoff", "tapoff"))
             j.n_cent, j.n_taps, j.Npad = e.plan.n_cent, e.plan.n_taps, e.plan.Npad
             j.out, j.item_begin = e.out.data_ptr(), total
+            j.emask = e.tables["emask"].data_ptr() if "emask" in e.tables else 0
+            j.rclass = e.tables["rclass"].data_ptr() if "rclass" in e.tables else 0
             total += e.plan.n_cent * e.plan.n_taps * e.plan.Npad
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         reg["table"], reg["sig"], reg["total"] = host.to(device), sig, total
@@ -238,7 +240,8 @@ def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tens
         assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == w.shape
     out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
     _lib.check(lib.e2e_pack_weights(_p(w), _p(mask), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]),
-                                    plan.n_cent, plan.n_taps, plan.Npad, _p(out), _lib.stream_ptr()), "pack_weights")
+                                    _p(dev.get("emask")), _p(dev.get("rclass")), plan.n_cent, plan.n_taps, plan.Npad,
+                                    _p(out), _lib.stream_ptr()), "pack_weights")
     e = _PackEntry()
     e.tables, e.plan, e.wref, e.mask, e.out, e.key, e.dead = dev, plan, weakref.ref(weight), mask, out, key, False
     dev["_wpe"] = e

@@ -49,6 +49,9 @@ class GemmPlan:
     iter_extra: Tuple[int, int, int] = (0, 0, 0)
     halo: bool = False          # stride-1 3x3 halo form (tcgen05 kernel eligible)
     col_bounds: int = 7         # bit 0/1/2: destination depth / row / column of a column block may leave the grid
+    emask: Optional[np.ndarray] = None     # (n_cent,) bitmask of column classes an entry feeds (None: all)
+    rclass: Optional[np.ndarray] = None    # (Npad,) column class 0..31 (None: 0)
+    useful: float = 1.0         # fraction of the (entry, column) weight pairs that are not masked out (FLOP accounting)
     _dev: Dict = field(default_factory=dict, repr=False)
 
     @property
@@ -71,6 +74,9 @@ class GemmPlan:
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
             self._dev[key] = dict(cents=t(self.cents), taps=t(self.taps), cols=t(self.cols), rowoff=t(self.rowoff),
                                   centoff=t(self.centoff), tapoff=t(self.tapoff))
+            if self.emask is not None:
+                self._dev[key]["emask"] = t(self.emask)
+                self._dev[key]["rclass"] = t(self.rclass if self.rclass is not None else np.zeros(self.Npad))
         return self._dev[key]
 
 
@@ -80,8 +86,12 @@ def _pad_even(cents: List[List[int]], centoff: List[List[int]]):
         centoff.append([-1] * 8)
 
 
-def _finish(cents, centoff, taps, tapoff, cols, rowoff, **kw) -> GemmPlan:
+def _finish(cents, centoff, taps, tapoff, cols, rowoff, emask=None, rclass=None, **kw) -> GemmPlan:
     Npad = ceil_to(max(len(rowoff), 1), 16)
+    if emask is not None:
+        emask = np.asarray(list(emask) + [0] * (len(cents) - len(emask)), np.int32)      # padded entries feed nothing
+        rclass = np.asarray(list(rclass) + [0] * (Npad - len(rclass)), np.int32)
+        kw = dict(kw, emask=emask, rclass=rclass)
     rowoff = list(rowoff) + [-1] * (Npad - len(rowoff))
     cols = list(cols)
     while len(cols) < Npad // 8:
@@ -232,7 +242,42 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
                                     istride=(1, 1, 1), ivoff=(smin, 0, 0), ostride=(1, 1, 1),
                                     iter_extra=(smax - smin, 0, 0), halo=True, col_bounds=1))
         return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, wgrad, fwd3, variants, False)
-    # strided: one point-form GEMM per (H, W) output parity; its K entries are the taps that reach
+    if shh == 2 and sww == 2:
+        # stride 2 in H and W: ALL FOUR output parities in ONE point-form GEMM.  dx[2u + p] (p = parity per axis)
+        # receives tap k = 1 (p = 0) from d(raw)[u], and taps k = 2 / k = 0 (p = 1) from d(raw)[u] / d(raw)[u + 1].
+        # K entries = (offset class per axis: 0 reads u, 1 reads u + 1) x Cout blocks; the weight of (class, parity)
+        # is tap k = ke + p with ke = 1 (class 0) or -1 (class 1), and class 1 does not reach parity 0: those
+        # (entry, column) pairs are masked to zero at pack time (emask / rclass).  Columns = (ph, pw, source block,
+        # shift group) stored at (depth o*sd - s, row 2u + ph, column 2w + pw): the two W parities of a voxel pair are
+        # written by the same CTA back to back, so every 32-byte sector is completed by one kernel (four separate
+        # parity launches wrote half sectors: measured 3.7x the algorithmic DRAM traffic) and d(raw) is read once.
+        vc, vo, em = [], [], []
+        for ch_ in (0, 1):
+            for cw_ in (0, 1):
+                keh, kew = (1 if ch_ == 0 else -1), (1 if cw_ == 0 else -1)
+                classes = sum(1 << (ph * 2 + pw) for ph in (0, 1) for pw in (0, 1) if ph >= ch_ and pw >= cw_)
+                for ce, co in zip(g_cents, g_centoff):
+                    vc.append([0, ce[1], 0, ch_, cw_])
+                    vo.append([v + (keh + 1) * 3 + (kew + 1) for v in co])      # kept >= 0: negative = padded channel;
+                    em.append(classes)                                          # the -4 lives in tapoff below
+        _pad_even(vc, vo)
+        pcols, prow, pcls = [], [], []
+        for ph in (0, 1):
+            for pw in (0, 1):
+                for (i, blk, m, s_), r in zip(ucols, urow):
+                    pcols.append([i, blk, m, -s_, ph, pw])
+                    prow.append([(v + ph * 3 + pw) if v >= 0 else -1 for v in r])
+                    pcls.append(ph * 2 + pw)
+        for a, b in _col_chunks(len(pcols)):
+            rr = [v for r in prow[a:b] for v in r]
+            rc = [c for c in pcls[a:b] for _ in range(8)]
+            variants.append(_finish([list(c) for c in vc], [list(c) for c in vo], [[0, 0, 0]], [-4], [list(c) for c in pcols[a:b]],
+                                    rr, emask=em, rclass=rc, istride=(1, 1, 1), ivoff=(0, 0, 0), ostride=stride,
+                                    iter_off=(0, 0, 0), col_bounds=7, useful=9.0 / 16.0))
+        # depth stride 2: the odd depth slices receive nothing and stay zero (the caller zero-fills); depth stride 1
+        # with the shift still leaves the slices the shift pushes out uncovered -> zero-fill as well
+        return ShiftConvPlan(src_channels, cin, cout, stride, fwd, fwd_chunks, wgrad, None, variants, True)
+    # strided (general): one point-form GEMM per (H, W) output parity; its K entries are the taps that reach
     # that parity, each fetched from d(raw) at o + (p - k + 1) / stride.  dx is zeroed by the caller
     # (depths / voxels that no tap reaches stay zero).
     for ph in range(shh):

@@ -148,10 +148,13 @@ int e2e_gather_wgrad_direct_ok(const e2e_wgrad_t* p);
 /*
  * wpacked[e/2][t][e%2][n][j] = bf16( w[rowoff[n] + centoff[e*8+j] + tapoff[t]] * (mask ? mask[same] : 1) )
  * (0 where rowoff or centoff is negative).  This is where the DSFF mask meets the weights.
+ * emask / rclass (both may be null): K entry e only feeds the columns whose class rclass[n] (0..31) has its bit set in
+ * emask[e]; other (e, n) pairs pack 0.  (The stride-2 data gradient computes all four output parities in one GEMM:
+ * an entry that reads d(raw) one row / column further only reaches the odd output rows / columns.)
  */
 int e2e_pack_weights(const float* w, const float* mask, const int32_t* rowoff, const int32_t* centoff,
-                     const int32_t* tapoff, int32_t n_cent, int32_t n_taps, int32_t Npad,
-                     void* wpacked, void* stream);
+                     const int32_t* tapoff, const int32_t* emask, const int32_t* rclass, int32_t n_cent, int32_t n_taps,
+                     int32_t Npad, void* wpacked, void* stream);
 /* the same for many (plan, weight) pairs in one launch: jobs is a DEVICE array; job j packs items
  * [item_begin, item_begin + n_cent*n_taps*Npad) (one item = 8 bf16 = 16 bytes of `out`) */
 typedef struct {
@@ -163,6 +166,8 @@ typedef struct {
   int32_t n_cent, n_taps, Npad, pad_;
   void* out;
   int64_t item_begin;
+  const int32_t* emask;           /* see e2e_pack_weights; may be null */
+  const int32_t* rclass;
 } e2e_pack_job_t;
 int e2e_pack_weights_multi(const e2e_pack_job_t* jobs, int32_t n_jobs, int64_t total_items, void* stream);
 /* grad[rowoff[n] + centoff[e*8+j] + tapoff[t]] = dwp[...]  (inverse scatter; every weight appears once) */

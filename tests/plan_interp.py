@@ -30,6 +30,8 @@ def pack(plan, w, mask=None):
                 ro = plan.rowoff[n]
                 if ro < 0:
                     continue
+                if plan.emask is not None and not ((int(plan.emask[e]) >> int(plan.rclass[n])) & 1):
+                    continue                      # this entry does not feed this column's class
                 for j in range(8):
                     co = plan.centoff[e * 8 + j]
                     if co < 0:

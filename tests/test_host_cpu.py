@@ -171,23 +171,26 @@ def test_real_layer_plans_are_consistent():
         assert all(ch.Npad <= 256 for ch in plan.fwd_chunks) and sum(
             int((ch.rowoff >= 0).sum()) for ch in plan.fwd_chunks) == cout
         assert f.n_cent % 2 == 0 and f.Npad % 16 == 0
-        nvar = stride[1] * stride[2] if plan.dgrad_needs_zero else 1
-        seen = {}
+        # data gradient: every (input channel, output parity) is produced by exactly one column, over all variants
+        # (stride 2 x 2: ONE GEMM whose column groups are the four parities, stored at row / column offsets (ph, pw))
+        npar = stride[1] * stride[2]
+        seen = []
         for var in plan.dgrad:
-            par = tuple(int(v) for v in var.iter_off)
-            live = var.rowoff[var.rowoff >= 0] // 9
-            # columns of a variant address distinct channels
-            cols = []
-            for q, (dst, blk, chmask, *_r) in enumerate(var.cols):
+            assert tuple(int(v) for v in var.iter_off) == (0, 0, 0) or npar == 1 or var.emask is None
+            for q, (dst, blk, chmask, od, oh, ow) in enumerate(var.cols):
                 if dst < 0:
                     continue
                 base = int(np.cumsum([0] + src)[dst]) + blk * 8
-                cols += [base + j for j in range(8) if chmask & (1 << j)]
-            assert len(cols) == len(set(cols))
-            seen.setdefault(par, []).extend(cols)
-        assert len(seen) == nvar
-        for par, cols in seen.items():
-            assert sorted(cols) == list(range(cin)), (src, stride, par)
+                par = (int(var.iter_off[1]) + int(oh), int(var.iter_off[2]) + int(ow)) if npar > 1 else (0, 0)
+                seen += [(base + j, par) for j in range(8) if chmask & (1 << j)]
+        assert len(seen) == len(set(seen))
+        want = {(c, (ph, pw)) for c in range(cin) for ph in range(stride[1]) for pw in range(stride[2])}
+        assert set(seen) == want, (src, stride)
+        if stride[1] == 2 and stride[2] == 2:
+            v0 = plan.dgrad[0]
+            assert v0.emask is not None and abs(v0.useful - 9 / 16) < 1e-12 and v0.n_cent >= 4 * (cout // 8)
+            # an entry that reads d(raw) one row / column further only feeds the odd output rows / columns
+            assert sorted(set(int(m) for m in v0.emask if m)) == [8, 10, 12, 15]
 
 
 @pytest.mark.parametrize("src,cout,spatial", [([72], 8, (3, 4, 6)), ([40, 40], 16, (4, 3, 5))])

@@ -71,6 +71,10 @@ def main():
         report("in_bwd (reduce + apply) " + tag, 5 * nb, timeit(lambda: _lib.check(lib.e2e_in_bwd(
             p(dy), p(raw), p(mean), p(rstd), p(ga), p(be), 0.01, B, Cb, V, p(partial), nch, p(sums), p(draw), p(dg),
             p(db), p(dbi), st())), a.iters))
+        scratch = torch.empty(int(lib.e2e_in_bwd_scratch_floats(B, Cb, V)), dtype=torch.float32, device=dev)
+        report("in_bwd plane-resident (A/B, 3 HBM passes) " + tag, 3 * nb, timeit(lambda: _lib.check(lib.e2e_in_bwd_fused(
+            p(dy), p(None), p(None), p(raw), p(mean), p(rstd), p(ga), p(be), 0.01, B, Cb, D, H, W, 1, 1, 1, p(scratch), p(sums),
+            p(draw), p(dg), p(db), p(dbi), st())), a.iters))
         k = (1, 2, 2) if D == 64 and H == 160 else (2, 2, 2)
         yo = torch.empty((B, Cb, D // k[0], H // k[1], W // k[2], 8), dtype=torch.bfloat16, device=dev)
         am = torch.empty(yo.shape, dtype=torch.uint8, device=dev)
@@ -96,6 +100,9 @@ def main():
     report("mask_apply_multi kernel, 35 tensors (w, momentum RMW + mask read)", n * 4 * 6,
            timeit(lambda: _lib.check(lib.e2e_mask_apply_multi(p(wt), p(bt), p(mt), p(nt), n_t, mx, st())), a.iters))
     report("Masking.apply_mask() incl. Python host side", n * 4 * 6, timeit(ts.mask.apply_mask, a.iters))
+    # fused optimizer step: clip coefficient + Nesterov SGD + weight decay + mask (grad read twice, p / momentum RMW, mask read)
+    nparam = sum(q.numel() for q in ts.network.parameters())
+    report("FusedSGD.step(): clip + SGD + apply_mask, 147 tensors", nparam * 4 * 6 + n * 4, timeit(ts.optimizer.step, a.iters))
     del ts
     # sliding window: one (16, 64, 160, 160) tile into a (16, 128, 320, 320) accumulator
     ncls, px, py, pz, X, Y, Z = 16, 64, 160, 160, 128, 320, 320
@@ -107,6 +114,16 @@ def main():
     report("window_accumulate 16 classes, 64x160x160 tile", P * (ncls * 4 + 2 * ncls * 4 + 2 * 4 + 4),
            timeit(lambda: _lib.check(lib.e2e_window_accumulate(p(logits), p(gauss), p(agg), p(wsum), ncls, px, py, pz,
                                                                 X, Y, Z, 32, 80, 80, 0, 1.0, 1, 1, st())), a.iters))
+    feat = torch.randn(6, px, py, pz, 8, device=dev).bfloat16()
+    hw = torch.randn(ncls, 48, device=dev)
+    report("window_head_accumulate (1x1x1 head + softmax + accumulate), 48 ch -> 16", P * (48 * 2 + 2 * ncls * 4 + 2 * 4 + 4),
+           timeit(lambda: _lib.check(lib.e2e_window_head_accumulate(p(feat), 6, p(hw), 48, p(gauss), p(agg), p(wsum), ncls, px,
+                                                                     py, pz, X, Y, Z, 32, 80, 80, 0, 1.0, 1, st())), a.iters))
+    wsum.fill_(1.0)
+    lab = torch.empty((150, 400, 400), dtype=torch.uint8, device=dev)
+    report("resample_argmax (16,128,320,320) -> (150,400,400) labels", 150 * 400 * 400 + ncls * X * Y * Z * 4,
+           timeit(lambda: _lib.check(lib.e2e_resample_argmax(p(agg), ncls, X, Y, Z, 150, 400, 400, 1, 1, 1, p(None), p(lab), st())),
+                  a.iters))
     seg = torch.empty(X, Y, Z, dtype=torch.int64, device=dev)
     Vv = X * Y * Z
     report("window_finalize (16,128,320,320)", Vv * (2 * ncls * 4 + 4 + 8),

@@ -57,6 +57,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--B", type=int, default=2)
     ap.add_argument("--ops", default="fwd,dgrad,wgrad")
+    ap.add_argument("--stats", type=int, default=1, help="forward with the InstanceNorm statistics fused into the epilogue")
+    ap.add_argument("--accum", type=int, default=0, help="data gradient: bitmask of destinations that accumulate (fan-in)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, impl, which = a.B, a.impl, a.ops.split(",")
@@ -77,13 +79,15 @@ def main():
         wpf = [ops.pack_weights(c, w, None) for c in plan.fwd_chunks]
         wpd = [ops.pack_weights(v, w, None) for v in plan.dgrad]
 
+        stats = a.stats and impl == 1           # forward as the network runs it: InstanceNorm sums in the epilogue
+
         def fwd():
             if impl == 1 and plan.fwd3 is not None and os.environ.get("E2E_STACK3", "1") == "1":
-                ops.run_gemm(plan.fwd3, ops.pack_weights(plan.fwd3, w, None), xs8, (D, H, W), (Do, Ho, Wo), B, [raw],
-                             (Do, Ho, Wo), [cout // 8], impl)
+                ops.run_gemm_chunks([plan.fwd3], w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
+                                    [cout // 8], impl, want_stats=stats)
             else:
                 ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo),
-                                    [cout // 8], impl)
+                                    [cout // 8], impl, want_stats=stats)
 
         def dgrad():
             if plan.dgrad_needs_zero:
@@ -93,7 +97,7 @@ def main():
                 it = plan.dgrad_iter_grid(grp[0], D, H, W)
                 if min(it) > 0:
                     ops.run_gemm_chunks(grp, w, None, [raw], (Do, Ho, Wo), it, B, dxs, (D, H, W),
-                                        [x.shape[1] for x in xs8], impl)
+                                        [x.shape[1] for x in xs8], impl, accumulate=a.accum)
 
         def wgrad():
             ops.run_wgrad(plan.wgrad, xs8, (D, H, W), (Do, Ho, Wo), B, raw, tuple(w.shape), impl)
