@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __r
 // to hide under the memory traffic, so it is folded into the accumulate pass: the fp32 logits (ncls * 4 B per
 // voxel written by a head kernel and read back here) never exist.  x: bf16 C8 [Cb][px][py][pz][8] of ONE tile;
 // w: fp32 [ncls][C] (rounded to bf16 here, like the packed operand of the GEMM head); one thread per voxel.
-template <int NC>
+template <int NC, int VPT>      // VPT voxels per thread: every weight fetched from shared memory is used VPT times
 __global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4* __restrict__ x, int Cb, const float* __restrict__ w,
                                                                      int C, const float* __restrict__ gauss, float* __restrict__ agg,
                                                                      float* __restrict__ wsum, int ncls, int px, int py, int pz,
@@ -81,56 +81,78 @@ __global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4
   __syncthreads();
   const long long P = (long long)px * py * pz;
   const long long V = (long long)X * Y * Z;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % pz);
-    const long long t = i / pz;
-    const int j = (int)(t % py), ii = (int)(t / py);
-    const int si = (flip & 1) ? px - 1 - ii : ii;
-    const int sj = (flip & 2) ? py - 1 - j : j;
-    const int sk = (flip & 4) ? pz - 1 - k : k;
-    const long long s = ((long long)si * py + sj) * pz + sk;
-    float v[NC];
+  const long long span = (long long)blockDim.x * VPT;
+  for (long long i0 = blockIdx.x * span + threadIdx.x; i0 < P; i0 += (long long)gridDim.x * span) {
+    long long src[VPT], dst[VPT], ii_[VPT];
+    bool ok[VPT];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) v[c] = 0.f;
+    for (int q = 0; q < VPT; ++q) {
+      const long long i = i0 + (long long)q * blockDim.x;
+      ok[q] = i < P;
+      const long long ic = ok[q] ? i : 0;
+      const int k = (int)(ic % pz);
+      const long long t = ic / pz;
+      const int j = (int)(t % py), ii = (int)(t / py);
+      const int si = (flip & 1) ? px - 1 - ii : ii;
+      const int sj = (flip & 2) ? py - 1 - j : j;
+      const int sk = (flip & 4) ? pz - 1 - k : k;
+      src[q] = ((long long)si * py + sj) * pz + sk;
+      dst[q] = ((long long)(x0 + ii) * Y + (y0 + j)) * Z + (z0 + k);
+      ii_[q] = ic;
+    }
+    float v[VPT][NC];
+#pragma unroll
+    for (int q = 0; q < VPT; ++q)
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[q][c] = 0.f;
     for (int cb = 0; cb < Cb; ++cb) {
-      const uint4 q = ld_nc_16(x + (long long)cb * P + s);
-      const float f[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y),
-                          bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+      float f[VPT][8];
+#pragma unroll
+      for (int q = 0; q < VPT; ++q) {
+        const uint4 u = ld_nc_16(x + (long long)cb * P + src[q]);
+        f[q][0] = bf16_lo(u.x); f[q][1] = bf16_hi(u.x); f[q][2] = bf16_lo(u.y); f[q][3] = bf16_hi(u.y);
+        f[q][4] = bf16_lo(u.z); f[q][5] = bf16_hi(u.z); f[q][6] = bf16_lo(u.w); f[q][7] = bf16_hi(u.w);
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float4* wr = reinterpret_cast<const float4*>(w_s + (cb * 8 + e) * NC);
 #pragma unroll
         for (int c4 = 0; c4 < NC / 4; ++c4) {
           const float4 ww = wr[c4];
-          v[4 * c4 + 0] = __fmaf_rn(f[e], ww.x, v[4 * c4 + 0]);
-          v[4 * c4 + 1] = __fmaf_rn(f[e], ww.y, v[4 * c4 + 1]);
-          v[4 * c4 + 2] = __fmaf_rn(f[e], ww.z, v[4 * c4 + 2]);
-          v[4 * c4 + 3] = __fmaf_rn(f[e], ww.w, v[4 * c4 + 3]);
+#pragma unroll
+          for (int q = 0; q < VPT; ++q) {
+            v[q][4 * c4 + 0] = __fmaf_rn(f[q][e], ww.x, v[q][4 * c4 + 0]);
+            v[q][4 * c4 + 1] = __fmaf_rn(f[q][e], ww.y, v[q][4 * c4 + 1]);
+            v[q][4 * c4 + 2] = __fmaf_rn(f[q][e], ww.z, v[q][4 * c4 + 2]);
+            v[q][4 * c4 + 3] = __fmaf_rn(f[q][e], ww.w, v[q][4 * c4 + 3]);
+          }
         }
       }
     }
-    float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c < ncls) mx = fmaxf(mx, v[c]);
-    float sum = 0.f;
+    for (int q = 0; q < VPT; ++q) {
+      if (!ok[q]) continue;
+      float mx = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      v[c] = (c < ncls) ? expf(v[c] - mx) : 0.f;
-      sum += v[c];
+      for (int c = 0; c < NC; ++c)
+        if (c < ncls) mx = fmaxf(mx, v[q][c]);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        v[q][c] = (c < ncls) ? expf(v[q][c] - mx) : 0.f;
+        sum += v[q][c];
+      }
+      const float inv = 1.0f / sum;
+      const float g = gauss ? gauss[ii_[q]] : 1.f;
+      float a[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) a[c] = (c < ncls) ? agg[c * V + dst[q]] : 0.f;
+      const float w0 = add_weight ? wsum[dst[q]] : 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+        if (c < ncls) agg[c * V + dst[q]] = a[c] + ((v[q][c] * inv) * scale) * g;
+      if (add_weight) wsum[dst[q]] = w0 + g;
     }
-    const float inv = 1.0f / sum;
-    const float g = gauss ? gauss[i] : 1.f;
-    const long long dst = ((long long)(x0 + ii) * Y + (y0 + j)) * Z + (z0 + k);
-    float a[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) a[c] = (c < ncls) ? agg[c * V + dst] : 0.f;
-    const float w0 = add_weight ? wsum[dst] : 0.f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c < ncls) agg[c * V + dst] = a[c] + ((v[c] * inv) * scale) * g;
-    if (add_weight) wsum[dst] = w0 + g;
   }
 }
 
@@ -191,17 +213,19 @@ extern "C" int e2e_window_head_accumulate(const void* x, int32_t Cb, const float
   E2E_ARG(x0 >= 0 && y0 >= 0 && z0 >= 0 && x0 + px <= X && y0 + py <= Y && z0 + pz <= Z,
           "window_head_accumulate: tile (%d,%d,%d)+(%d,%d,%d) outside volume (%d,%d,%d)", x0, y0, z0, px, py, pz, X, Y, Z);
   const long long P = (long long)px * py * pz;
-  long long blocks = (P + 255) / 256;
-  const long long cap = (long long)e2e_num_sms() * 8;
-  if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   const uint4* xp = (const uint4*)x;
-#define E2E_WHA(NC)                                                                                                       \
-  window_head_accumulate_kernel<NC><<<(unsigned)blocks, 256, (size_t)Cb * 8 * NC * 4, st>>>(                               \
-      xp, Cb, w, C, gauss, agg, wsum, ncls, px, py, pz, X, Y, Z, x0, y0, z0, flip, scale, add_weight)
-  if (ncls <= 4) E2E_WHA(4);
-  else if (ncls <= 16) E2E_WHA(16);
-  else E2E_WHA(32);
+#define E2E_WHA(NC, VPT)                                                                                                   \
+  do {                                                                                                                     \
+    long long blocks = (P + 256 * VPT - 1) / (256 * VPT);                                                                  \
+    const long long cap = (long long)e2e_num_sms() * 8;                                                                    \
+    if (blocks > cap) blocks = cap;                                                                                        \
+    window_head_accumulate_kernel<NC, VPT><<<(unsigned)blocks, 256, (size_t)Cb * 8 * NC * 4, st>>>(                        \
+        xp, Cb, w, C, gauss, agg, wsum, ncls, px, py, pz, X, Y, Z, x0, y0, z0, flip, scale, add_weight);                   \
+  } while (0)
+  if (ncls <= 4) E2E_WHA(4, 4);
+  else if (ncls <= 16) E2E_WHA(16, 2);
+  else E2E_WHA(32, 1);
 #undef E2E_WHA
   E2E_LAUNCHED("window_head_accumulate");
   return E2E_OK;
