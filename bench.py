@@ -322,7 +322,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------- our arm
@@ -509,8 +509,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": v, "unit": "patches/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": "oracle fwd+DS loss+bwd+clip+SGD+apply_mask on one 1x1x32x96x96 crop "
                                           "(0.18 patch), %d steps of %.1f s" % (n, dt)}
-    print(json.dumps(line))
-    sys.stdout.flush()
+    _emit(line)
     if ts is not None:
         _finish_ranks(ts, world)
 
@@ -612,6 +611,15 @@ def inference_leg(dev, world, rank, args):
                        str(gather_how)}}
 
 
+_RESULT_OUT = None
+
+
+def _emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -625,6 +633,12 @@ def main():
     ap.add_argument("--no-inference", action="store_true", help="skip the sliding-window inference leg")
     ap.add_argument("--infer-volume", type=int, nargs=3, default=[300, 512, 512])
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON result): everything the mirrored reference classes print
+    # (Masking's density tables, the poly-LR notices) goes to stderr
+    global _RESULT_OUT
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     if args.impl == "reference":
         run_reference(args)
     else:

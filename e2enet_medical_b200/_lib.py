@@ -115,6 +115,9 @@ SIGNATURES = {
     "e2e_shift_depth": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I64, _I32, _I32, _VP]),
     "e2e_in_stats": (C.c_int, [_VP, _I32, _I32, _I64, _F, _VP, _I32, _VP, _VP, _VP]),
     "e2e_in_apply": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP]),
+    "e2e_in_apply_from_slots": (C.c_int, [_VP, _VP, _I32, _F, _VP, _VP, _F, _I32, _I32, _I64, _VP, _VP, _VP, _VP]),
+    "e2e_in_apply_pool_from_slots": (C.c_int, [_VP, _VP, _I32, _F, _VP, _VP, _F, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
+                                               _VP, _VP, _VP, _VP, _VP, _VP]),
     "e2e_in_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _F, _I32, _I32, _I64, _VP, _I32, _VP, _VP, _VP, _VP,
                              _VP, _VP]),
     "e2e_in_bwd_scratch_floats": (C.c_int64, [_I32, _I32, _I64]),
@@ -139,7 +142,8 @@ SIGNATURES = {
     "e2e_sgd_update": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _I32, _VP]),
     "e2e_softmax_stats_partial_count": (C.c_int, [_I32, _I32, _I64]),
     "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP, _VP]),
-    "e2e_softmax_stats_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I32, _I32, _I64, _VP, _VP]),
+    "e2e_dc_ce_from_stats": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _F, _I32, _I32, _F, _F, _VP, _VP, _VP, _VP, _VP]),
+    "e2e_softmax_stats_bwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _I64, _VP, _VP]),
     "e2e_window_accumulate": (C.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,
                                         _I32, _I32, _F, _I32, _I32, _VP]),
     "e2e_window_head_accumulate": (C.c_int, [_VP, _I32, _VP, _I32, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32,

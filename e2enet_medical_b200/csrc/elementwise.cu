@@ -168,20 +168,81 @@ __global__ void __launch_bounds__(1024) in_stats_from_slots_kernel(const float* 
   rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Plane statistics inside the consumer kernel (no separate tiny launch): every block of a (chunk, plane) grid forms
+// the SAME fixed-order fp64 sums, so all blocks of a plane see bit-identical values; block (chunk 0) publishes them.
+//   mean / rstd of plane (b, cb) from the per-CTA slots a fused conv epilogue wrote: stats[slot][b][{sum, sumsq}][C]
+__device__ __forceinline__ void plane_mean_rstd_from_slots(const float* __restrict__ stats, int n_slots, int B, int C, int b,
+                                                           int cb, long long V, float eps, float* s_mean /*[8]*/,
+                                                           float* s_rstd /*[8]*/) {
+  __shared__ double s_red[2][32][8];
+  const int j = threadIdx.x & 7, g = threadIdx.x >> 3;             // 256 threads: 8 channels x 32 slot groups
+  double s = 0.0, q = 0.0;
+  const int c = cb * 8 + j;
+  if (c < C) {
+    for (int k = g; k < n_slots; k += 32) {
+      const float* row = stats + ((long long)(k * B + b) * 2) * C + c;
+      s += (double)__ldcg(row);
+      q += (double)__ldcg(row + C);
+    }
+  }
+  s_red[0][g][j] = s;
+  s_red[1][g][j] = q;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double ss = 0.0, qq = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { ss += s_red[0][i][threadIdx.x]; qq += s_red[1][i][threadIdx.x]; }
+    const double m = ss / (double)V;
+    double var = qq / (double)V - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)m;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+}
+//   sum dz / sum dz*xhat of a plane from the chunk partials of the backward's first pass: partial[plane][chunk][16]
+__device__ __forceinline__ void plane_sums_from_partials(const float* __restrict__ partial, int plane, int nchunk,
+                                                         float* s_sums /*[16]*/) {
+  __shared__ double s_red2[16][16];
+  const int k = threadIdx.x & 15, g = threadIdx.x >> 4;            // 256 threads: 16 values x 16 chunk groups
+  double s = 0.0;
+  for (int c = g; c < nchunk; c += 16) s += (double)__ldcg(partial + ((long long)plane * nchunk + c) * 16 + k);
+  s_red2[g][k] = s;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += s_red2[i][threadIdx.x];
+    s_sums[threadIdx.x] = (float)t;
+  }
+  __syncthreads();
+}
+
 // grid (nchunk, B*Cb)
 __global__ void __launch_bounds__(EW_THREADS) in_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ mean,
                                                               const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float slope, int Cb,
-                                                              long long V, int nchunk, uint4* __restrict__ out) {
+                                                              long long V, int nchunk, uint4* __restrict__ out,
+                                                              const float* __restrict__ stats, int n_slots, int B, float eps,
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const int plane = blockIdx.y, chunk = blockIdx.x;
   const int cb = plane % Cb;
+  __shared__ float s_mean[8], s_rstd[8];
+  if (stats) {                      // statistics straight from the conv epilogue's slots (see plane_mean_rstd_from_slots)
+    plane_mean_rstd_from_slots(stats, n_slots, B, Cb * 8, plane / Cb, cb, V, eps, s_mean, s_rstd);
+    if (chunk == 0 && threadIdx.x < 8) {
+      mean_out[plane * 8 + threadIdx.x] = s_mean[threadIdx.x];
+      rstd_out[plane * 8 + threadIdx.x] = s_rstd[threadIdx.x];
+    }
+  }
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float g = gamma[cb * 8 + j], r = rstd[plane * 8 + j];
+    const float g = gamma[cb * 8 + j], r = stats ? s_rstd[j] : rstd[plane * 8 + j];
+    const float m = stats ? s_mean[j] : mean[plane * 8 + j];
     sc[j] = g * r;
-    sh[j] = beta[cb * 8 + j] - mean[plane * 8 + j] * g * r;
+    sh[j] = beta[cb * 8 + j] - m * g * r;
   }
   const long long per = (V + nchunk - 1) / nchunk;
   const long long lo = chunk * per, hi = min(V, lo + per);
@@ -275,19 +336,23 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_apply_kernel(const uint4* _
                                                                   const float* __restrict__ rstd,
                                                                   const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta,
-                                                                  const float* __restrict__ sums, float slope, int Cb,
+                                                                  const float* __restrict__ partial1,
+                                                                  float* __restrict__ sums, float slope, int Cb,
                                                                   long long V, int nchunk, uint4* __restrict__ draw,
                                                                   float* __restrict__ partial2) {
   const int plane = blockIdx.y, chunk = blockIdx.x;
   const int cb = plane % Cb;
   const float invV = 1.0f / (float)V;
+  __shared__ float s_sums[16];
+  plane_sums_from_partials(partial1, plane, nchunk, s_sums);      // pass 1's totals, formed here (no tiny launch between)
+  if (chunk == 0 && threadIdx.x < 16) sums[plane * 16 + threadIdx.x] = s_sums[threadIdx.x];
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
     ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
-    m1[j] = sums[plane * 16 + j] * invV;
-    m2[j] = sums[plane * 16 + 8 + j] * invV;
+    m1[j] = s_sums[j] * invV;
+    m2[j] = s_sums[8 + j] * invV;
   }
   const long long per = (V + nchunk - 1) / nchunk;
   const long long lo = chunk * per, hi = min(V, lo + per);
@@ -371,17 +436,28 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* 
                                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float slope, int Cb, PoolGeo g,
                                                                    int nchunk, uint4* __restrict__ out, uint4* __restrict__ pooled,
-                                                                   uint2* __restrict__ amax) {
+                                                                   uint2* __restrict__ amax, const float* __restrict__ stats,
+                                                                   int n_slots, int B, float eps, float* __restrict__ mean_out,
+                                                                   float* __restrict__ rstd_out) {
   const int plane = blockIdx.y, chunk = blockIdx.x;
   const int cb = plane % Cb;
+  const long long V = (long long)g.D * g.H * g.W;
+  __shared__ float s_mean[8], s_rstd[8];
+  if (stats) {
+    plane_mean_rstd_from_slots(stats, n_slots, B, Cb * 8, plane / Cb, cb, V, eps, s_mean, s_rstd);
+    if (chunk == 0 && threadIdx.x < 8) {
+      mean_out[plane * 8 + threadIdx.x] = s_mean[threadIdx.x];
+      rstd_out[plane * 8 + threadIdx.x] = s_rstd[threadIdx.x];
+    }
+  }
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float ga = gamma[cb * 8 + j], r = rstd[plane * 8 + j];
+    const float ga = gamma[cb * 8 + j], r = stats ? s_rstd[j] : rstd[plane * 8 + j];
+    const float m = stats ? s_mean[j] : mean[plane * 8 + j];
     sc[j] = ga * r;
-    sh[j] = beta[cb * 8 + j] - mean[plane * 8 + j] * ga * r;
+    sh[j] = beta[cb * 8 + j] - m * ga * r;
   }
-  const long long V = (long long)g.D * g.H * g.W;
   const long long Vo = V / (g.kd * g.kh * g.kw);
   const long long per = (Vo + nchunk - 1) / nchunk;
   const long long lo = chunk * per, hi = min(Vo, lo + per);
@@ -439,20 +515,26 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __
                                                                  const uint2* __restrict__ amax, const uint4* __restrict__ raw,
                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                                 const float* __restrict__ sums, float slope, int Cb, PoolGeo g,
-                                                                 int nchunk, uint4* __restrict__ draw, float* __restrict__ partial) {
+                                                                 const float* __restrict__ partial1, float* __restrict__ sums,
+                                                                 float slope, int Cb, PoolGeo g, int nchunk,
+                                                                 uint4* __restrict__ draw, float* __restrict__ partial) {
   const int plane = blockIdx.y, chunk = blockIdx.x;
   const int cb = plane % Cb;
   const long long V = (long long)g.D * g.H * g.W;
   const long long Vo = V / (g.kd * g.kh * g.kw);
   const float invV = 1.0f / (float)V;
+  __shared__ float s_sums[16];
+  if (PASS) {
+    plane_sums_from_partials(partial1, plane, nchunk, s_sums);
+    if (chunk == 0 && threadIdx.x < 16) sums[plane * 16 + threadIdx.x] = s_sums[threadIdx.x];
+  }
   float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[plane * 8 + j]; rs[j] = rstd[plane * 8 + j];
     ga[j] = gamma[cb * 8 + j]; be[j] = beta[cb * 8 + j];
-    m1[j] = PASS ? sums[plane * 16 + j] * invV : 0.f;
-    m2[j] = PASS ? sums[plane * 16 + 8 + j] * invV : 0.f;
+    m1[j] = PASS ? s_sums[j] * invV : 0.f;
+    m2[j] = PASS ? s_sums[8 + j] * invV : 0.f;
   }
   const long long per = (Vo + nchunk - 1) / nchunk;
   const long long lo = chunk * per, hi = min(Vo, lo + per);
@@ -880,8 +962,26 @@ extern "C" int e2e_in_apply(const void* raw, const float* mean, const float* rst
   if (nchunk > want) nchunk = want;
   if (nchunk < 1) nchunk = 1;
   in_apply_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, V, nchunk, (uint4*)out);
+      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, V, nchunk, (uint4*)out, nullptr, 0, B, 0.f, nullptr, nullptr);
   E2E_LAUNCHED("in_apply");
+  return E2E_OK;
+}
+
+// e2e_in_stats_final + e2e_in_apply in one launch: mean / rstd come from the conv epilogue's statistic slots
+// (stats[n_slots][B][2][Cb*8]); they are also written to mean_out / rstd_out (B*Cb*8 each) for the backward.
+extern "C" int e2e_in_apply_from_slots(const void* raw, const float* stats, int32_t n_slots, float eps, const float* gamma,
+                                       const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* mean_out,
+                                       float* rstd_out, void* out, void* stream) {
+  E2E_ARG(raw && stats && gamma && beta && out && mean_out && rstd_out && n_slots > 0 && B > 0 && Cb > 0 && V > 0,
+          "in_apply_from_slots: bad arguments");
+  int nchunk = (int)((V + 4095) / 4096);
+  const int want = (e2e_num_sms() * 8 + B * Cb - 1) / (B * Cb);
+  if (nchunk > want) nchunk = want;
+  if (nchunk < 1) nchunk = 1;
+  in_apply_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
+      (const uint4*)raw, nullptr, nullptr, gamma, beta, slope, Cb, V, nchunk, (uint4*)out, stats, n_slots, B, eps, mean_out,
+      rstd_out);
+  E2E_LAUNCHED("in_apply_from_slots");
   return E2E_OK;
 }
 
@@ -897,13 +997,11 @@ extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, co
   in_bwd_reduce_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta,
                                                     slope, Cb, V, nchunk, partial);
   E2E_LAUNCHED("in_bwd_reduce");
-  const int n = B * Cb * 16 * 32;
-  in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
-  E2E_LAUNCHED("in_bwd_final");
-  in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, sums,
-                                                   slope, Cb, V, nchunk, (uint4*)draw, partial);
+  float* partial2 = partial + (size_t)B * Cb * nchunk * 16;        // pass 2 reads ALL of pass 1's partials: separate region
+  in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, partial,
+                                                   sums, slope, Cb, V, nchunk, (uint4*)draw, partial2);
   E2E_LAUNCHED("in_bwd_apply");
-  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial2, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;
 }
@@ -954,10 +1052,10 @@ extern "C" int e2e_in_bwd_fused(const void* dy, const void* dyp, const uint8_t* 
   return E2E_OK;
 }
 
-extern "C" int e2e_in_apply_pool(const void* raw, const float* mean, const float* rstd, const float* gamma,
-                                 const float* beta, float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W,
-                                 int32_t kd, int32_t kh, int32_t kw, void* out, void* pooled, uint8_t* argmax, void* stream) {
-  E2E_ARG(raw && mean && rstd && gamma && beta && out && pooled && argmax && B > 0 && Cb > 0, "in_apply_pool: bad arguments");
+static int in_apply_pool_impl(const void* raw, const float* mean, const float* rstd, const float* stats, int n_slots, float eps,
+                              float* mean_out, float* rstd_out, const float* gamma, const float* beta, float slope, int32_t B,
+                              int32_t Cb, int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, void* out,
+                              void* pooled, uint8_t* argmax, void* stream) {
   E2E_ARG(kd >= 1 && kh >= 1 && kw >= 1 && kd * kh * kw <= 8 && D % kd == 0 && H % kh == 0 && W % kw == 0,
           "in_apply_pool: window (%d,%d,%d) must divide (%d,%d,%d) and hold at most 8 voxels", kd, kh, kw, D, H, W);
   const PoolGeo g{D, H, W, kd, kh, kw};
@@ -970,16 +1068,37 @@ extern "C" int e2e_in_apply_pool(const void* raw, const float* mean, const float
   cudaStream_t st = (cudaStream_t)stream;
   if (kd == 1 && kh == 2 && kw == 2)
     in_apply_pool_kernel<1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
-                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax, stats, n_slots, B, eps,
+                                                                 mean_out, rstd_out);
   else if (kd == 2 && kh == 2 && kw == 2)
     in_apply_pool_kernel<2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
-                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax);
+                                                                 (uint4*)out, (uint4*)pooled, (uint2*)argmax, stats, n_slots, B, eps,
+                                                                 mean_out, rstd_out);
   else {
     e2e_set_error("in_apply_pool: window (%d,%d,%d) is not instantiated (use the separate max-pool kernel)", kd, kh, kw);
     return E2E_ERR_UNSUPPORTED;
   }
   E2E_LAUNCHED("in_apply_pool");
   return E2E_OK;
+}
+
+extern "C" int e2e_in_apply_pool(const void* raw, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W,
+                                 int32_t kd, int32_t kh, int32_t kw, void* out, void* pooled, uint8_t* argmax, void* stream) {
+  E2E_ARG(raw && mean && rstd && gamma && beta && out && pooled && argmax && B > 0 && Cb > 0, "in_apply_pool: bad arguments");
+  return in_apply_pool_impl(raw, mean, rstd, nullptr, 0, 0.f, nullptr, nullptr, gamma, beta, slope, B, Cb, D, H, W, kd, kh, kw,
+                            out, pooled, argmax, stream);
+}
+
+// e2e_in_stats_final + e2e_in_apply_pool in one launch (see e2e_in_apply_from_slots)
+extern "C" int e2e_in_apply_pool_from_slots(const void* raw, const float* stats, int32_t n_slots, float eps, const float* gamma,
+                                            const float* beta, float slope, int32_t B, int32_t Cb, int32_t D, int32_t H,
+                                            int32_t W, int32_t kd, int32_t kh, int32_t kw, float* mean_out, float* rstd_out,
+                                            void* out, void* pooled, uint8_t* argmax, void* stream) {
+  E2E_ARG(raw && stats && n_slots > 0 && mean_out && rstd_out && gamma && beta && out && pooled && argmax && B > 0 && Cb > 0,
+          "in_apply_pool_from_slots: bad arguments");
+  return in_apply_pool_impl(raw, nullptr, nullptr, stats, n_slots, eps, mean_out, rstd_out, gamma, beta, slope, B, Cb, D, H, W,
+                            kd, kh, kw, out, pooled, argmax, stream);
 }
 
 extern "C" int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
@@ -999,26 +1118,24 @@ extern "C" int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* a
     e2e_set_error("in_bwd_pool: window (%d,%d,%d) is not instantiated", kd, kh, kw);
     return E2E_ERR_UNSUPPORTED;
   }
-#define E2E_BWD_POOL(PASS, DRAW, SUMS)                                                                                     \
+#define E2E_BWD_POOL(PASS, DRAW, SUMS, POUT)                                                                                   \
   do {                                                                                                                     \
     if (k122)                                                                                                              \
       in_bwd_pool_kernel<PASS, 1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
-                                                                     (const uint4*)raw, mean, rstd, gamma, beta, SUMS, slope, Cb, \
-                                                                     g, nchunk, DRAW, partial);                           \
+                                                                     (const uint4*)raw, mean, rstd, gamma, beta, partial, SUMS, slope, \
+                                                                     Cb, g, nchunk, DRAW, POUT);                          \
     else                                                                                                                   \
       in_bwd_pool_kernel<PASS, 2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
-                                                                     (const uint4*)raw, mean, rstd, gamma, beta, SUMS, slope, Cb, \
-                                                                     g, nchunk, DRAW, partial);                           \
+                                                                     (const uint4*)raw, mean, rstd, gamma, beta, partial, SUMS, slope, \
+                                                                     Cb, g, nchunk, DRAW, POUT);                          \
   } while (0)
-  E2E_BWD_POOL(0, nullptr, nullptr);
+  float* partial2 = partial + (size_t)B * Cb * nchunk * 16;
+  E2E_BWD_POOL(0, nullptr, nullptr, partial);
   E2E_LAUNCHED("in_bwd_pool_reduce");
-  const int n = B * Cb * 16 * 32;
-  in_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(partial, B * Cb, nchunk, sums);
-  E2E_LAUNCHED("in_bwd_final");
-  E2E_BWD_POOL(1, (uint4*)draw, sums);
+  E2E_BWD_POOL(1, (uint4*)draw, sums, partial2);
   E2E_LAUNCHED("in_bwd_pool_apply");
 #undef E2E_BWD_POOL
-  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial, B, Cb, nchunk, dgamma, dbeta, dbias);
+  in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial2, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
   return E2E_OK;
 }

@@ -101,10 +101,55 @@ __global__ void softmax_stats_final_kernel(const float* __restrict__ partial, in
   if (i == 3 * C && lane == 0) ce_sum[0] += (float)ce_all;
 }
 
+// DC_and_CE_loss from the statistics (dice_loss.py:155-190, 302-359; crossentropy.py:4-11), one block:
+//   dc[b,c] = (2 tp + smooth) / (2 tp + fp + fn + smooth + 1e-8),  fp = S_p - tp, fn = S_y - tp  =>  den = S_p + S_y + smooth + 1e-8
+//   loss = weight_ce * ce_sum / n_vox - weight_dice * mean_{b, c >= c0} dc        (batch_dice: tp, S_p, S_y summed over b first)
+// and the coefficients the backward pass needs: gsp = d loss / d S_p, gtp = d loss / d tp, gce = d loss / d ce_sum.
+// Replaces ~45 (B, C)-sized ATen launches per deep-supervision output (forward + backward) by this one.
+__global__ void __launch_bounds__(256) dc_ce_from_stats_kernel(const float* __restrict__ stats, const float* __restrict__ ce_sum,
+                                                               int B, int C, float n_vox, float smooth, int do_bg, int batch_dice,
+                                                               float weight_ce, float weight_dice, float* __restrict__ loss,
+                                                               float* __restrict__ gsp, float* __restrict__ gtp,
+                                                               float* __restrict__ gce) {
+  __shared__ float s_dc[256];
+  const int c0 = do_bg ? 0 : 1;
+  const int n = B * C;
+  float acc = 0.f;                                   // sum of dc over this thread's (b, c) entries, fixed assignment
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = i / C, c = i - b * C;
+    float tp, sp, sy;
+    if (batch_dice) {
+      tp = sp = sy = 0.f;
+      for (int bb = 0; bb < B; ++bb) {
+        const float* q = stats + ((long long)bb * C + c) * 3;
+        sp += q[0]; tp += q[1]; sy += q[2];
+      }
+    } else {
+      const float* q = stats + (long long)i * 3;
+      sp = q[0]; tp = q[1]; sy = q[2];
+    }
+    const float num = 2.f * tp + smooth, den = sp + sy + smooth + 1e-8f;
+    const float cnt = batch_dice ? (float)(C - c0) : (float)(B * (C - c0));
+    const bool on = c >= c0;
+    gtp[i] = on ? -weight_dice * (2.f / den) / cnt : 0.f;
+    gsp[i] = on ? weight_dice * (num / (den * den)) / cnt : 0.f;
+    if (on && (!batch_dice || b == 0)) acc += (num / den) / cnt;
+  }
+  s_dc[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float dc = 0.f;
+    for (int i = 0; i < (int)blockDim.x; ++i) dc += s_dc[i];       // fixed order
+    loss[0] = weight_ce * (ce_sum[0] / n_vox) - weight_dice * dc;
+    gce[0] = weight_ce / n_vox;
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(256) softmax_stats_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ target,
                                                                 const float* __restrict__ gsp, const float* __restrict__ gtp,
-                                                                const float* __restrict__ gce, int C, long long V,
+                                                                const float* __restrict__ gce, const float* __restrict__ gscale,
+                                                                int C, long long V,
                                                                 int chunks_per_b, float* __restrict__ dlogits) {
   const int b = blockIdx.y;
   const long long per = (V + chunks_per_b - 1) / chunks_per_b;
@@ -118,7 +163,13 @@ __global__ void __launch_bounds__(256) softmax_stats_bwd_kernel(const float* __r
     a[c] = (c < C) ? gsp[b * C + c] : 0.f;
     t[c] = (c < C) ? gtp[b * C + c] : 0.f;
   }
-  const float gc = gce[0];
+  float gc = gce[0];
+  if (gscale) {                                      // upstream gradient of the (scalar) loss, read on the device
+    const float gs = gscale[0];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { a[c] *= gs; t[c] *= gs; }
+    gc *= gs;
+  }
   for (long long v = lo + threadIdx.x; v < hi; v += blockDim.x) {
     float z[NC];
     float mx = -INFINITY;
@@ -181,15 +232,27 @@ extern "C" int e2e_softmax_stats_fwd(const float* logits, const float* target, i
   return E2E_OK;
 }
 
+extern "C" int e2e_dc_ce_from_stats(const float* stats, const float* ce_sum, int32_t B, int32_t C, int64_t n_vox, float smooth,
+                                    int32_t do_bg, int32_t batch_dice, float weight_ce, float weight_dice, float* loss,
+                                    float* gsp, float* gtp, float* gce, void* stream) {
+  E2E_ARG(stats && ce_sum && loss && gsp && gtp && gce && B > 0 && C > 0 && n_vox > 0, "dc_ce_from_stats: bad arguments");
+  E2E_ARG(C - (do_bg ? 0 : 1) > 0, "dc_ce_from_stats: no foreground class");
+  dc_ce_from_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(stats, ce_sum, B, C, (float)n_vox, smooth, do_bg, batch_dice,
+                                                               weight_ce, weight_dice, loss, gsp, gtp, gce);
+  E2E_LAUNCHED("dc_ce_from_stats");
+  return E2E_OK;
+}
+
 extern "C" int e2e_softmax_stats_bwd(const float* logits, const float* target, const float* gsp, const float* gtp,
-                                     const float* gce, int32_t B, int32_t C, int64_t V, float* dlogits, void* stream) {
+                                     const float* gce, const float* gscale, int32_t B, int32_t C, int64_t V, float* dlogits,
+                                     void* stream) {
   E2E_ARG(logits && target && gsp && gtp && gce && dlogits && B > 0 && C > 0 && V > 0, "softmax_stats_bwd: bad arguments");
   E2E_ARG(C <= 32, "softmax_stats_bwd: at most 32 classes (got %d)", C);
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(chunks_for(V, B), B);
-  if (C <= 4) softmax_stats_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
-  else if (C <= 16) softmax_stats_bwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
-  else softmax_stats_bwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, C, V, grid.x, dlogits);
+  if (C <= 4) softmax_stats_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, gscale, C, V, grid.x, dlogits);
+  else if (C <= 16) softmax_stats_bwd_kernel<16><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, gscale, C, V, grid.x, dlogits);
+  else softmax_stats_bwd_kernel<32><<<grid, 256, 0, st>>>(logits, target, gsp, gtp, gce, gscale, C, V, grid.x, dlogits);
   E2E_LAUNCHED("softmax_stats_bwd");
   return E2E_OK;
 }

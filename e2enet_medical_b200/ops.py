@@ -333,7 +333,8 @@ def _grad_slot(param: torch.Tensor):
 
 
 def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid, B: int, grad: torch.Tensor,
-              weight_shape, impl: int = 0, out: Optional[torch.Tensor] = None, out_is_zero: bool = False) -> torch.Tensor:
+              weight_shape, impl: int = 0, out: Optional[torch.Tensor] = None, out_is_zero: bool = False,
+              scratch_from=None) -> torch.Tensor:
     """returns the fp32 weight gradient in the reference's parameter layout (written into `out` if given)."""
     lib = _lib.load()
     device = grad.device
@@ -374,7 +375,9 @@ def run_wgrad(plan: GemmPlan, srcs: Sequence[torch.Tensor], src_grid, iter_grid,
         with _Timed("wgrad", flops):
             _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
         return gw
-    dwp = torch.zeros(plan.packed_numel, dtype=torch.float32, device=device)
+    dwp = scratch_from.take_scratch(plan.packed_numel) if scratch_from is not None else None
+    if dwp is None:
+        dwp = torch.zeros(plan.packed_numel, dtype=torch.float32, device=device)
     p.dwp = dwp.data_ptr()
     with _Timed("wgrad", flops):
         _lib.check(lib.e2e_gather_wgrad(C.byref(p), _lib.stream_ptr()), "gather_wgrad")
@@ -496,10 +499,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         nch = _nchunk(V, B * Cb)
         mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
         rstd = torch.empty_like(mean)
-        if stats is not None:
-            _lib.check(lib.e2e_in_stats_final(_p(stats), stats.shape[0], B, Cb * 8, V, EPS, _p(mean), _p(rstd),
-                                              _lib.stream_ptr()), "in_stats_final")
-        else:
+        if stats is None:
             partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
             _lib.check(lib.e2e_in_stats(_p(raw), B, Cb, V, EPS, _p(partial), nch, _p(mean), _p(rstd), _lib.stream_ptr()),
                        "in_stats")
@@ -512,14 +512,23 @@ class ShiftConvINLReLU(torch.autograd.Function):
             kd, kh, kw = (int(v) for v in pool_k)
             yp = torch.empty((B, Cb, Do // kd, Ho // kh, Wo // kw, 8), dtype=torch.bfloat16, device=dev)
             am = torch.empty(yp.shape, dtype=torch.uint8, device=dev)
-            _lib.check(lib.e2e_in_apply_pool(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, Do, Ho, Wo,
-                                             kd, kh, kw, _p(y), _p(yp), _p(am), _lib.stream_ptr()), "in_apply_pool")
+            if stats is not None:       # mean / rstd are formed from the epilogue's slots inside the same launch
+                _lib.check(lib.e2e_in_apply_pool_from_slots(_p(raw), _p(stats), stats.shape[0], EPS, _p(g32), _p(b32), slope,
+                                                            B, Cb, Do, Ho, Wo, kd, kh, kw, _p(mean), _p(rstd), _p(y), _p(yp),
+                                                            _p(am), _lib.stream_ptr()), "in_apply_pool_from_slots")
+            else:
+                _lib.check(lib.e2e_in_apply_pool(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, Do, Ho, Wo,
+                                                 kd, kh, kw, _p(y), _p(yp), _p(am), _lib.stream_ptr()), "in_apply_pool")
             ctx.pool_k = (kd, kh, kw)
             ctx.out_ptrs = (y.data_ptr(), yp.data_ptr())
             ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, am, *srcs)
             return y, yp
-        _lib.check(lib.e2e_in_apply(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, V, _p(y),
-                                    _lib.stream_ptr()), "in_apply")
+        if stats is not None:
+            _lib.check(lib.e2e_in_apply_from_slots(_p(raw), _p(stats), stats.shape[0], EPS, _p(g32), _p(b32), slope, B, Cb, V,
+                                                   _p(mean), _p(rstd), _p(y), _lib.stream_ptr()), "in_apply_from_slots")
+        else:
+            _lib.check(lib.e2e_in_apply(_p(raw), _p(mean), _p(rstd), _p(g32), _p(b32), slope, B, Cb, V, _p(y),
+                                        _lib.stream_ptr()), "in_apply")
         ctx.out_ptrs = (y.data_ptr(),)
         ctx.save_for_backward(weight, gamma, beta, raw, mean, rstd, *srcs)
         return y
@@ -545,7 +554,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         impl = CONFIG["impl"]
         dy = dy.contiguous() if dy is not None else None
         nch = _nchunk(V, B * Cb)
-        partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+        partial = torch.empty(B * Cb * nch * 24, dtype=torch.float32, device=dev)     # pass 1 (16) + pass 2 (8) per chunk
         sums = torch.empty(B * Cb * 16, dtype=torch.float32, device=dev)
         draw = torch.empty_like(raw)
         # small-parameter gradients go straight into the flat gradient arena when the trainer installed one
@@ -587,7 +596,8 @@ class ShiftConvINLReLU(torch.autograd.Function):
         gw = None
         if ctx.needs_input_grad[2]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
+            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step,
+                           scratch_from=arena)
             if arena is not None:
                 arena.mark_ready(weight)
         # data gradients of every source
@@ -634,7 +644,8 @@ class TConv(torch.autograd.Function):
         gw = dx = None
         if ctx.needs_input_grad[1]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
+            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step,
+                           scratch_from=arena)
             if arena is not None:
                 arena.mark_ready(weight)
         if ctx.needs_input_grad[3]:
@@ -696,7 +707,8 @@ class SegHead(torch.autograd.Function):
         gw = dx = None
         if ctx.needs_input_grad[1]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step)
+            gw = run_wgrad(plan.fwd, [x], (D, H, W), (D, H, W), B, g, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step,
+                           scratch_from=arena)
             if arena is not None:
                 arena.mark_ready(weight)
         if ctx.needs_input_grad[2]:
@@ -742,6 +754,51 @@ class SoftmaxStats(torch.autograd.Function):
                               else g.contiguous().float())
         gsp, gtp, gce = z(gsp, (B, Cc)), z(gtp, (B, Cc)), z(gce, ())
         dx = torch.empty_like(x)
-        _lib.check(lib.e2e_softmax_stats_bwd(_p(x), _p(t), _p(gsp), _p(gtp), _p(gce), B, Cc, V, _p(dx),
+        _lib.check(lib.e2e_softmax_stats_bwd(_p(x), _p(t), _p(gsp), _p(gtp), _p(gce), _p(None), B, Cc, V, _p(dx),
                                              _lib.stream_ptr()), "softmax_stats_bwd")
         return dx, None
+
+
+class DiceCELoss(torch.autograd.Function):
+    """DC_and_CE_loss(net_output, target) of the reference trainer's configuration as FOUR launches forward (statistics,
+    their fixed-order reduction, the dice / CE formulas on the (B, C) statistics) and ONE backward (the upstream
+    gradient -- e.g. a GradScaler's scale times the deep-supervision weight -- is read on the device): no (B, C)-sized
+    ATen arithmetic at all.  Reference: dice_loss.py:155-190, 302-359; crossentropy.py:4-11."""
+
+    @staticmethod
+    def forward(ctx, logits, target, smooth, do_bg, batch_dice, weight_ce, weight_dice):
+        _need_cuda(logits, "dc_ce_loss")
+        lib = _lib.load()
+        x = logits.contiguous().float()
+        t = target.detach().contiguous().float()
+        B, Cc = x.shape[:2]
+        V = x[0, 0].numel()
+        if t.numel() != B * V:
+            raise ValueError("dc_ce_loss: target must hold one class index per voxel (got %s for logits %s)"
+                             % (tuple(target.shape), tuple(logits.shape)))
+        dev = x.device
+        buf = torch.zeros(B * Cc * 3 + 1, dtype=torch.float32, device=dev)          # stats | ce_sum (one zero fill)
+        stats, ce = buf[:B * Cc * 3], buf[B * Cc * 3:]
+        partial = torch.empty(max(1, int(lib.e2e_softmax_stats_partial_count(B, Cc, V))), dtype=torch.float32, device=dev)
+        _lib.check(lib.e2e_softmax_stats_fwd(_p(x), _p(t), B, Cc, V, _p(partial), _p(stats), _p(ce), _lib.stream_ptr()),
+                   "softmax_stats_fwd")
+        out = torch.empty(2 * B * Cc + 2, dtype=torch.float32, device=dev)            # loss | gce | gsp | gtp
+        loss, gce, gsp, gtp = out[0:1], out[1:2], out[2:2 + B * Cc], out[2 + B * Cc:]
+        _lib.check(lib.e2e_dc_ce_from_stats(_p(stats), _p(ce), B, Cc, B * V, float(smooth), 1 if do_bg else 0,
+                                            1 if batch_dice else 0, float(weight_ce), float(weight_dice), _p(loss), _p(gsp),
+                                            _p(gtp), _p(gce), _lib.stream_ptr()), "dc_ce_from_stats")
+        ctx.save_for_backward(x, t, out)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, t, out = ctx.saved_tensors
+        lib = _lib.load()
+        B, Cc = x.shape[:2]
+        V = x[0, 0].numel()
+        gce, gsp, gtp = out[1:2], out[2:2 + B * Cc], out[2 + B * Cc:]
+        gs = gout.detach().reshape(1).float().contiguous()
+        dx = torch.empty_like(x)
+        _lib.check(lib.e2e_softmax_stats_bwd(_p(x), _p(t), _p(gsp), _p(gtp), _p(gce), _p(gs), B, Cc, V, _p(dx),
+                                             _lib.stream_ptr()), "softmax_stats_bwd")
+        return dx, None, None, None, None, None, None

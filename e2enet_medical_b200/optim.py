@@ -57,6 +57,11 @@ class GradArena(object):
                 self.bucket_last.append(id(p))
                 lo, b = end, b + 1
         self.n_buckets = len(self.bucket_range)
+        # packed fp32 scratch of the weight-gradient GEMMs (they ADD their split-K results into it): one persistent
+        # buffer zeroed once per step instead of one torch.zeros per layer; sized from the first step's demand
+        self._scratch = None
+        self._scratch_used = 0
+        self._scratch_demand = 0
         self.zeroed_this_step = False       # begin_step() zeroed the whole buffer and nothing has been added since
         self._pending = None                # per-step: set of parameter ids of each bucket still missing
         self.on_bucket_ready = None         # callback(bucket index) -- installed by the data-parallel trainer
@@ -75,9 +80,25 @@ class GradArena(object):
         their slots) and re-arm the bucket bookkeeping"""
         self.flat.zero_()
         self.zeroed_this_step = True
+        if self._scratch is None and self._scratch_demand > 0:
+            self._scratch = torch.empty(self._scratch_demand, dtype=torch.float32, device=self.flat.device)
+        if self._scratch is not None:
+            self._scratch.zero_()
+        self._scratch_used = 0
+        self._scratch_demand = 0
         self._pending = [set() for _ in range(self.n_buckets)]
         for p in self.params:
             self._pending[self.bucket_of[id(p)]].add(id(p))
+
+    def take_scratch(self, numel: int):
+        """a zeroed fp32 slice of the per-step scratch, or None (first step / not enough room: the caller allocates)"""
+        numel = (int(numel) + 63) // 64 * 64
+        self._scratch_demand += numel
+        if self._scratch is None or self._scratch_used + numel > self._scratch.numel():
+            return None
+        v = self._scratch.narrow(0, self._scratch_used, numel)
+        self._scratch_used += numel
+        return v
 
     def mark_ready(self, p):
         """called by the backward ops right after p's gradient has been enqueued into its arena slot"""

@@ -193,7 +193,13 @@ int e2e_in_stats_final(const float* stats, int32_t n_slots, int32_t B, int32_t C
                        float* rstd, void* stream);
 int e2e_in_apply(const void* raw, const float* mean, const float* rstd, const float* gamma, const float* beta,
                  float slope, int32_t B, int32_t Cb, int64_t V, void* out, void* stream);
-/* backward: sums[b][c] = {sum dz, sum dz*xhat}; then draw, dgamma, dbeta, dbias */
+/* e2e_in_stats_final + e2e_in_apply in ONE launch: every block forms its plane's mean / rstd from the epilogue slots
+ * (stats[n_slots][B][2][Cb*8]) in the same fixed order; they are also stored to mean_out / rstd_out for the backward */
+int e2e_in_apply_from_slots(const void* raw, const float* stats, int32_t n_slots, float eps, const float* gamma,
+                            const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* mean_out, float* rstd_out,
+                            void* out, void* stream);
+/* backward: sums[b][c] = {sum dz, sum dz*xhat}; then draw, dgamma, dbeta, dbias.
+ * partial: scratch fp32 [B*Cb][nchunk][16] (pass 1) followed by [B*Cb][nchunk][8] (pass 2) = 24*B*Cb*nchunk floats */
 int e2e_in_bwd(const void* dy, const void* raw, const float* mean, const float* rstd, const float* gamma,
                const float* beta, float slope, int32_t B, int32_t Cb, int64_t V, float* partial, int32_t nchunk,
                float* sums, void* draw, float* dgamma, float* dbeta, float* dbias, void* stream);
@@ -205,6 +211,11 @@ int e2e_in_bwd(const void* dy, const void* raw, const float* mean, const float* 
 int e2e_in_apply_pool(const void* raw, const float* mean, const float* rstd, const float* gamma, const float* beta,
                       float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh,
                       int32_t kw, void* out, void* pooled, uint8_t* argmax, void* stream);
+int e2e_in_apply_pool_from_slots(const void* raw, const float* stats, int32_t n_slots, float eps, const float* gamma,
+                                 const float* beta, float slope, int32_t B, int32_t Cb, int32_t D, int32_t H, int32_t W,
+                                 int32_t kd, int32_t kh, int32_t kw, float* mean_out, float* rstd_out, void* out, void* pooled,
+                                 uint8_t* argmax, void* stream);
+/* partial: 24*B*Cb*nchunk floats, as e2e_in_bwd */
 int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* argmax, const void* raw, const float* mean,
                     const float* rstd, const float* gamma, const float* beta, float slope, int32_t B, int32_t Cb,
                     int32_t D, int32_t H, int32_t W, int32_t kd, int32_t kh, int32_t kw, float* partial, int32_t nchunk,
@@ -287,9 +298,18 @@ int e2e_sgd_update(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t m
 int e2e_softmax_stats_partial_count(int32_t B, int32_t C, int64_t V);      /* floats of scratch `partial` */
 int e2e_softmax_stats_fwd(const float* logits, const float* target, int32_t B, int32_t C, int64_t V,
                           float* partial, float* stats, float* ce_sum, void* stream);
-/* dlogits = p_k (g_k - sum_j p_j g_j) + gce (p_k - [y==k]),  g_j = gsp[b][j] + gtp[b][j] [y==j]; gce: device scalar */
+/* DC_and_CE_loss from the statistics in one tiny launch (dice_loss.py:155-190, 302-359): loss[0] = weight_ce * ce_sum /
+ * n_vox - weight_dice * mean dc, dc = (2 tp + smooth) / (S_p + S_y + smooth + 1e-8) over (b, c >= (do_bg ? 0 : 1))
+ * (batch_dice: statistics summed over b first), and the coefficients of its gradient: gsp = dloss/dS_p [B][C],
+ * gtp = dloss/dtp [B][C], gce = dloss/dce_sum [1].  n_vox = B * V. */
+int e2e_dc_ce_from_stats(const float* stats, const float* ce_sum, int32_t B, int32_t C, int64_t n_vox, float smooth,
+                         int32_t do_bg, int32_t batch_dice, float weight_ce, float weight_dice, float* loss, float* gsp,
+                         float* gtp, float* gce, void* stream);
+/* dlogits = s * (p_k (g_k - sum_j p_j g_j) + gce (p_k - [y==k])),  g_j = gsp[b][j] + gtp[b][j] [y==j]; gce: device scalar;
+ * s = gscale[0] (device scalar: the upstream gradient of the loss, e.g. a GradScaler's scale) or 1 when gscale is null */
 int e2e_softmax_stats_bwd(const float* logits, const float* target, const float* gsp, const float* gtp,
-                          const float* gce, int32_t B, int32_t C, int64_t V, float* dlogits, void* stream);
+                          const float* gce, const float* gscale, int32_t B, int32_t C, int64_t V, float* dlogits,
+                          void* stream);
 
 /* ---------------------------------------------------------------- sliding-window accumulate */
 /*

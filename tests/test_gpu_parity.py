@@ -376,7 +376,7 @@ def test_stages_vs_torch_same_operands(dev, src, cout, stride, spatial, impl):
     be = torch.from_numpy((0.1 * rs.standard_normal(cout)).astype(np.float32)).to(dev)
     V, Cb = Do * Ho * Wo, cout // 8
     nch = ops._nchunk(V, B * Cb)
-    partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+    partial = torch.empty(B * Cb * nch * 24, dtype=torch.float32, device=dev)
     mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
     rstd = torch.empty_like(mean)
     P = ops._p

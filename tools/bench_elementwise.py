@@ -55,7 +55,7 @@ def main():
         y = torch.empty_like(raw)
         draw = torch.empty_like(raw)
         nch = ops._nchunk(V, B * Cb)
-        partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+        partial = torch.empty(B * Cb * nch * 24, dtype=torch.float32, device=dev)
         mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
         rstd = torch.empty_like(mean)
         sums = torch.empty(B * Cb * 16, dtype=torch.float32, device=dev)

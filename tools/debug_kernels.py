@@ -70,7 +70,7 @@ def check(src, cout, stride, spatial, B=2, seed=0):
     V = Do * Ho * Wo
     Cb = cout // 8
     nch = ops._nchunk(V, B * Cb)
-    partial = torch.empty(B * Cb * nch * 16, dtype=torch.float32, device=dev)
+    partial = torch.empty(B * Cb * nch * 24, dtype=torch.float32, device=dev)
     mean = torch.empty(B * Cb * 8, dtype=torch.float32, device=dev)
     rstd = torch.empty_like(mean)
     P = ops._p
