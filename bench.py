@@ -339,6 +339,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
     _lib.load()
     ops.CONFIG["impl"] = args.kernel_impl
     pools = POOLS["btcv"]
@@ -463,7 +464,7 @@ def run_ours(args):
     line = {
         "metric": "train patches/s", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "E2ENet BTCV-shaped training: batch 2 per GPU, 1x64x160x160, 14 classes, density 0.2, "
                                "SGD nesterov + clip 12 + Masking.step() (BASELINE.json configs[1])",
                    "global_batch": BATCH * world, "parallelism": "dp%d" % world,
@@ -498,6 +499,12 @@ def run_ours(args):
         ts._graph = None
         del ts
         torch.cuda.empty_cache()
+        if args.precision == "bf16":
+            try:
+                line["fp16_mode"] = fp16_mode_leg(dev, data_d, targets_d, args)
+            except Exception as e:                      # noqa: BLE001
+                line["fp16_mode"] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
         line["torch_cudnn_baseline"] = torch_cudnn_baseline(dev)
         tb = line["torch_cudnn_baseline"].get("train_fp16", {})
         if "patches_per_s" in tb:
@@ -512,6 +519,39 @@ def run_ours(args):
     _emit(line)
     if ts is not None:
         _finish_ranks(ts, world)
+
+
+def fp16_mode_leg(dev, data_d, targets_d, args):
+    """the same iteration on the fp16 build of the library (libe2enet_b200_fp16.so: fp16 activations / gradients /
+    packed weights = the reference's shipped AMP arithmetic, with the GradScaler as device state of the fused
+    optimizer): same kernels, same tcgen05 rate -- reported so that the precision option has a measured cost"""
+    import torch
+    from e2enet_medical_b200 import ops
+    from e2enet_medical_b200.training import POOLS, TrainStep
+    ops.set_precision("fp16")
+    try:
+        ts = TrainStep(IN_CH, NCLS, POOLS["btcv"], PATCH, DENSITY, 0.5, 1200, dev, 1, seed=0)
+        for _ in range(3):
+            ts.step(data_d, targets_d)
+        ts.enable_graph(data_d, targets_d, warmup=2)
+        for _ in range(2):
+            ts.step(ts._static_data, ts._static_targets)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            l = ts.step(ts._static_data, ts._static_targets)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out = {"ms_per_step": ms, "patches_per_s": BATCH / (ms / 1e3), "loss": float(l),
+               "loss_scale": float(ts.optimizer.loss_scale()), "skipped_last_step": bool(float(ts.optimizer._norm_coef[2])),
+               "library": "libe2enet_b200_fp16.so", "parity": "profiles/r02_parity_fullsize*.json (fp16 rows)"}
+        ts._graph = None
+        del ts
+        return out
+    finally:
+        ops.set_precision("bf16")
 
 
 def _finish_ranks(ts, world):
@@ -627,6 +667,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel-impl", type=int, default=1, help="0: mma.sync gather kernels, 1: tcgen05 where available")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16"],
+                    help="16-bit type of activations / gradients / packed weights (bf16 = north_star's; fp16 = the reference's AMP)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the Masking-update and stock torch/cuDNN comparator legs")
     ap.add_argument("--no-graph", action="store_true", help="time eager steps only (no whole-step CUDA graph)")

@@ -11,6 +11,12 @@ import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libe2enet_b200.so")
+# storage / operand precision of activations, gradients and packed weights: "bf16" (default, north_star) or "fp16"
+# (the reference's shipped AMP arithmetic; same kernels compiled with -DE2E_FP16, needs a loss scale in training)
+LIB_PATHS = {"bf16": LIB_PATH, "fp16": os.path.join(_PKG, "libe2enet_b200_fp16.so")}
+_precision = os.environ.get("E2E_PRECISION", "bf16")
+if _precision not in LIB_PATHS:
+    raise ValueError("E2E_PRECISION must be one of %s" % sorted(LIB_PATHS))
 
 E2E_MAX_SRC = 4
 
@@ -99,6 +105,7 @@ _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "e2e_last_error": (C.c_char_p, []),
     "e2e_version": (C.c_int, []),
+    "e2e_precision": (C.c_char_p, []),
     "e2e_launch_count": (C.c_longlong, []),
     "e2e_gather_gemm": (C.c_int, [C.POINTER(GemmParams), _VP]),
     "e2e_gather_gemm_multi": (C.c_int, [C.POINTER(GemmParams), _I32, _VP]),
@@ -138,7 +145,7 @@ SIGNATURES = {
     "e2e_mask_grow": (C.c_int, [_VP, _VP, _VP, _I32, _I32, _VP]),
     "e2e_mask_counts": (C.c_int, [_VP, _VP, _I64, _VP, _VP]),
     "e2e_sgd_partial_count": (C.c_int, [_I32, _I64]),
-    "e2e_sgd_clip_coef": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _VP, _VP]),
+    "e2e_sgd_clip_coef": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _VP, _VP, _VP]),
     "e2e_sgd_update": (C.c_int, [_VP, _I32, _I64, _VP, _VP, _I32, _VP]),
     "e2e_softmax_stats_partial_count": (C.c_int, [_I32, _I32, _I64]),
     "e2e_softmax_stats_fwd": (C.c_int, [_VP, _VP, _I32, _I32, _I64, _VP, _VP, _VP, _VP]),
@@ -152,7 +159,7 @@ SIGNATURES = {
     "e2e_window_finalize": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
 }
 
-_lib = None
+_libs = {}
 _lock = threading.Lock()
 
 
@@ -160,25 +167,50 @@ class E2EError(RuntimeError):
     pass
 
 
-def load():
-    """dlopen the CUDA library; raises (never falls back) if it is not built."""
-    global _lib
-    if _lib is not None:
-        return _lib
+def precision() -> str:
+    return _precision
+
+
+def set_precision(name: str):
+    """selects which build of the library the ops use from now on ("bf16" | "fp16").  Call it before building
+    networks / training steps (packed operands and captured graphs belong to one precision); ops.set_precision()
+    is the public wrapper that also invalidates the packed-operand cache."""
+    global _precision
+    if name not in LIB_PATHS:
+        raise ValueError("precision must be one of %s" % sorted(LIB_PATHS))
+    _precision = name
+
+
+def act_dtype():
+    """torch dtype of C8 activations / gradients under the current precision"""
+    import torch
+    return torch.float16 if _precision == "fp16" else torch.bfloat16
+
+
+def load(which: str = None):
+    """dlopen the CUDA library of the current (or the named) precision; raises (never falls back) if it is not built."""
+    which = which or _precision
+    lib = _libs.get(which)
+    if lib is not None:
+        return lib
     with _lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
+        lib = _libs.get(which)
+        if lib is not None:
+            return lib
+        path = LIB_PATHS[which]
+        if not os.path.exists(path):
             raise E2EError(
-                "libe2enet_b200.so is missing (%s). Build it with `python -m e2enet_medical_b200.build`; "
-                "this package has no CPU / eager fallback." % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                "%s is missing (%s). Build it with `python -m e2enet_medical_b200.build`; "
+                "this package has no CPU / eager fallback." % (os.path.basename(path), path))
+        lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)       # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        _lib = lib
-    return _lib
+        if lib.e2e_precision().decode() != which:
+            raise E2EError("%s was built for %s, expected %s" % (path, lib.e2e_precision().decode(), which))
+        _libs[which] = lib
+    return lib
 
 
 def check(rc: int, what: str = ""):
@@ -193,4 +225,6 @@ def stream_ptr():
 
 
 def launch_count() -> int:
-    return int(load().e2e_launch_count())
+    """kernels launched by this process through the C ABI (all loaded precisions)"""
+    load()
+    return sum(int(l.e2e_launch_count()) for l in _libs.values())

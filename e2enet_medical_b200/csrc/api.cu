@@ -20,4 +20,5 @@ void e2e_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed
 
 extern "C" const char* e2e_last_error(void) { return g_err; }
 extern "C" int e2e_version(void) { return 100; }
+extern "C" const char* e2e_precision(void) { return E2E_PRECISION_NAME; }
 extern "C" long long e2e_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -42,7 +42,22 @@ void e2e_count_launch(int n = 1);
     }                                                                              \
   } while (0)
 
-typedef __nv_bfloat16 bf16;
+// 16-bit storage type of activations, gradients and packed weights.  The default build is bf16 (north_star); the
+// same sources compiled with -DE2E_FP16 give libe2enet_b200_fp16.so, whose operands are IEEE fp16 -- the reference's
+// shipped AMP arithmetic (torch.cuda.amp.autocast, nnUNetTrainer_simple.py:552-557) -- at the same tcgen05
+// kind::f16 rate.  fp16 needs a loss scale (training.TrainStep keeps one on the device).
+#ifdef E2E_FP16
+#include <cuda_fp16.h>
+typedef __half act16;
+#define E2E_UMMA_FMT 0u                                      /* instruction-descriptor a/b format: 0 = F16, 1 = BF16 */
+#define E2E_TMAP_ACT CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define E2E_PRECISION_NAME "fp16"
+#else
+typedef __nv_bfloat16 act16;
+#define E2E_UMMA_FMT 1u
+#define E2E_TMAP_ACT CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define E2E_PRECISION_NAME "bf16"
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -71,20 +86,35 @@ __device__ __forceinline__ void ldmatrix_x4_t(uint32_t& r0, uint32_t& r1, uint32
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col)
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+// D(16x8, f32) += A(16x16, act16, row) * B(16x8, act16, col)
+__device__ __forceinline__ void mma_act_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
+#ifdef E2E_FP16
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+#else
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+#endif
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+#ifdef E2E_FP16
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float act_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float act_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float act_round(float x) { return __half2float(__float2half_rn(x)); }
+#else
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float act_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float act_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float act_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+#endif
 
 // streaming 16-byte loads / stores that do not pollute L1
 __device__ __forceinline__ uint4 ld_nc_16(const void* p) {

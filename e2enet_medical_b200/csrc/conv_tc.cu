@@ -61,7 +61,7 @@ struct TcParams {
   // column chunks of one GEMM batched into one launch: work item = (tile, chunk); chunks differ in
   // packed weights, column table and width only (Npad above is the widest: it fixes the geometry)
   int n_chunks;
-  const bf16* wpacked[TC_MAX_CHUNKS];
+  const act16* wpacked[TC_MAX_CHUNKS];
   const e2e_colblk_t* cols[TC_MAX_CHUNKS];
   int npad[TC_MAX_CHUNKS];
   void* dst[E2E_MAX_SRC];
@@ -250,7 +250,6 @@ __device__ __forceinline__ float warp_colsum8(float (&v)[8], int lane) {
   r += __shfl_xor_sync(0xffffffffu, r, 16);
   return r;
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 struct ColInfo {            // one 8-column block of the result, decoded once per CTA
   int32_t off;              // voxel offset of (blk, od, oh, ow) inside one sample of the destination
@@ -356,7 +355,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       int t = work / p.n_chunks;
       const int ch = work - t * p.n_chunks;
       const uint32_t bbytes = (uint32_t)(NT * 2 * 16) * (uint32_t)p.npad[ch];
-      const bf16* wsrc = p.wpacked[ch];
+      const act16* wsrc = p.wpacked[ch];
       const int wt = t % p.tiles_w; t /= p.tiles_w;
       const int ht = t % p.tiles_h; t /= p.tiles_h;
       const int d = t % p.D;
@@ -429,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
     for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
       const int npc = p.npad[work % p.n_chunks];           // width of this column chunk
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=npc, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npc >> 3) << 17) | (8u << 24);
+      const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | ((uint32_t)(npc >> 3) << 17) | (8u << 24);
       const uint64_t bdesc = make_desc(0, npc * 16, 128);
       const uint32_t b_hi = (uint32_t)(bdesc >> 32), b_lo0 = (uint32_t)bdesc;
       const uint32_t b_tap_units = (uint32_t)(2 * npc * 16) >> 4;
@@ -560,7 +559,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
         tc_ld16(acc0 + j * Npad + c0, v);
         if (two) tc_ld16(acc0 + j * Npad + c0 + 16, v + 16);
         // destination of column block u of this chunk (nullptr: nothing to store)
-        auto dst_of = [&](int u) -> bf16* {
+        auto dst_of = [&](int u) -> act16* {
           const ColInfo col = ccols[(c0 >> 3) + u];
           if (!inb || col.dst < 0) return nullptr;
           if (need_bounds) {
@@ -568,11 +567,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             if ((need_bounds & 2) && (unsigned)(hs + col.oh) >= (unsigned)p.Hd) return nullptr;
             if ((need_bounds & 4) && (unsigned)(ws + col.ow) >= (unsigned)p.Wd) return nullptr;
           }
-          return reinterpret_cast<bf16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
+          return reinterpret_cast<act16*>(p.dst[col.dst]) + (size_t)(uint32_t)(tv + col.off + b * col.bstride) * 8;
         };
         // accumulate mode: the values already stored at the destinations are fetched BEFORE the TMEM wait so that
         // their latency overlaps it (issued back to back: no store in between that they could alias)
-        bf16* dps[4] = {nullptr, nullptr, nullptr, nullptr};
+        act16* dps[4] = {nullptr, nullptr, nullptr, nullptr};
         uint4 olds[4];
         if constexpr (do_accum) {
 #pragma unroll
@@ -593,11 +592,11 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
           if constexpr (do_accum) {
             // gradient fan-in: another consumer of this activation already stored its contribution here
             const uint4 old = olds[u];
-            f[0] += bf16_lo(old.x); f[1] += bf16_hi(old.x); f[2] += bf16_lo(old.y); f[3] += bf16_hi(old.y);
-            f[4] += bf16_lo(old.z); f[5] += bf16_hi(old.z); f[6] += bf16_lo(old.w); f[7] += bf16_hi(old.w);
+            f[0] += act_lo(old.x); f[1] += act_hi(old.x); f[2] += act_lo(old.y); f[3] += act_hi(old.y);
+            f[4] += act_lo(old.z); f[5] += act_hi(old.z); f[6] += act_lo(old.w); f[7] += act_hi(old.w);
           }
-          pk[u] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+          pk[u] = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]),
+                             pack_act2(f[6], f[7]));
         }
         if constexpr (do_stats) {
           // sums of the values exactly as stored (the packed bf16), rows outside the grid excluded
@@ -608,7 +607,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             const uint32_t wv[4] = {pk[u].x, pk[u].y, pk[u].z, pk[u].w};
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
-              const float lo = on ? bf16_lo(wv[hh]) : 0.f, hi = on ? bf16_hi(wv[hh]) : 0.f;
+              const float lo = on ? act_lo(wv[hh]) : 0.f, hi = on ? act_hi(wv[hh]) : 0.f;
               t1[u * 8 + 2 * hh] = lo; t1[u * 8 + 2 * hh + 1] = hi;
               t2[u * 8 + 2 * hh] = lo * lo; t2[u * 8 + 2 * hh + 1] = hi * hi;
             }
@@ -629,7 +628,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (u >= 2 && !two) break;
-          bf16* dp;
+          act16* dp;
           if constexpr (do_accum) dp = dps[u]; else dp = dst_of(u);
           if (dp == nullptr) continue;
           const uint4 o = pk[u];
@@ -653,7 +652,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
                   if (m2 == 3) {
                     *reinterpret_cast<uint32_t*>(dp + e) = ow[2 * h2 + q2];
                   } else if (m2) {
-                    const bf16* ov = reinterpret_cast<const bf16*>(&ow[2 * h2 + q2]);
+                    const act16* ov = reinterpret_cast<const act16*>(&ow[2 * h2 + q2]);
                     if (m2 & 1) dp[e] = ov[0];
                     if (m2 & 2) dp[e + 1] = ov[1];
                   }
@@ -730,8 +729,8 @@ struct S3Params {
   int src_cb[E2E_MAX_SRC];
   int dst_cb;
   const e2e_centry_t* cents;
-  const bf16* wpacked;
-  bf16* dst;
+  const act16* wpacked;
+  act16* dst;
   float* stats;                     // see TcParams::stats (slot = blockIdx.x)
   int stats_ctot;
   int stats_smem_off;               // per-warp accumulators [S3_EPI_WARPS][2][Np]
@@ -813,7 +812,7 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
+    const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
     const uint64_t adesc = make_desc(0, S3_SLAB, 128);             // LBO: next 8 channels, SBO: next 8 voxels
     const uint64_t bdesc = make_desc(0, N3 * 16, 128);
     const uint32_t a_hi = (uint32_t)(adesc >> 32), a_lo0 = (uint32_t)adesc;
@@ -967,15 +966,15 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
             o[e] = left + __uint_as_float(v[u][1][e]) + right;
           }
           if (ok) {
-            const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
-                                        pack_bf16x2(o[6], o[7]));
-            bf16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
+            const uint4 pk = make_uint4(pack_act2(o[0], o[1]), pack_act2(o[2], o[3]), pack_act2(o[4], o[5]),
+                                        pack_act2(o[6], o[7]));
+            act16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
             *reinterpret_cast<uint4*>(dp) = pk;
             if (do_stats) {                       // sums of the values exactly as stored (the packed bf16)
               const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
               for (int hh = 0; hh < 4; ++hh) {
-                const float lo = bf16_lo(wv[hh]), hi = bf16_hi(wv[hh]);
+                const float lo = act_lo(wv[hh]), hi = act_hi(wv[hh]);
                 rs[u][2 * hh] += lo;
                 rs[u][2 * hh + 1] += hi;
                 rq[u][2 * hh] = __fmaf_rn(lo, lo, rq[u][2 * hh]);
@@ -1074,8 +1073,8 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
     p.prefetch = pf;
   }
   p.cents = g->cents;
-  p.wpacked = reinterpret_cast<const bf16*>(g->wpacked);
-  p.dst = reinterpret_cast<bf16*>(g->dst[0]);
+  p.wpacked = reinterpret_cast<const act16*>(g->wpacked);
+  p.dst = reinterpret_cast<act16*>(g->dst[0]);
   p.dst_cb = g->dst_cb[0];
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1163,7 +1162,7 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
   p.n_cent = g->n_cent; p.Npad = npmax; p.ivd = g->ivd;
   p.n_chunks = n;
   for (int i = 0; i < n; ++i) {
-    p.wpacked[i] = reinterpret_cast<const bf16*>(gs[i].wpacked);
+    p.wpacked[i] = reinterpret_cast<const act16*>(gs[i].wpacked);
     p.cols[i] = gs[i].cols;
     p.npad[i] = gs[i].Npad;
   }
@@ -1256,7 +1255,7 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
                             (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
       cuuint32_t box[5] = {8, (cuuint32_t)(8 * m * g->isw), (cuuint32_t)(16 * g->ish), 1, 1};
       cuuint32_t estr[5] = {1, (cuuint32_t)g->isw, (cuuint32_t)g->ish, 1, 1};
-      r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+      r = encode(&maps.m[i], E2E_TMAP_ACT, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
@@ -1464,7 +1463,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
       }
     } else if (warp == 1) {
       // D=f32, A=B=bf16, A and B MN-major, N=ncol, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+      const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(ncol >> 3) << 17) | (8u << 24);
       int stage = 0, phase = 0;
       const uint32_t krow_units = (uint32_t)(2 * p.x_rowpitch) >> 4;     // 16 voxels = 2 window rows
@@ -1654,7 +1653,7 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
       }
     } else if (warp == 1) {
       // D=f32, A=B=bf16, A and B MN-major, N = 3*Npad, M=128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+      const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
       int stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
@@ -1903,7 +1902,7 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
                             (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
       cuuint32_t box[5] = {8, (cuuint32_t)(8 * g->isw), (cuuint32_t)(16 * g->ish), 1, 1};
       cuuint32_t estr[5] = {1, (cuuint32_t)g->isw, (cuuint32_t)g->ish, 1, 1};
-      r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
+      r = encode(&maps.x[i], E2E_TMAP_ACT, 5, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }

@@ -12,12 +12,12 @@ constexpr int EW_THREADS = 256;
 constexpr int UNR = 4;            // independent 16-byte vectors in flight per thread and operand
 
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
-  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
-  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+  f[0] = act_lo(v.x); f[1] = act_hi(v.x); f[2] = act_lo(v.y); f[3] = act_hi(v.y);
+  f[4] = act_lo(v.z); f[5] = act_hi(v.z); f[6] = act_lo(v.w); f[7] = act_hi(v.w);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                    pack_bf16x2(f[6], f[7]));
+  return make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]), pack_act2(f[4], f[5]),
+                    pack_act2(f[6], f[7]));
 }
 
 // ------------------------------------------------------------------ layout conversion

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(THREADS, (WN <= 6) ? 2 : 1) gather_gemm_kernel
   const RowInfo my = rows[r];
   const int ibd = my.od * p.isd + p.ivd, ibh = my.oh * p.ish + p.ivh, ibw = my.ow * p.isw + p.ivw;
   const int nk = (p.n_cent >> 1) * p.n_taps;
-  const bf16* wp = reinterpret_cast<const bf16*>(p.wpacked);
+  const act16* wp = reinterpret_cast<const act16*>(p.wpacked);
 
   auto load_stage = [&](int ks, int st) {
     const int pr = ks / p.n_taps, t = ks - pr * p.n_taps;
@@ -67,13 +67,13 @@ __global__ void __launch_bounds__(THREADS, (WN <= 6) ? 2 : 1) gather_gemm_kernel
     const int d = ibd + ce.dd + tp.dd, h = ibh + ce.dh + tp.dh, w = ibw + ce.dw + tp.dw;
     const bool ok = (my.b >= 0) && (unsigned)d < (unsigned)p.Di && (unsigned)h < (unsigned)p.Hi &&
                     (unsigned)w < (unsigned)p.Wi;
-    const bf16* sp = reinterpret_cast<const bf16*>(p.src[ce.src]);
+    const act16* sp = reinterpret_cast<const act16*>(p.src[ce.src]);
     size_t off = 0;
     if (ok) off = ((((size_t)my.b * p.src_cb[ce.src] + ce.blk) * p.Di + d) * p.Hi + h) * (size_t)p.Wi + w;
     cp_async_16(smem_u32(sA + st * 4096 + half * 2048 + r * 16), sp + off * 8, ok ? 16 : 0);
     if (tid < 2 * NT) {
       const int hb = tid / NT, nr = tid - hb * NT;
-      const bf16* ws = wp + (((size_t)ks * 2 + hb) * p.Npad + n0 + nr) * 8;
+      const act16* ws = wp + (((size_t)ks * 2 + hb) * p.Npad + n0 + nr) * 8;
       cp_async_16(smem_u32(sB + st * (NT * 32) + tid * 16), ws, 16);
     }
   };
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, (WN <= 6) ? 2 : 1) gather_gemm_kernel
 #pragma unroll
     for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-      for (int nj = 0; nj < WN; ++nj) mma_bf16_16816(acc[mi][nj], a[mi], b[nj][0], b[nj][1]);
+      for (int nj = 0; nj < WN; ++nj) mma_act_16816(acc[mi][nj], a[mi], b[nj][0], b[nj][1]);
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(THREADS, (WN <= 6) ? 2 : 1) gather_gemm_kernel
       for (int nj = 0; nj < WN; ++nj) {
         const int cb = wn * WN + nj;
         const int row = wm * 32 + mi * 16 + g;
-        *reinterpret_cast<uint32_t*>(sO + (cb * BM + row) * 16 + t4 * 4) = pack_bf16x2(acc[mi][nj][0], acc[mi][nj][1]);
-        *reinterpret_cast<uint32_t*>(sO + (cb * BM + row + 8) * 16 + t4 * 4) = pack_bf16x2(acc[mi][nj][2], acc[mi][nj][3]);
+        *reinterpret_cast<uint32_t*>(sO + (cb * BM + row) * 16 + t4 * 4) = pack_act2(acc[mi][nj][0], acc[mi][nj][1]);
+        *reinterpret_cast<uint32_t*>(sO + (cb * BM + row + 8) * 16 + t4 * 4) = pack_act2(acc[mi][nj][2], acc[mi][nj][3]);
       }
     __syncthreads();
     for (int idx = tid; idx < (NT / 8) * BM; idx += THREADS) {
@@ -154,13 +154,13 @@ __global__ void __launch_bounds__(THREADS, (WN <= 6) ? 2 : 1) gather_gemm_kernel
       if (col.dst < 0 || col.chmask == 0) continue;
       const int d = ri.od * p.osd + col.od, h = ri.oh * p.osh + col.oh, w = ri.ow * p.osw + col.ow;
       if ((unsigned)d >= (unsigned)p.Dd || (unsigned)h >= (unsigned)p.Hd || (unsigned)w >= (unsigned)p.Wd) continue;
-      bf16* dp = reinterpret_cast<bf16*>(p.dst[col.dst]) +
+      act16* dp = reinterpret_cast<act16*>(p.dst[col.dst]) +
                  (((((size_t)ri.b * p.dst_cb[col.dst] + col.blk) * p.Dd + d) * p.Hd + h) * (size_t)p.Wd + w) * 8;
       const uint4 v = *reinterpret_cast<const uint4*>(sO + (size_t)idx * 16);
       if (col.chmask == 0xff) {
         *reinterpret_cast<uint4*>(dp) = v;
       } else {
-        const bf16* vv = reinterpret_cast<const bf16*>(&v);
+        const act16* vv = reinterpret_cast<const act16*>(&v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (col.chmask & (1 << j)) dp[j] = vv[j];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(THREADS, 1) gather_wgrad_kernel(const __grid_c
   if (tile_lo >= tile_hi) return;
 
   const int r = tid & (KT - 1), q = tid >> 6;          // row r, lane group q in 0..3
-  const bf16* gp = reinterpret_cast<const bf16*>(p.grad);
+  const act16* gp = reinterpret_cast<const act16*>(p.grad);
 
   // my 4 slabs (q, q+4, q+8, q+12): decode (cent, tap) once
   int my_dd[4], my_dh[4], my_dw[4], my_src[4], my_blk[4];
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(THREADS, 1) gather_wgrad_kernel(const __grid_c
     for (int nb = q; nb < MT / 8; nb += 4) {
       const int gnb = nrow0 / 8 + nb;
       const bool ok = rv && gnb < p.grad_cb;
-      const bf16* sp = gp + (ok ? (((size_t)b * p.grad_cb + gnb) * Vo + v) * 8 : 0);
+      const act16* sp = gp + (ok ? (((size_t)b * p.grad_cb + gnb) * Vo + v) * 8 : 0);
       cp_async_16(smem_u32(sG + (nb * KT + r) * 16), sp, ok ? 16 : 0);
     }
     const int ibd = od * p.isd + p.ivd, ibh = oh * p.ish + p.ivh, ibw = ow * p.isw + p.ivw;
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) gather_wgrad_kernel(const __grid_c
       const bool ok = rv && my_src[i] >= 0 && (unsigned)d < (unsigned)p.Di && (unsigned)h < (unsigned)p.Hi &&
                       (unsigned)w < (unsigned)p.Wi;
       const int si = ok ? my_src[i] : 0;
-      const bf16* sp = reinterpret_cast<const bf16*>(p.src[si]);
+      const act16* sp = reinterpret_cast<const act16*>(p.src[si]);
       size_t off = 0;
       if (ok) off = ((((size_t)b * p.src_cb[si] + my_blk[i]) * p.Di + d) * p.Hi + h) * (size_t)p.Wi + w;
       cp_async_16(smem_u32(sA + (sl * KT + r) * 16), sp + off * 8, ok ? 16 : 0);
@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(THREADS, 1) gather_wgrad_kernel(const __grid_c
         const int nb = 2 * mt + (mi & 1);
         const int vrow = k16 * 16 + (mi >> 1) * 8 + (lane & 7);
         ldmatrix_x4_t(a[0], a[1], a[2], a[3], g_base + (nb * KT + vrow) * 16);
-        mma_bf16_16816(acc[mt][0], a, b[0][0], b[0][1]);
-        mma_bf16_16816(acc[mt][1], a, b[1][0], b[1][1]);
+        mma_act_16816(acc[mt][0], a, b[0][0], b[0][1]);
+        mma_act_16816(acc[mt][1], a, b[1][0], b[1][1]);
       }
     }
   }
@@ -350,7 +350,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
                                     const int32_t* __restrict__ rowoff, const int32_t* __restrict__ centoff,
                                     const int32_t* __restrict__ tapoff, const int32_t* __restrict__ emask,
                                     const int32_t* __restrict__ rclass, int n_cent, int n_taps, int Npad,
-                                    bf16* __restrict__ out) {
+                                    act16* __restrict__ out) {
   // one thread per (ks, half, n): writes 8 bf16 (16 B)
   const long long total = (long long)n_cent * n_taps * Npad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -379,7 +379,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const float* __
         }
         v[u] = x;
       }
-      o[jj] = pack_bf16x2(v[0], v[1]);
+      o[jj] = pack_act2(v[0], v[1]);
     }
     *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -420,9 +420,9 @@ __global__ void pack_weights_multi_kernel(const e2e_pack_job_t* __restrict__ job
         }
         v[u] = x;
       }
-      o[jj] = pack_bf16x2(v[0], v[1]);
+      o[jj] = pack_act2(v[0], v[1]);
     }
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(jb.out) + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<act16*>(jb.out) + li * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -595,7 +595,7 @@ extern "C" int e2e_pack_weights(const float* w, const float* mask, const int32_t
   int blocks = (int)((total + 255) / 256);
   if (blocks > e2e_num_sms() * 16) blocks = e2e_num_sms() * 16;
   pack_weights_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, mask, rowoff, centoff, tapoff, emask, rclass, n_cent, n_taps, Npad, reinterpret_cast<bf16*>(wpacked));
+      w, mask, rowoff, centoff, tapoff, emask, rclass, n_cent, n_taps, Npad, reinterpret_cast<act16*>(wpacked));
   E2E_LAUNCHED("pack_weights");
   return E2E_OK;
 }

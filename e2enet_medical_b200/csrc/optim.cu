@@ -6,6 +6,10 @@
 // that turns them into the total norm and the clip coefficient ON THE DEVICE (no host read-back), and the
 // update itself, which also applies the DSFF mask to the new weight and momentum.  Hyper-parameters live in a
 // small device array so a captured CUDA graph follows learning-rate changes (poly-LR, :863-877).
+// Optional dynamic loss scale (the reference's GradScaler, :553-562: scale -> unscale_ -> skip the step on inf / nan,
+// halve the scale; double it after `growth_interval` clean steps) as device state scaler[5] = {scale, clean steps,
+// growth interval, backoff factor, growth factor}: gradients are multiplied by 1 / scale on the fly and the state
+// advances inside the coefficient kernel -- no host round trip, so it lives inside a captured graph.
 #include "common.cuh"
 
 namespace {
@@ -14,9 +18,9 @@ constexpr int OPT_THREADS = 256;
 
 // grid (chunks, n_tensors): partial[t * chunks + c] = sum over this block's slice of (g * gscale)^2
 __global__ void __launch_bounds__(OPT_THREADS) sgd_sumsq_kernel(const e2e_sgd_tensor_t* __restrict__ ts, const float* __restrict__ hp,
-                                                                float* __restrict__ partial) {
+                                                                const float* __restrict__ scaler, float* __restrict__ partial) {
   const e2e_sgd_tensor_t t = ts[blockIdx.y];
-  const float gs = hp[4];
+  const float gs = scaler ? hp[4] / scaler[0] : hp[4];
   const long long n = t.numel;
   const long long stride = (long long)gridDim.x * blockDim.x;
   float acc = 0.f;
@@ -43,9 +47,10 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_sumsq_kernel(const e2e_sgd_te
 }
 
 // one block: out[0] = total L2 norm, out[1] = clip coefficient min(1, max_norm / (norm + 1e-6)) (1 if max_norm <= 0),
-// out[2] = 1 if the norm is inf / nan (the update is then skipped, like GradScaler.step does)
+// out[2] = 1 if the norm is inf / nan (the update is then skipped, like GradScaler.step does), out[3] = the gradient
+// multiplier grad_scale / loss_scale this step used; then the loss-scale state advances (GradScaler.update)
 __global__ void __launch_bounds__(1024) sgd_coef_kernel(const float* __restrict__ partial, int n, const float* __restrict__ hp,
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ scaler, float* __restrict__ out) {
   __shared__ double red[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];       // fixed order per thread
@@ -64,6 +69,19 @@ __global__ void __launch_bounds__(1024) sgd_coef_kernel(const float* __restrict_
     out[0] = norm;
     out[1] = coef;
     out[2] = bad ? 1.f : 0.f;
+    out[3] = scaler ? hp[4] / scaler[0] : hp[4];
+    if (scaler) {
+      float sc = scaler[0], clean = scaler[1];
+      if (bad) {
+        sc *= scaler[3];
+        clean = 0.f;
+      } else if (++clean >= scaler[2]) {
+        sc *= scaler[4];
+        clean = 0.f;
+      }
+      scaler[0] = sc;
+      scaler[1] = clean;
+    }
   }
 }
 
@@ -74,7 +92,7 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_update_kernel(const e2e_sgd_t
   if (coef3[2] != 0.f) return;                      // non-finite gradients: skip the step
   const e2e_sgd_tensor_t t = ts[blockIdx.y];
   const float lr = hp[0], mom = hp[1], wd = hp[2];
-  const float gmul = hp[4] * coef3[1];
+  const float gmul = coef3[3] * coef3[1];
   const long long n = t.numel;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.mom | (uintptr_t)t.mask) & 15) == 0);
@@ -120,13 +138,13 @@ extern "C" int e2e_sgd_partial_count(int32_t n_tensors, int64_t max_numel) {
 }
 
 extern "C" int e2e_sgd_clip_coef(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t max_numel, const float* hyper,
-                                 float* partial, float* norm_coef, void* stream) {
+                                 float* scaler, float* partial, float* norm_coef, void* stream) {
   E2E_ARG(tensors && hyper && partial && norm_coef && n_tensors > 0 && max_numel > 0, "sgd_clip_coef: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = opt_chunks(max_numel, n_tensors);
-  sgd_sumsq_kernel<<<dim3(chunks, n_tensors), OPT_THREADS, 0, st>>>(tensors, hyper, partial);
+  sgd_sumsq_kernel<<<dim3(chunks, n_tensors), OPT_THREADS, 0, st>>>(tensors, hyper, scaler, partial);
   E2E_LAUNCHED("sgd_sumsq");
-  sgd_coef_kernel<<<1, 1024, 0, st>>>(partial, chunks * n_tensors, hyper, norm_coef);
+  sgd_coef_kernel<<<1, 1024, 0, st>>>(partial, chunks * n_tensors, hyper, scaler, norm_coef);
   E2E_LAUNCHED("sgd_coef");
   return E2E_OK;
 }

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4
   extern __shared__ float w_s[];                 // [Cb * 8][NC]: w_s[k * NC + c] = bf16(w[c][k]) (0 beyond C / ncls)
   for (int i = threadIdx.x; i < Cb * 8 * NC; i += blockDim.x) {
     const int k = i / NC, c = i - k * NC;
-    w_s[i] = (k < C && c < ncls) ? __bfloat162float(__float2bfloat16_rn(w[c * C + k])) : 0.f;
+    w_s[i] = (k < C && c < ncls) ? act_round(w[c * C + k]) : 0.f;
   }
   __syncthreads();
   const long long P = (long long)px * py * pz;
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4
 #pragma unroll
       for (int q = 0; q < VPT; ++q) {
         const uint4 u = ld_nc_16(x + (long long)cb * P + src[q]);
-        f[q][0] = bf16_lo(u.x); f[q][1] = bf16_hi(u.x); f[q][2] = bf16_lo(u.y); f[q][3] = bf16_hi(u.y);
-        f[q][4] = bf16_lo(u.z); f[q][5] = bf16_hi(u.z); f[q][6] = bf16_lo(u.w); f[q][7] = bf16_hi(u.w);
+        f[q][0] = act_lo(u.x); f[q][1] = act_hi(u.x); f[q][2] = act_lo(u.y); f[q][3] = act_hi(u.y);
+        f[q][4] = act_lo(u.z); f[q][5] = act_hi(u.z); f[q][6] = act_lo(u.w); f[q][7] = act_hi(u.w);
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {

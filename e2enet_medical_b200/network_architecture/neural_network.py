@@ -289,7 +289,7 @@ class SegmentationNetwork(NeuralNetwork):
                 t = torch.stack([torch.flip(tile[i], tuple(a + 1 for a in m)) if m else tile[i] for i, _, m in grp])
             if head_fused:
                 feat, hw = self.e2e_head_features(t)
-                assert feat.dtype == torch.bfloat16 and feat.is_contiguous() and tuple(feat.shape[2:5]) == (px, py, pz)
+                assert feat.dtype == _lib.act_dtype() and feat.is_contiguous() and tuple(feat.shape[2:5]) == (px, py, pz)
                 hw = hw.float().contiguous()
                 Cb, per = feat.shape[1], feat[0].numel() * 2
             else:

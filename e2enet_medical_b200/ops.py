@@ -142,7 +142,7 @@ def _dgrad_into(groups, weight, mask, srcs_of_gemm, src_grid, iter_grid_of, B, t
 
 def c8_shape(x: torch.Tensor):
     B, Cb, D, H, W, e = x.shape
-    assert e == 8 and x.dtype == torch.bfloat16 and x.is_contiguous()
+    assert e == 8 and x.dtype == _lib.act_dtype() and x.is_contiguous()
     return B, Cb, D, H, W
 
 
@@ -155,6 +155,16 @@ _WEIGHT_EPOCH = [0]
 
 def bump_weight_epoch():
     _WEIGHT_EPOCH[0] += 1
+
+
+def set_precision(name: str):
+    """"bf16" (default) or "fp16": the 16-bit type of activations, gradients and packed weights from now on (the
+    library build that serves the calls, _lib.LIB_PATHS).  Packed operands are re-made on their next use; tensors,
+    networks' cached activations and captured CUDA graphs of the other precision must not be reused."""
+    if name != _lib.precision():
+        _lib.set_precision(name)
+        bump_weight_epoch()
+        fanin_reset()
 
 
 class _PackEntry(object):
@@ -238,7 +248,7 @@ def pack_weights(plan: GemmPlan, weight: torch.Tensor, mask: Optional[torch.Tens
     assert w.dtype == torch.float32 and w.is_contiguous()
     if mask is not None:
         assert mask.dtype == torch.float32 and mask.is_contiguous() and mask.shape == w.shape
-    out = torch.empty(plan.packed_numel, dtype=torch.bfloat16, device=weight.device)
+    out = torch.empty(plan.packed_numel, dtype=_lib.act_dtype(), device=weight.device)
     _lib.check(lib.e2e_pack_weights(_p(w), _p(mask), _p(dev["rowoff"]), _p(dev["centoff"]), _p(dev["tapoff"]),
                                     _p(dev.get("emask")), _p(dev.get("rclass")), plan.n_cent, plan.n_taps, plan.Npad,
                                     _p(out), _lib.stream_ptr()), "pack_weights")
@@ -396,7 +406,7 @@ def nc_to_c8(x: torch.Tensor) -> torch.Tensor:
     V = 1
     for s in sp:
         V *= s
-    y = torch.empty((B, (Cc + 7) // 8) + sp + (8,), dtype=torch.bfloat16, device=x.device)
+    y = torch.empty((B, (Cc + 7) // 8) + sp + (8,), dtype=_lib.act_dtype(), device=x.device)
     _lib.check(_lib.load().e2e_nc_to_c8(_p(x), _p(y), B, Cc, V, _lib.stream_ptr()), "nc_to_c8")
     return y
 
@@ -486,7 +496,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         dev = srcs[0].device
         Cb = plan.cout // 8
         impl = CONFIG["impl"]
-        raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=torch.bfloat16, device=dev)
+        raw = torch.empty((B, Cb, Do, Ho, Wo, 8), dtype=_lib.act_dtype(), device=dev)
         # the conv epilogue also reduces the InstanceNorm sums of the values it stores (no separate statistics pass)
         if impl == 1 and plan.fwd3 is not None and CONFIG.get("stack3", True):
             # narrow layer: kw-stacked tcgen05 kernel (N = 3 x Cout per MMA)
@@ -510,7 +520,7 @@ class ShiftConvINLReLU(torch.autograd.Function):
         ctx.pool_k = None
         if pool_k is not None:
             kd, kh, kw = (int(v) for v in pool_k)
-            yp = torch.empty((B, Cb, Do // kd, Ho // kh, Wo // kw, 8), dtype=torch.bfloat16, device=dev)
+            yp = torch.empty((B, Cb, Do // kd, Ho // kh, Wo // kw, 8), dtype=_lib.act_dtype(), device=dev)
             am = torch.empty(yp.shape, dtype=torch.uint8, device=dev)
             if stats is not None:       # mean / rstd are formed from the epilogue's slots inside the same launch
                 _lib.check(lib.e2e_in_apply_pool_from_slots(_p(raw), _p(stats), stats.shape[0], EPS, _p(g32), _p(b32), slope,
@@ -623,7 +633,7 @@ class TConv(torch.autograd.Function):
         B, Cb, D, H, W = c8_shape(x)
         kd, kh, kw = plan.k
         impl = CONFIG["impl"]
-        y = torch.empty((B, plan.cout // 8, D * kd, H * kh, W * kw, 8), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((B, plan.cout // 8, D * kd, H * kh, W * kw, 8), dtype=_lib.act_dtype(), device=x.device)
         run_gemm_chunks(plan.fwd, weight, mask, [x], (D, H, W), (D, H, W), B, [y], (D * kd, H * kh, W * kw),
                         [plan.cout // 8], impl)
         ctx.plan, ctx.mask = plan, mask
@@ -662,7 +672,7 @@ class MaxPool(torch.autograd.Function):
         _need_cuda(x, "maxpool")
         B, Cb, D, H, W = c8_shape(x)
         kd, kh, kw = (int(v) for v in k)
-        y = torch.empty((B, Cb, D // kd, H // kh, W // kw, 8), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((B, Cb, D // kd, H // kh, W // kw, 8), dtype=_lib.act_dtype(), device=x.device)
         am = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
         _lib.check(_lib.load().e2e_maxpool_fwd(_p(x), _p(y), _p(am), B * Cb, D, H, W, kd, kh, kw, _lib.stream_ptr()),
                    "maxpool_fwd")
@@ -677,7 +687,7 @@ class MaxPool(torch.autograd.Function):
         (am,) = ctx.saved_tensors
         B, Cb, D, H, W = ctx.shape
         kd, kh, kw = ctx.k
-        dx = torch.empty((B, Cb, D, H, W, 8), dtype=torch.bfloat16, device=dy.device)
+        dx = torch.empty((B, Cb, D, H, W, 8), dtype=_lib.act_dtype(), device=dy.device)
         _lib.check(_lib.load().e2e_maxpool_bwd(_p(dy.contiguous()), _p(am), _p(dx), B * Cb, D, H, W, kd, kh, kw,
                                                _lib.stream_ptr()), "maxpool_bwd")
         return dx, None

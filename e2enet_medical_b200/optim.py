@@ -137,7 +137,8 @@ class FusedSGD(torch.optim.Optimizer):
     drop-in Masking: `opt.set_masks_from(masking)`).  `grad_scale`: multiplies every gradient first (1 / world
     size for a summed all-reduce, or a loss scaler's inverse)."""
 
-    def __init__(self, params, lr=1e-2, momentum=0.99, weight_decay=3e-5, nesterov=True, max_norm=12.0, grad_scale=1.0):
+    def __init__(self, params, lr=1e-2, momentum=0.99, weight_decay=3e-5, nesterov=True, max_norm=12.0, grad_scale=1.0,
+                 loss_scale=None, growth_interval=2000, backoff_factor=0.5, growth_factor=2.0):
         defaults = dict(lr=lr, momentum=momentum, weight_decay=weight_decay, nesterov=nesterov, dampening=0)
         super().__init__(params, defaults)
         if len(self.param_groups) != 1:
@@ -152,6 +153,10 @@ class FusedSGD(torch.optim.Optimizer):
         self._norm_coef = None
         self._partial = None
         self.last_launches = 0
+        # dynamic loss scale on the device (fp16 precision): the GradScaler of the reference loop, :553-562
+        self._scaler_init = None if loss_scale is None else (float(loss_scale), 0.0, float(growth_interval),
+                                                             float(backoff_factor), float(growth_factor))
+        self._scaler = None
 
     # -------------------------------------------------------------- configuration
     def set_masks(self, masks: Dict[torch.Tensor, torch.Tensor]):
@@ -205,7 +210,7 @@ class FusedSGD(torch.optim.Optimizer):
         if self._hyper is None:
             self._hyper = torch.zeros(5, dtype=torch.float32, device=dev)
             self._hyper_host = torch.zeros(5, dtype=torch.float32).pin_memory()
-            self._norm_coef = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._norm_coef = torch.zeros(4, dtype=torch.float32, device=dev)
 
     def sync_hyper(self):
         """param_groups -> the device hyper-parameter array (call before replaying a graph that captured step())"""
@@ -217,6 +222,20 @@ class FusedSGD(torch.optim.Optimizer):
         h[3] = float(self.max_norm) if self.max_norm is not None else 0.0
         h[4] = self.grad_scale
         self._hyper.copy_(h, non_blocking=True)
+
+    def enable_loss_scale(self, init_scale=65536.0, growth_interval=2000, backoff_factor=0.5, growth_factor=2.0):
+        """GradScaler defaults (torch.cuda.amp.GradScaler(): 2**16, x2 every 2000 clean steps, x0.5 on inf / nan)"""
+        self._scaler_init = (float(init_scale), 0.0, float(growth_interval), float(backoff_factor), float(growth_factor))
+        self._scaler = None
+
+    def loss_scale(self, device=None) -> Optional[torch.Tensor]:
+        """device scalar (a view of the scaler state) the loss is multiplied by before backward(); None = no scaling"""
+        if self._scaler_init is None:
+            return None
+        if self._scaler is None:
+            dev = device if device is not None else self.param_groups[0]['params'][0].device
+            self._scaler = torch.tensor(self._scaler_init, dtype=torch.float32, device=dev)
+        return self._scaler[0]
 
     @property
     def total_norm(self) -> Optional[torch.Tensor]:
@@ -237,8 +256,10 @@ class FusedSGD(torch.optim.Optimizer):
         if not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
         st = _lib.stream_ptr()
-        _lib.check(lib.e2e_sgd_clip_coef(_p(self._table), self._n, self._max_numel, _p(self._hyper), _p(self._partial),
-                                         _p(self._norm_coef), st), "sgd_clip_coef")
+        if self._scaler_init is not None:
+            self.loss_scale(ps[0].device)
+        _lib.check(lib.e2e_sgd_clip_coef(_p(self._table), self._n, self._max_numel, _p(self._hyper), _p(self._scaler),
+                                         _p(self._partial), _p(self._norm_coef), st), "sgd_clip_coef")
         _lib.check(lib.e2e_sgd_update(_p(self._table), self._n, self._max_numel, _p(self._hyper), _p(self._norm_coef),
                                       1 if self.param_groups[0]['nesterov'] else 0, st), "sgd_update")
         from . import ops

@@ -18,6 +18,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import _lib
+
 POOLS = {
     "btcv": [[1, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
     "brats": [[2, 2, 2]] * 5,
@@ -125,9 +127,14 @@ class TrainStep(object):
             from .optim import FusedSGD
             self.optimizer = FusedSGD(self.network.parameters(), 1e-2, momentum=0.99, weight_decay=3e-5, nesterov=True,
                                       max_norm=12.0, grad_scale=1.0 / max(1, world_size))
+            if _lib.precision() == "fp16":
+                # fp16 gradients need the reference loop's loss scaling (GradScaler, nnUNetTrainer_simple.py:553-562);
+                # here it is device state of the fused optimizer, so it also lives inside the captured graph
+                self.optimizer.enable_loss_scale()
         else:
             self.optimizer = torch.optim.SGD(self.network.parameters(), 1e-2, weight_decay=3e-5, momentum=0.99,
                                              nesterov=True)
+            self.amp_grad_scaler = torch.amp.GradScaler("cuda") if _lib.precision() == "fp16" else None
         args = SparseArgs()
         args.update_frequency = update_frequency
         random.seed(seed)
@@ -162,7 +169,7 @@ class TrainStep(object):
         for p in self.network.parameters():
             hooks.append(p.register_post_accumulate_grad_hook(lambda q, order=order: order.append(q)))
         self.optimizer.zero_grad(set_to_none=True)
-        self.loss(self.network(data), targets).backward()
+        self._backward(self.loss(self.network(data), targets))
         for h in hooks:
             h.remove()
         seen = set(id(q) for q in order)
@@ -189,12 +196,27 @@ class TrainStep(object):
             dist.all_reduce(self.arena.bucket(b), group=self.group)
         self._reduced.add(b)
 
+    def _backward(self, l):
+        """backward of the (loss-scaled, under fp16) loss; the scale is a device scalar of the fused optimizer"""
+        sc = self.optimizer.loss_scale(self.device) if self.fused_optimizer else None
+        (l if sc is None else l * sc).backward()
+
     def _device_step(self, data, targets):
         """everything of one iteration that runs on the device (no host synchronisation)"""
         if not self.fused_optimizer:
             self.optimizer.zero_grad()
             output = self.network(data)
             l = self.loss(output, targets)
+            gs = self.amp_grad_scaler
+            if gs is not None:                           # the reference loop's fp16 branch, :552-562
+                gs.scale(l).backward()
+                if self.world_size > 1:
+                    self._allreduce_grads()
+                gs.unscale_(self.optimizer)
+                torch.nn.utils.clip_grad_norm_(self.network.parameters(), 12)
+                gs.step(self.optimizer)
+                gs.update()
+                return l.detach()
             l.backward()
             if self.world_size > 1:
                 self._allreduce_grads()
@@ -208,7 +230,7 @@ class TrainStep(object):
         self.arena.begin_step()
         output = self.network(data)
         l = self.loss(output, targets)
-        l.backward()
+        self._backward(l)
         if self.world_size > 1:
             for b in range(self.arena.n_buckets):        # buckets whose completion the hooks did not see
                 if b not in self._reduced:

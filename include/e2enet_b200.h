@@ -43,6 +43,10 @@ extern "C" {
 
 const char* e2e_last_error(void);
 int e2e_version(void);
+/* "bf16" (libe2enet_b200.so, the default) or "fp16" (libe2enet_b200_fp16.so: the same sources compiled with -DE2E_FP16 --
+ * activations, gradients and packed weights are IEEE fp16, the arithmetic of the reference's torch.cuda.amp loop,
+ * nnUNetTrainer_simple.py:552-557).  Every "bf16" in this header reads "the library's 16-bit type". */
+const char* e2e_precision(void);
 /* number of kernels launched by this library in this process so far (bench: gpu_launches) */
 long long e2e_launch_count(void);
 
@@ -267,9 +271,14 @@ int e2e_mask_counts(const float* mask, uint8_t* fired, int64_t numel, int32_t* n
  * (nnUNetTrainer_simple.py:367-371,560-564; core_channel.py:427-434).  `tensors` is a DEVICE array; hyper is a
  * DEVICE float[5] = {lr, momentum, weight_decay, max_norm (<= 0: no clipping), grad_scale (multiplies every
  * gradient first, e.g. 1/world_size or a GradScaler's inverse scale)} so captured graphs follow LR schedules.
- *   e2e_sgd_clip_coef: norm_coef[0] = ||grad_scale * g||_2 over all tensors, [1] = min(1, max_norm / (norm + 1e-6)),
- *                      [2] = 1 if the norm is not finite; partial: scratch of e2e_sgd_partial_count() floats.
- *   e2e_sgd_update:    g' = g * grad_scale * coef + wd * p;  buf = momentum * buf + g';
+ *   e2e_sgd_clip_coef: norm_coef (float[4]): [0] = ||m * g||_2 over all tensors with m = grad_scale (/ loss scale),
+ *                      [1] = min(1, max_norm / (norm + 1e-6)), [2] = 1 if the norm is not finite, [3] = m;
+ *                      partial: scratch of e2e_sgd_partial_count() floats.  scaler: null, or DEVICE float[5] =
+ *                      {loss scale, clean steps, growth interval, backoff factor, growth factor} -- the reference's
+ *                      GradScaler (nnUNetTrainer_simple.py:553-562) as device state: gradients are un-scaled on the
+ *                      fly, a non-finite norm skips the update and multiplies the scale by the backoff factor,
+ *                      `growth interval` clean steps multiply it by the growth factor.
+ *   e2e_sgd_update:    g' = g * m * coef + wd * p;  buf = momentum * buf + g';
  *                      p = (p - lr * (nesterov ? g' + momentum * buf : buf)) * mask;  buf *= mask   (mask may be null);
  *                      skipped entirely when norm_coef[2] != 0.  Gradients are left unscaled in memory.
  */
@@ -282,7 +291,7 @@ typedef struct {
 } e2e_sgd_tensor_t;
 int e2e_sgd_partial_count(int32_t n_tensors, int64_t max_numel);
 int e2e_sgd_clip_coef(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t max_numel, const float* hyper,
-                      float* partial, float* norm_coef, void* stream);
+                      float* scaler, float* partial, float* norm_coef, void* stream);
 int e2e_sgd_update(const e2e_sgd_tensor_t* tensors, int32_t n_tensors, int64_t max_numel, const float* hyper,
                    const float* norm_coef, int32_t nesterov, void* stream);
 

@@ -9,7 +9,17 @@ import torch.nn.functional as F
 from oracle import network as onet
 
 pytestmark = pytest.mark.gpu
-ULP = 2.0 ** -8
+
+
+def _ulp():
+    """one unit in the last place of the library's 16-bit type relative to the tensor maximum"""
+    from e2enet_medical_b200 import _lib
+    return 2.0 ** -8 if _lib.precision() == "bf16" else 2.0 ** -11
+
+
+def _act():
+    from e2enet_medical_b200 import _lib
+    return _lib.act_dtype()
 
 
 def rel(a, b):
@@ -34,22 +44,22 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     cin = sum(src)
     plan = build_shiftconv_plan(src, cout, (1, 1, 1))
     D, H, W = spatial
-    bf = lambda t: t.bfloat16().float()
+    bf = lambda t: t.to(_act()).float()
     xs = [bf(torch.from_numpy(rs.standard_normal((B, c) + spatial).astype(np.float32))).to(dev) for c in src]
     w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
     xs8 = [ops.nc_to_c8(x) for x in xs]
     wp = ops.pack_weights(plan.fwd, w, None)
     outs = []
     for impl in (0, 1):
-        raw = torch.full((B, cout // 8, D, H, W, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+        raw = torch.full((B, cout // 8, D, H, W, 8), float("nan"), dtype=_act(), device=dev)
         ops.run_gemm(plan.fwd, wp, xs8, (D, H, W), (D, H, W), B, [raw], (D, H, W), [cout // 8], impl)
         torch.cuda.synchronize()
         outs.append(ops.c8_to_nc(raw, cout))
     assert not torch.isnan(outs[1]).any()
     xc = torch.cat(xs, 1).clone().requires_grad_(True)
     ref = F.conv3d(onet.shift_depth(xc), w, None, padding=(0, 1, 1))
-    assert rel(outs[1], ref) < ULP
-    assert rel(outs[1], outs[0]) < ULP
+    assert rel(outs[1], ref) < _ulp()
+    assert rel(outs[1], outs[0]) <= 2 * _ulp()
     # weight gradient: tcgen05 kernel (K = voxels, MN-major operands) vs mma.sync kernel vs torch
     g = bf(torch.from_numpy(rs.standard_normal((B, cout, D, H, W)).astype(np.float32))).to(dev)
     g8 = ops.nc_to_c8(g)
@@ -79,7 +89,7 @@ def test_tcgen05_conv_matches_mma_sync_and_torch(src, cout, spatial, B):
     for o, c in zip(douts, src):
         got = ops.c8_to_nc(o, c)
         assert not torch.isnan(got).any()
-        assert rel(got, xc.grad[:, off:off + c]) < ULP
+        assert rel(got, xc.grad[:, off:off + c]) < _ulp()
         off += c
 
 
@@ -97,7 +107,7 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
     from e2enet_medical_b200.plans import build_tconv_plan
     dev = torch.device("cuda:0")
     rs = np.random.RandomState(7)
-    bf = lambda t: t.bfloat16().float()
+    bf = lambda t: t.to(_act()).float()
     D, H, W = spatial
     fine = (D * k[0], H * k[1], W * k[2])
     x = bf(torch.from_numpy(rs.standard_normal((B, cin) + spatial).astype(np.float32))).to(dev)
@@ -111,7 +121,7 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
     (yr * g).sum().backward()
     res = {}
     for impl in (0, 1):
-        y = torch.full((B, cout // 8) + fine + (8,), float("nan"), dtype=torch.bfloat16, device=dev)
+        y = torch.full((B, cout // 8) + fine + (8,), float("nan"), dtype=_act(), device=dev)
         ops.run_gemm_chunks(plan.fwd, w, None, [x8], spatial, spatial, B, [y], fine, [cout // 8], impl)   # one launch
         dx = torch.full_like(x8, float("nan"))
         ops.run_gemm_chunks(plan.dgrad, w, None, [g8], fine, spatial, B, [dx], spatial, [cin // 8], impl)
@@ -121,8 +131,8 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
     for impl in (0, 1):
         y, dx, gw = res[impl]
         assert not torch.isnan(y).any() and not torch.isnan(dx).any()
-        assert rel(y, yr) < ULP, (impl, rel(y, yr))
-        assert rel(dx, xr.grad) < ULP, (impl, rel(dx, xr.grad))
+        assert rel(y, yr) < _ulp(), (impl, rel(y, yr))
+        assert rel(dx, xr.grad) < _ulp(), (impl, rel(dx, xr.grad))
         assert rel(gw, wr.grad) < 2e-4, (impl, rel(gw, wr.grad))
 
 
@@ -143,17 +153,17 @@ def test_tcgen05_kw_stacked_forward(src, cout, spatial, B):
     plan = build_shiftconv_plan(src, cout, (1, 1, 1))
     assert plan.fwd3 is not None
     D, H, W = spatial
-    bf = lambda t: t.bfloat16().float()
+    bf = lambda t: t.to(_act()).float()
     xs8 = [ops.nc_to_c8(bf(torch.from_numpy(rs.standard_normal((B, c) + spatial).astype(np.float32))).to(dev)) for c in src]
     w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
     Cb = cout // 8
-    a = torch.full((B, Cb, D, H, W, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+    a = torch.full((B, Cb, D, H, W, 8), float("nan"), dtype=_act(), device=dev)
     b_ = torch.full_like(a, float("nan"))
     ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (D, H, W), B, [a], (D, H, W), [Cb], 1)
     ops.run_gemm(plan.fwd3, ops.pack_weights(plan.fwd3, w, None), xs8, (D, H, W), (D, H, W), B, [b_], (D, H, W), [Cb], 1)
     torch.cuda.synchronize()
     assert not torch.isnan(b_.float()).any()
-    assert rel(b_, a) < ULP, rel(b_, a)
+    assert rel(b_, a) <= 2 * _ulp(), rel(b_, a)       # two roundings of sums in different order: one spacing apart
 
 
 @pytest.mark.parametrize("src,cout,stride,spatial,B,use3", [
@@ -179,7 +189,7 @@ def test_fused_epilogue_instancenorm_statistics(src, cout, stride, spatial, B, u
     plan = build_shiftconv_plan(src, cout, stride)
     D, H, W = spatial
     Do, Ho, Wo = plan.out_grid(D, H, W)
-    bf = lambda t: t.bfloat16().float()
+    bf = lambda t: t.to(_act()).float()
     xs8 = [ops.nc_to_c8(bf(torch.from_numpy((rs.standard_normal((B, c) + spatial) + 0.3).astype(np.float32))).to(dev))
            for c in src]
     w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
@@ -189,7 +199,7 @@ def test_fused_epilogue_instancenorm_statistics(src, cout, stride, spatial, B, u
     p = lambda t: C.c_void_p(t.data_ptr())
     res = []
     for rep in range(2):
-        raw = torch.full((B, Cb, Do, Ho, Wo, 8), float("nan"), dtype=torch.bfloat16, device=dev)
+        raw = torch.full((B, Cb, Do, Ho, Wo, 8), float("nan"), dtype=_act(), device=dev)
         stats = ops.run_gemm_chunks(plans, w, None, xs8, (D, H, W), (Do, Ho, Wo), B, [raw], (Do, Ho, Wo), [Cb], 1,
                                     want_stats=True)
         assert stats is not None and stats.shape[1:] == (B, 2, cout), "the tcgen05 launch must fuse the statistics"

@@ -28,6 +28,14 @@ def test_library_loads_and_exports_declared_symbols():
         assert hasattr(lib, name), name
     assert lib.e2e_version() >= 100
     assert lib.e2e_launch_count() == 0          # nothing may launch on import / load
+    assert lib.e2e_precision() == b"bf16" and _lib.precision() == "bf16" and _lib.act_dtype() == torch.bfloat16
+    # the fp16 build (same sources, -DE2E_FP16) exports the same ABI
+    lib16 = _lib.load("fp16")
+    assert lib16 is not lib and lib16.e2e_precision() == b"fp16"
+    for name in declared:
+        assert hasattr(lib16, name), name
+    with pytest.raises(ValueError):
+        _lib.set_precision("fp8")
 
 
 def test_product_has_no_cpu_fallback():
