@@ -25,6 +25,8 @@
 // elementStrides = k and a per-entry start offset).  No halo, one MMA per (K step, sub-tile).
 #include "common.cuh"
 
+#include <type_traits>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -712,17 +714,58 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 // rotate through three 3*Np-column TMEM slots, so the epilogue of one M tile overlaps the MMAs of the
 // next work item.  Packed weights [pair][kh][2][3*Np][8] stay resident in shared memory.
 // =====================================================================================
+// (b, d, ht, wt) of the tiles blockIdx.x, blockIdx.x + G, ... without a division per tile: the stride G is decomposed
+// once and added digit by digit with carries.  The role warps of these kernels are single dependent instruction streams
+// (one elected lane does the work), so the ~6 integer divisions of a tile decode cost several hundred cycles per work
+// item -- measured on conv_tc3 with every load, MMA and epilogue switched off: 1.1 us per item of pure loop overhead.
+struct TileWalk {
+  int wt, ht, d, b, gw, gh, gd, gb, tw, th, D;
+  __device__ __forceinline__ void init(int tile0, int G, int tiles_w, int tiles_h, int D_) {
+    tw = tiles_w; th = tiles_h; D = D_;
+    int t = tile0;
+    wt = t % tw; t /= tw;
+    ht = t % th; t /= th;
+    d = t % D; b = t / D;
+    t = G;
+    gw = t % tw; t /= tw;
+    gh = t % th; t /= th;
+    gd = t % D; gb = t / D;
+  }
+  __device__ __forceinline__ void next() {
+    wt += gw;
+    int c = wt >= tw ? 1 : 0;
+    wt -= c ? tw : 0;
+    ht += gh + c;
+    c = ht >= th ? 1 : 0;
+    ht -= c ? th : 0;
+    d += gd + c;
+    c = d >= D ? 1 : 0;
+    d -= c ? D : 0;
+    b += gb + c;
+  }
+};
+
 constexpr int S3_MT = 2;                            // M tiles (4 rows each) per work item: they share one window
 constexpr int S3_TH = 4 * S3_MT, S3_TW = 32, S3_ADV = 30, S3_ROWS = S3_TH + 2;
 constexpr int S3_SLAB = S3_ROWS * S3_TW * 16;      // 5120 B: [10 rows][32 voxels][8 ch]
 constexpr int S3_PPS = 2;                           // K pairs per pipeline stage (2 * 3 * S3_MT = 12 MMAs)
-constexpr int S3_EPI_WARPS = 8;
-constexpr int S3_THREADS = 64 + 32 * S3_EPI_WARPS;
+#ifndef E2E_S3_EPI_WARPS
+#define E2E_S3_EPI_WARPS 12
+#endif
+constexpr int S3_EPI_WARPS = E2E_S3_EPI_WARPS;      // 3 epilogue warps per scheduler within the 128-register cap of 448 threads
+                                                    // (measured against 8: loc4 forward 0.336 -> 0.333 ms, 48->48 0.269 -> 0.259 ms)
+constexpr int S3_UB = (6 + S3_EPI_WARPS / 4 - 1) / (S3_EPI_WARPS / 4);    // 8-channel blocks per warp when statistics are fused (Np <= 48)
+constexpr int S3_NPROD = 2;                         // TMA producer threads (lane 0 of warps 0 .. S3_NPROD-1), alternating stages
+constexpr int S3_EPI0 = S3_NPROD + S3_MT;           // then S3_MT MMA issuer threads (one per M tile of a work item), then the epilogue
+constexpr int S3_THREADS = 32 * (S3_EPI0 + S3_EPI_WARPS);
 
 struct S3Params {
   int B, D, H, W;
   int n_cent, Np, N3, ivd;          // Np = padded Cout (multiple of 8), N3 = 3 * Np (multiple of 16)
   int prefetch;                     // L2 prefetch distance in tiles of this CTA (0 = off)
+  int seq_mt;                       // 1: one issuer thread per M tile of a work item (E2E_TC3_SEQ=0: one warp issues both, interleaved)
+  int dbg;                          // E2E_TC3_DBG (timing experiments only, results are wrong): 1 = the epilogue only hands the
+                                    // accumulator slots back, 2 = the issuer skips the MMAs, 4 = no TMA loads, 8 = 128-byte aligned boxes
   int stages, acc_stages;
   int tiles_h, tiles_w, n_tiles;
   int b_region_bytes, stage_bytes;
@@ -736,12 +779,20 @@ struct S3Params {
   int stats_smem_off;               // per-warp accumulators [S3_EPI_WARPS][2][Np]
 };
 
+__device__ __forceinline__ void s3_commit(int dbg, uint32_t bar) {
+  if (dbg & 16) mbar_arrive(bar);          // (timing experiment, only meaningful with dbg & 2: a plain arrive instead of tcgen05.commit)
+  else tc_commit(bar);
+}
+
+// FULL: every epilogue warp owns exactly S3_UB 8-channel blocks (Np = 8 * S3_UB * S3_EPI_WARPS / 4 = 48, the layers this
+// kernel mostly serves): one TMEM round trip per M tile and no per-block guards
+template <bool FULL>
 __global__ void __launch_bounds__(S3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_s;
-  __shared__ e2e_centry_t s_cents[MAX_CENT];
+  __shared__ int4 s_box[MAX_CENT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N3 = p.N3, Np = p.Np, S = p.stages, AS = p.acc_stages;
@@ -752,9 +803,12 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
   const uint32_t bfull_bar = smem_u32(&bars[24]);
 
-  for (int i = threadIdx.x; i < p.n_cent; i += blockDim.x) s_cents[i] = p.cents[i];
+  for (int i = threadIdx.x; i < p.n_cent; i += blockDim.x) {
+    const e2e_centry_t ce = p.cents[i];
+    s_box[i] = make_int4(ce.src, ce.dd, ce.blk, p.src_cb[ce.src]);
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.seq_mt ? S3_MT : 1); }
     for (int a = 0; a < AS; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), S3_EPI_WARPS); }
     mbar_init(bfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -771,47 +825,47 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   const uint32_t bbytes = 3u * 2u * 16u * (uint32_t)N3;          // packed weights of one K pair
 
-  if (warp == 0) {
-    // ================================================= TMA producer warp
-    int stage = 0, phase = 0;
-    if (lane == 0 && (int)blockIdx.x < p.n_tiles) {
+  if (warp < S3_NPROD) {
+    // ================================================= TMA producers: ONE thread each (lane 0 of warps 0 .. S3_NPROD-1),
+    // taking the pipeline stages alternately.  A producer is a single dependent instruction stream (wait, expect_tx, per
+    // box: entry lookup, coordinates, UTMALDG from uniform registers); issuing the boxes of a stage "in parallel" from
+    // several lanes compiled to a serial per-lane loop anyway (ELECT / R2UR.BROADCAST / UTMALDG / BRA.U.ANY), and with the
+    // loads alone (E2E_TC3_DBG=3) one producer warp bounded the kernel at 0.14 - 0.18 ms.
+    if (warp == 0 && lane == 0 && (int)blockIdx.x < p.n_tiles) {
       mbar_expect_tx(bfull_bar, bbytes * (uint32_t)npairs);
       for (int pr = 0; pr < npairs; ++pr)
         bulk_copy_g2s(smem_base + pr * bbytes, p.wpacked + (size_t)pr * (bbytes / 2), bbytes, bfull_bar);
     }
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h; t /= p.tiles_h;
-      const int d = t % p.D;
-      const int b = t / p.D;
-      const int h0 = ht * S3_TH, w0 = wt * S3_ADV - 1;
-      const int ptile = tile + p.prefetch * (int)gridDim.x;
-      const bool pf_ok = p.prefetch > 0 && ptile < p.n_tiles;
-      int pt = pf_ok ? ptile : tile;
-      const int pwt = pt % p.tiles_w; pt /= p.tiles_w;
-      const int pht = pt % p.tiles_h; pt /= p.tiles_h;
-      const int pd = pt % p.D, pb = pt / p.D;
-      const int ph0 = pht * S3_TH, pw0 = pwt * S3_ADV - 1;
-      for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
-        const int np = min(S3_PPS, npairs - pr0);
-        if (lane == 0) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), (uint32_t)np * 2u * (uint32_t)S3_SLAB);
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, gs = 0;
+      const uint32_t sa = smem_base + (uint32_t)p.b_region_bytes;
+      TileWalk tw;
+      tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.D);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tw.next()) {
+        const int d = tw.d + p.ivd, b = tw.b;
+        const int h0 = tw.ht * S3_TH - 1, c0 = (tw.wt * S3_ADV - 1) * 4;
+        for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS, ++gs) {
+          if ((int)(gs % (uint32_t)S3_NPROD) == warp) {
+            const int nb = 2 * min(S3_PPS, npairs - pr0);
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (p.dbg & 4) {
+              mbar_arrive(full_bar(stage));                      // (timing experiment: no loads at all)
+            } else {
+              mbar_expect_tx(full_bar(stage), (uint32_t)(nb * S3_SLAB));
+              const uint32_t dst0 = sa + (uint32_t)(stage * p.stage_bytes);
+              for (int k = 0; k < nb; ++k) {
+                const int4 bx = s_box[2 * pr0 + k];              // {source, depth offset, channel block, blocks per sample}
+                tma_load_4d(dst0 + (uint32_t)(k * S3_SLAB), &maps.m[bx.x], full_bar(stage), c0, h0, d + bx.y, b * bx.w + bx.z);
+              }
+            }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (lane < 2 * np) {
-          const e2e_centry_t ce = s_cents[2 * pr0 + lane];
-          tma_load_4d(smem_base + p.b_region_bytes + stage * p.stage_bytes + lane * S3_SLAB, &maps.m[ce.src],
-                      full_bar(stage), w0 * 4, h0 - 1, d + p.ivd + ce.dd, b * p.src_cb[ce.src] + ce.blk);
-          if (pf_ok)                               // same boxes of the tile this CTA processes p.prefetch rounds later
-            tma_prefetch_4d(&maps.m[ce.src], pw0 * 4, ph0 - 1, pd + p.ivd + ce.dd, pb * p.src_cb[ce.src] + ce.blk);
-        }
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ================================================= MMA issuer
+  } else if (warp < S3_EPI0) {
+    // ================================================= MMA issuers
     const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
     const uint64_t adesc = make_desc(0, S3_SLAB, 128);             // LBO: next 8 channels, SBO: next 8 voxels
     const uint64_t bdesc = make_desc(0, N3 * 16, 128);
@@ -822,6 +876,52 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     const uint32_t b_tap_units = (uint32_t)(2 * N3);               // one kh slice of a pair, in 16-byte units
     int stage = 0, phase = 0;
     uint32_t mcount = 0;                       // M tiles issued so far: slot = mcount % AS, phase = (mcount / AS) & 1
+    if (p.seq_mt) {
+      // One issuer THREAD per M tile of a work item (lane 0 of warps 1 and 2).  The issuer is a single dependent
+      // instruction stream -- waits, descriptor arithmetic, MMAs, commits: ~6 cycles per instruction -- and with one warp
+      // issuing both tiles (and electing a lane at every step) that stream, not the tensor pipe, bounded the kernel:
+      // with every load, MMA and epilogue switched off (E2E_TC3_DBG=7) the loop alone took 1.1 us per work item.
+      // The two issuers also decouple the tiles' accumulator slots: tile k waits only for the epilogue of tile k - 3
+      // (3 slots), where the interleaved single issuer needed BOTH slots of the next item before its first MMA.
+      // Both read the same K stages; a stage is released when both have committed (empty barrier count S3_MT).
+      if (lane == 0 && (int)blockIdx.x < p.n_tiles) {
+        const int mt = warp - S3_NPROD;
+        mbar_wait(bfull_bar, 0);
+        tc_fence_after();
+        int slot = mt % AS;
+        uint32_t sphase = (uint32_t)(mt / AS) & 1u;
+        const uint32_t a_mt = a_lo0 + sa0 + (uint32_t)(4 * mt * 32);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+          mbar_wait(tempty_bar(slot), sphase ^ 1u);
+          tc_fence_after();
+          const uint32_t acc = tmem_base + (uint32_t)(slot * N3);
+          uint32_t b_st = b_lo0 + sb0;
+          for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
+            const int np = min(S3_PPS, npairs - pr0);
+            mbar_wait(full_bar(stage), (uint32_t)phase);
+            tc_fence_after();
+            const uint32_t a_st = a_mt + (uint32_t)stage * stage_units;
+#pragma unroll
+            for (int i = 0; i < S3_PPS; ++i) {
+              if (i < np && !(p.dbg & 2)) {
+                const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
+                const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+                  tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
+                                (i + kh) ? 1u : (pr0 ? 1u : 0u));
+              }
+            }
+            s3_commit(p.dbg, empty_bar(stage));
+            b_st += (uint32_t)S3_PPS * 3u * b_tap_units;
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+          s3_commit(p.dbg, tfull_bar(slot));
+          slot += S3_MT;
+          if (slot >= AS) { slot -= AS; sphase ^= 1u; }
+        }
+      }
+    } else if (warp == S3_NPROD) {
     if ((int)blockIdx.x < p.n_tiles) {
       mbar_wait(bfull_bar, 0);
       tc_fence_after();
@@ -846,7 +946,7 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
           const uint32_t b_st = b_lo0 + sb0 + (uint32_t)pr0 * 3u * b_tap_units;
 #pragma unroll
           for (int i = 0; i < S3_PPS; ++i) {      // fully unrolled issue sequence (np <= S3_PPS)
-            if (i < np) {
+            if (i < np && !(p.dbg & 2)) {
               const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
               const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
 #pragma unroll
@@ -858,43 +958,44 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
               }
             }
           }
-          tc_commit(empty_bar(stage));
+          s3_commit(p.dbg, empty_bar(stage));
         }
         __syncwarp();
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
       if (elect_one_sync()) {
 #pragma unroll
-        for (int mt = 0; mt < S3_MT; ++mt) tc_commit(tfull_bar(slot[mt]));
+        for (int mt = 0; mt < S3_MT; ++mt) s3_commit(p.dbg, tfull_bar(slot[mt]));
       }
       __syncwarp();
       mcount += S3_MT;
     }
+    }
   } else {
-    // ================================================= epilogue: 2 warps per TMEM lane quadrant (= tile row),
-    // each takes every other 8-channel block of the result
+    // ================================================= epilogue: S3_EPI_WARPS / 4 warps per TMEM lane quadrant (= tile
+    // row), the warps of a quadrant take the 8-channel blocks of the result round-robin
     const int q = warp & 3;                    // tile row
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - S3_EPI0) >> 2;
     const int nblk = Np >> 3;
     uint32_t mcount = 0;
-    // InstanceNorm statistics: every thread keeps the running sums of ITS voxels' values for the (at most 3) channel
+    // InstanceNorm statistics: every thread keeps the running sums of ITS voxels' values for the (at most S3_UB) channel
     // blocks its warp handles in registers -- no shuffles per tile -- and the lanes / warps are combined only when
     // the sample changes and at the end (host guarantees nblk <= 6 when statistics are requested)
     const bool do_stats = p.stats != nullptr;
     float* wstat_all = reinterpret_cast<float*>(smem + ((smem_base - smem_u32(smem)) + p.stats_smem_off));
-    float* wstat = wstat_all + (warp - 2) * 2 * Np;
+    float* wstat = wstat_all + (warp - S3_EPI0) * 2 * Np;
     float* gslot = do_stats ? p.stats + (size_t)blockIdx.x * p.B * 2 * p.stats_ctot : nullptr;
-    const int et = (int)threadIdx.x - 64;
+    const int et = (int)threadIdx.x - 32 * S3_EPI0;
     constexpr int ethreads = S3_EPI_WARPS * 32;
-    float rs[3][8], rq[3][8];
+    float rs[S3_UB][8], rq[S3_UB][8];
 #pragma unroll
-    for (int u = 0; u < 3; ++u)
+    for (int u = 0; u < S3_UB; ++u)
 #pragma unroll
       for (int e = 0; e < 8; ++e) { rs[u][e] = 0.f; rq[u][e] = 0.f; }
     int sb = -1;
     auto flush_stats = [&](int fb) {
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
+      for (int u = 0; u < S3_UB; ++u) {
         const int cb = grp + u * (S3_EPI_WARPS / 4);
         const float s1 = warp_colsum8(rs[u], lane);
         const float s2 = warp_colsum8(rq[u], lane);
@@ -922,71 +1023,79 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
       for (int c = lane; c < 2 * Np; c += 32) wstat[c] = 0.f;
       asm volatile("bar.sync 1, %0;" ::"n"(ethreads) : "memory");
     }
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h; t /= p.tiles_h;
-      const int d = t % p.D;
-      const int b = t / p.D;
-      const int w = wt * S3_ADV - 1 + lane;
+    TileWalk tw;
+    tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.D);
+    int as = 0;
+    uint32_t aphase = 0;
+    const uint32_t plane8 = (uint32_t)(p.D * p.H * p.W) * 8u;           // elements between consecutive channel blocks
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tw.next()) {
+      const int ht = tw.ht, d = tw.d, b = tw.b;
+      const int w = tw.wt * S3_ADV - 1 + lane;
       if (do_stats && b != sb) {
         if (sb >= 0) flush_stats(sb);
         sb = b;
       }
-     for (int mt = 0; mt < S3_MT; ++mt, ++mcount) {
-      const int as = (int)(mcount % (uint32_t)AS);
-      const uint32_t aphase = (mcount / (uint32_t)AS) & 1u;
+     // voxel index of (b, channel block 0, d, first row of this quadrant, w); + plane per channel block, + 4 W per M tile
+     const uint32_t vox0 = (uint32_t)((((b * p.dst_cb) * p.D + d) * p.H + (ht * S3_TH + q)) * p.W + w);   // (host: < 2^28 voxels)
+     const bool wok = lane >= 1 && lane <= S3_ADV && w < p.W;
+     for (int mt = 0; mt < S3_MT; ++mt) {
       const int h = ht * S3_TH + 4 * mt + q;
-      const bool ok = lane >= 1 && lane <= S3_ADV && h < p.H && w < p.W;
+      const bool ok = wok && h < p.H;
+      const uint32_t off0 = (vox0 + (uint32_t)(4 * mt * p.W)) * 8u;
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N3);
-      constexpr int EB = 3;                      // blocks per TMEM round trip (9 loads in flight)
-      for (int cb0 = grp; cb0 < nblk; cb0 += EB * (S3_EPI_WARPS / 4)) {
-        uint32_t v[EB][3][8];
+      constexpr int EB = S3_UB;                  // blocks per TMEM round trip (3 loads each in flight)
+      constexpr int G = S3_EPI_WARPS / 4;
+      if (!(p.dbg & 1)) {
+        for (int cb0 = grp; cb0 < nblk; cb0 += EB * G) {
+          uint32_t v[EB][3][8];
 #pragma unroll
-        for (int u = 0; u < EB; ++u) {
-          const int cb = cb0 + u * (S3_EPI_WARPS / 4);
-          if (cb < nblk) {
-            tc_ld8(acc + cb * 8, v[u][0]);
-            tc_ld8(acc + Np + cb * 8, v[u][1]);
-            tc_ld8(acc + 2 * Np + cb * 8, v[u][2]);
+          for (int u = 0; u < EB; ++u) {
+            const int cb = cb0 + u * G;
+            if (FULL || cb < nblk) {
+              tc_ld8(acc + cb * 8, v[u][0]);
+              tc_ld8(acc + Np + cb * 8, v[u][1]);
+              tc_ld8(acc + 2 * Np + cb * 8, v[u][2]);
+            }
           }
-        }
-        tc_wait_ld();
+          tc_wait_ld();
 #pragma unroll
-        for (int u = 0; u < EB; ++u) {
-          const int cb = cb0 + u * (S3_EPI_WARPS / 4);
-          if (cb >= nblk) break;
-          float o[8];
+          for (int u = 0; u < EB; ++u) {
+            const int cb = cb0 + u * G;
+            if (!FULL && cb >= nblk) break;
+            float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[u][0][e]), 1);     // D'[w - 1][kw = 0]
-            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[u][2][e]), 1);  // D'[w + 1][kw = 2]
-            o[e] = left + __uint_as_float(v[u][1][e]) + right;
-          }
-          if (ok) {
-            const uint4 pk = make_uint4(pack_act2(o[0], o[1]), pack_act2(o[2], o[3]), pack_act2(o[4], o[5]),
-                                        pack_act2(o[6], o[7]));
-            act16* dp = p.dst + (((((size_t)b * p.dst_cb + cb) * p.D + d) * p.H + h) * (size_t)p.W + w) * 8;
-            *reinterpret_cast<uint4*>(dp) = pk;
-            if (do_stats) {                       // sums of the values exactly as stored (the packed bf16)
-              const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
+            for (int e = 0; e < 8; ++e) {
+              const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[u][0][e]), 1);     // D'[w - 1][kw = 0]
+              const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[u][2][e]), 1);  // D'[w + 1][kw = 2]
+              o[e] = left + __uint_as_float(v[u][1][e]) + right;
+            }
+            if (ok) {
+              const uint4 pk = make_uint4(pack_act2(o[0], o[1]), pack_act2(o[2], o[3]), pack_act2(o[4], o[5]),
+                                          pack_act2(o[6], o[7]));
+              *reinterpret_cast<uint4*>(p.dst + (off0 + (uint32_t)cb * plane8)) = pk;
+              if (do_stats) {                       // sums of the values exactly as stored (the packed 16-bit values)
+                const uint32_t wv[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-              for (int hh = 0; hh < 4; ++hh) {
-                const float lo = act_lo(wv[hh]), hi = act_hi(wv[hh]);
-                rs[u][2 * hh] += lo;
-                rs[u][2 * hh + 1] += hi;
-                rq[u][2 * hh] = __fmaf_rn(lo, lo, rq[u][2 * hh]);
-                rq[u][2 * hh + 1] = __fmaf_rn(hi, hi, rq[u][2 * hh + 1]);
+                for (int hh = 0; hh < 4; ++hh) {
+                  const float lo = act_lo(wv[hh]), hi = act_hi(wv[hh]);
+                  rs[u][2 * hh] += lo;
+                  rs[u][2 * hh + 1] += hi;
+                  rq[u][2 * hh] = __fmaf_rn(lo, lo, rq[u][2 * hh]);
+                  rq[u][2 * hh + 1] = __fmaf_rn(hi, hi, rq[u][2 * hh + 1]);
+                }
               }
             }
           }
+          if (FULL) break;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (++as == AS) { as = 0; aphase ^= 1u; }
      }
     }
     if (do_stats && sb >= 0) flush_stats(sb);
@@ -1031,6 +1140,7 @@ int e2e_conv_tc_supported(const e2e_gemm_t* p) {
     if (p->ivh != 0 || p->ivw != 0 || p->Do != p->Di || p->Ho != p->Hi || p->Wo != p->Wi) return 0;
     if (p->Dd != p->Di || p->Hd != p->Hi || p->Wd != p->Wi || p->n_dst != 1) return 0;
     if (p->Npad % 48 != 0 || p->Npad > 240) return 0;
+    if ((long long)p->B * p->dst_cb[0] * p->Dd * p->Hd * (long long)p->Wd >= (1ll << 28)) return 0;   // 32-bit element offsets in the epilogue
     const int region = ((p->n_cent / 2) * 3 * 2 * 16 * p->Npad + 1023) / 1024 * 1024;
     if (region + 3 * S3_PPS * 2 * S3_SLAB + S3_EPI_WARPS * 2 * (p->Npad / 3) * 4 + 128 > SMEM_BUDGET) return 0;   // resident weights + 3 stages + statistics
     return 3;
@@ -1057,12 +1167,17 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   {
     int grid0 = e2e_num_sms();
     if (grid0 > p.n_tiles) grid0 = p.n_tiles;
-    const bool can_stats = (p.Np >> 3) <= 3 * (S3_EPI_WARPS / 4);       // register accumulators: <= 3 blocks per warp
+    const bool can_stats = (p.Np >> 3) <= S3_UB * (S3_EPI_WARPS / 4);   // register accumulators: <= S3_UB blocks per warp
     if (slots_out) { *slots_out = can_stats ? grid0 : 0; return E2E_OK; }
     if (g->stats && !can_stats) {
-      e2e_set_error("conv_tc3: fused statistics support at most %d output channels", 8 * 3 * (S3_EPI_WARPS / 4));
+      e2e_set_error("conv_tc3: fused statistics support at most %d output channels", 8 * S3_UB * (S3_EPI_WARPS / 4));
       return E2E_ERR_UNSUPPORTED;
     }
+  }
+  {
+    static int seq = -1;
+    if (seq < 0) { const char* e = getenv("E2E_TC3_SEQ"); seq = e ? atoi(e) : 1; }
+    p.seq_mt = seq ? 1 : 0;
   }
   p.stats = g->stats;
   p.stats_ctot = g->stats_ctot;
@@ -1071,6 +1186,9 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("E2E_TC_PREFETCH"); pf = e ? atoi(e) : 0; }   // measured: 0.34 -> 0.44 ms with prefetch on (the TMA unit, not latency, is the limit)
     p.prefetch = pf;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("E2E_TC3_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
   }
   p.cents = g->cents;
   p.wpacked = reinterpret_cast<const act16*>(g->wpacked);
@@ -1097,13 +1215,19 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   static E2eDevOnce attr_once;
   if (attr_once.first()) {
     cudaFuncAttributes fa;
-    E2E_CUDA(cudaFuncGetAttributes(&fa, conv_tc3_kernel));
-    E2E_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    E2E_CUDA(cudaFuncGetAttributes(&fa, conv_tc3_kernel<true>));
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024 - (int)fa.sharedSizeBytes));
+    E2E_CUDA(cudaFuncGetAttributes(&fa, conv_tc3_kernel<false>));
+    E2E_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   227 * 1024 - (int)fa.sharedSizeBytes));
   }
   int grid = e2e_num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  conv_tc3_kernel<<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);
+  if ((p.Np >> 3) == S3_UB * (S3_EPI_WARPS / 4))
+    conv_tc3_kernel<true><<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);
+  else
+    conv_tc3_kernel<false><<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("conv_tc3");
   return E2E_OK;
 }

@@ -37,11 +37,33 @@ TCONVS = [  # name, cin, cout, k, input (D,H,W), count
 ]
 
 
+GRAPH = [os.environ.get("E2E_BENCH_GRAPH", "1") != "0"]
+
+
 def timeit(fn, iters):
+    """device time per call.  The calls are captured into ONE CUDA graph and replayed (default): a launch through the
+    C ABI costs ~0.1 ms of host time (tensor-map encodes, ctypes), which would otherwise bound every kernel shorter
+    than that -- in the real step the whole iteration is a graph too."""
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if GRAPH[0]:
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(iters):
+                    fn()
+        torch.cuda.current_stream().wait_stream(s)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
     e0.record()
     for _ in range(iters):
         fn()
