@@ -838,15 +838,16 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
     }
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0, gs = 0;
+      uint32_t phase = 0;
       const uint32_t sa = smem_base + (uint32_t)p.b_region_bytes;
       TileWalk tw;
       tw.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h, p.D);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tw.next()) {
         const int d = tw.d + p.ivd, b = tw.b;
         const int h0 = tw.ht * S3_TH - 1, c0 = (tw.wt * S3_ADV - 1) * 4;
-        for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS, ++gs) {
-          if ((int)(gs % (uint32_t)S3_NPROD) == warp) {
+        for (int pr0 = 0; pr0 < npairs; pr0 += S3_PPS) {
+          if (stage % S3_NPROD == warp) {        // a stage index always has the same producer: mbarrier parity waits tell
+                                                 // only one phase from the next, so nobody may wait two phases ahead
             const int nb = 2 * min(S3_PPS, npairs - pr0);
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (p.dbg & 4) {
@@ -1699,7 +1700,10 @@ struct WgsParams {
 constexpr int GS_TH = 8;                    // tile rows
 constexpr int GS_WROWS = GS_TH + 2;         // gradient window rows (H halo)
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+constexpr int GS_NPROD = 3;                 // TMA producer threads; then one MMA issuer thread, then 4 epilogue warps
+constexpr int GS_THREADS = 32 * (GS_NPROD + 1 + 4);
+
+__global__ void __launch_bounds__(GS_THREADS, 1)
 wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[20];
@@ -1744,52 +1748,64 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
   if (my_tiles > 0) {
-    if (warp == 0) {
-      // producer WARP: lane 0 waits for the stage and arms the barrier, then lanes 0..ne-1 issue the x
-      // boxes and lanes 16..18 the three gradient copies in parallel (19 TMA issues from one thread
-      // per 64-voxel tile could not keep up with 12 MMAs)
-      int stage = 0, phase = 0;
-      const uint32_t tx = (uint32_t)ne * (uint32_t)(GS_TH * 128) + 3u * (uint32_t)(Npad >> 3) * (uint32_t)p.g_slab_bytes;
-      e2e_centry_t ce = s_cents[lane < ne ? lane : 0];
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        int t = tile;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h; t /= p.tiles_h;
-        const int d = t % p.D;
-        const int b = t / p.D;
-        const int h0 = ht * GS_TH, w0 = wt * 8;
-        if (lane == 0) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), tx);
-        }
-        __syncwarp();
-        const uint32_t sx = smem_base + stage * p.stage_bytes;
-        if (lane < ne) {
-          tma_load_4d(sx + lane * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), w0 * 4, h0, d + p.ivd + ce.dd,
-                      b * p.src_cb[ce.src] + ce.blk);
-        } else if (lane >= 16 && lane < 19) {
-          // three kw-shifted copies of the haloed gradient window: copy kw holds g[., w - (kw - 1)]
-          const int kw = lane - 16;
-          tma_load_4d(sx + p.x_bytes + kw * (Npad >> 3) * p.g_slab_bytes, &maps.g, full_bar(stage),
-                      (w0 - (kw - 1)) * 4, h0 - 1, d, b * p.grad_cb);
-        }
-        if (++stage == S) { stage = 0; phase ^= 1; }
-      }
-    } else if (warp == 1) {
-      // D=f32, A=B=bf16, A and B MN-major, N = 3*Npad, M=128
-      const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
-      int stage = 0, phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
-        if (elect_one_sync()) {
+    if (warp < GS_NPROD) {
+      // TMA producers: ONE thread each (lane 0 of warps 0 .. GS_NPROD-1); the ne x boxes and 3 gradient boxes of a
+      // tile are dealt round-robin to them.  (Issuing the 19 boxes "in parallel" from 19 lanes of one warp compiles to
+      // a serial per-lane ELECT / R2UR / UTMALDG loop: ~1500 cycles per 64-voxel tile against 860 cycles of MMAs.)
+      // Producer 0 arms the barrier with the bytes of ALL boxes; the others' bytes may land first (the transaction
+      // count goes negative until the expect arrives, the phase cannot complete before that one pending arrival).
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = (uint32_t)ne * (uint32_t)(GS_TH * 128) + 3u * (uint32_t)(Npad >> 3) * (uint32_t)p.g_slab_bytes;
+        int t = tile_lo;
+        int wt = t % p.tiles_w; t /= p.tiles_w;
+        int ht = t % p.tiles_h; t /= p.tiles_h;
+        int d = t % p.D, b = t / p.D;
+        const int nb = ne + 3;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+          const int h0 = ht * GS_TH, w0 = wt * 8;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (warp == 0) mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sx = smem_base + stage * p.stage_bytes;
-          const uint32_t sg = sx + p.x_bytes;
-          const uint64_t a0 = make_desc(sx, 128, p.x_slab_bytes);
-          const uint64_t b0 = make_desc(sg, 128, p.g_slab_bytes);
-          const uint32_t a_hi = (uint32_t)(a0 >> 32), b_hi = (uint32_t)(b0 >> 32);
-          const uint32_t a_lo0 = (uint32_t)a0, b_lo0 = (uint32_t)b0;
+          for (int k = warp; k < nb; k += GS_NPROD) {
+            if (k < ne) {
+              const e2e_centry_t ce = s_cents[k];
+              tma_load_4d(sx + k * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), w0 * 4, h0, d + p.ivd + ce.dd,
+                          b * p.src_cb[ce.src] + ce.blk);
+            } else {
+              // three kw-shifted copies of the haloed gradient window: copy kw holds g[., w - (kw - 1)]
+              const int kw = k - ne;
+              tma_load_4d(sx + p.x_bytes + kw * (Npad >> 3) * p.g_slab_bytes, &maps.g, full_bar(stage),
+                          (w0 - (kw - 1)) * 4, h0 - 1, d, b * p.grad_cb);
+            }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++wt == p.tiles_w) {
+            wt = 0;
+            if (++ht == p.tiles_h) {
+              ht = 0;
+              if (++d == p.D) { d = 0; ++b; }
+            }
+          }
+        }
+      }
+    } else if (warp == GS_NPROD) {
+      // MMA issuer: one thread.  D=f32, A=B=the 16-bit type, A and B MN-major, N = 3*Npad, M=128
+      if (lane == 0) {
+        const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | (1u << 15) | (1u << 16) |
+                               ((uint32_t)(N3 >> 3) << 17) | (8u << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint64_t a00 = make_desc(smem_base, 128, p.x_slab_bytes);
+        const uint64_t b00 = make_desc(smem_base + p.x_bytes, 128, p.g_slab_bytes);
+        const uint32_t a_hi = (uint32_t)(a00 >> 32), b_hi = (uint32_t)(b00 >> 32);
+        const uint32_t stage_units = (uint32_t)p.stage_bytes >> 4;
+        for (int it = 0; it < my_tiles; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_lo0 = (uint32_t)a00 + (uint32_t)stage * stage_units;
+          const uint32_t b_lo0 = (uint32_t)b00 + (uint32_t)stage * stage_units;
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -1799,12 +1815,10 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
                             b_lo0 + (uint32_t)((2 * k + 2 - kh) * 8), b_hi, idesc, (it | k) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));
+          if (++stage == S) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        tc_commit(done_bar);
       }
-      if (elect_one_sync()) tc_commit(done_bar);
-      __syncwarp();
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;             // accumulator row = (entry r/8, channel r%8)
@@ -1924,7 +1938,7 @@ static int wgrad_gshift_launch(const e2e_wgrad_t* g, PFN_cuTensorMapEncodeTiled_
   if (attr_once.first()) {
     E2E_CUDA(cudaFuncSetAttribute(wgrad_gshift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
   }
-  wgrad_gshift_kernel<<<p.n_groups * p.splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+  wgrad_gshift_kernel<<<p.n_groups * p.splits, GS_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("wgrad_gshift");
   return E2E_OK;
 }
