@@ -18,11 +18,12 @@ from .plans import GemmPlan, SegHeadPlan, ShiftConvPlan, TConvPlan
 EPS = 1e-5
 # 0: mma.sync gather kernels everywhere; 1: tcgen05/TMA kernel where a layer qualifies
 CONFIG = {"impl": 1, "stack3": True, "fuse_pool": True, "fuse_stats": True, "fuse_fanin": True, "wgrad_direct": False,
-          "in_bwd_plane": False}
+          "in_bwd_plane": False, "wgrad_side_stream": True}
 # A/B switches for measurements (tools/, bench.py): E2E_FUSE_STATS=0 / E2E_FUSE_FANIN=0 / E2E_FUSE_POOL=0 / E2E_STACK3=0
 import os as _os
 for _k, _e in (("fuse_stats", "E2E_FUSE_STATS"), ("fuse_fanin", "E2E_FUSE_FANIN"), ("fuse_pool", "E2E_FUSE_POOL"),
-               ("stack3", "E2E_STACK3"), ("wgrad_direct", "E2E_WGRAD_DIRECT"), ("in_bwd_plane", "E2E_IN_BWD_PLANE")):
+               ("stack3", "E2E_STACK3"), ("wgrad_direct", "E2E_WGRAD_DIRECT"), ("in_bwd_plane", "E2E_IN_BWD_PLANE"),
+               ("wgrad_side_stream", "E2E_WGRAD_SIDE")):
     if _os.environ.get(_e) is not None:
         CONFIG[_k] = _os.environ[_e] not in ("0", "false", "False")
 # optional per-launch CUDA-event timing of the GEMM kernels (bench.py roofline): records are
@@ -64,6 +65,59 @@ class _Timed(object):
 
 def _p(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------- side stream of the backward pass
+# A layer's weight gradient feeds nothing but the optimizer (and the data-parallel all-reduce), while its data gradient is
+# on the critical path: dgrad(L) -> InstanceNorm backward(L-1) -> dgrad(L-1) ...  The weight-gradient GEMMs are tensor-bound,
+# the InstanceNorm backward kernels HBM-bound and small enough to share an SM with a GEMM CTA, so the weight gradients of a
+# training step (trainer-installed gradient arena only: nothing else may touch the slot before the join) are launched on a
+# second stream and overlap the norm kernels of the layers below.  Everything the side stream reads (the raw-output gradient
+# and the saved layer inputs) is kept referenced until `side_join()` -- the caching allocator would otherwise hand the
+# blocks to later main-stream kernels while the side stream still reads them; inside a CUDA-graph capture the fork / join
+# become graph edges.
+_SIDE = {"stream": {}, "keep": [], "dirty": False}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    st = _SIDE["stream"].get(str(device))
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE["stream"][str(device)] = st
+    return st
+
+
+class _SideSection(object):
+    """with _SideSection(device, *tensors_read): launches inside go to the side stream, ordered after everything enqueued
+    on the current stream so far"""
+
+    def __init__(self, device, *keep):
+        self.side = side_stream(device)
+        _SIDE["keep"].append(keep)
+
+    def __enter__(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.side.wait_event(ev)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        _SIDE["dirty"] = True
+
+    def __exit__(self, *a):
+        self.ctx.__exit__(*a)
+
+
+def side_pending() -> bool:
+    return _SIDE["dirty"]
+
+
+def side_join():
+    """the current stream waits for the side stream; the tensors kept for it are released"""
+    if _SIDE["dirty"]:
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(side_stream(cur.device))
+        _SIDE["dirty"] = False
+    _SIDE["keep"].clear()
 
 
 def _need_cuda(t: torch.Tensor, what: str):
@@ -606,8 +660,14 @@ class ShiftConvINLReLU(torch.autograd.Function):
         gw = None
         if ctx.needs_input_grad[2]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step,
-                           scratch_from=arena)
+            fresh = arena is not None and arena.zeroed_this_step
+            if fresh and CONFIG["wgrad_side_stream"]:
+                with _SideSection(draw.device, draw, *srcs):
+                    gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot,
+                                   out_is_zero=True, scratch_from=arena)
+            else:
+                gw = run_wgrad(plan.wgrad, srcs, (D, H, W), (Do, Ho, Wo), B, draw, tuple(weight.shape), impl, out=slot,
+                               out_is_zero=fresh, scratch_from=arena)
             if arena is not None:
                 arena.mark_ready(weight)
         # data gradients of every source
@@ -654,8 +714,14 @@ class TConv(torch.autograd.Function):
         gw = dx = None
         if ctx.needs_input_grad[1]:
             arena, slot = _grad_slot(weight)
-            gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=arena is not None and arena.zeroed_this_step,
-                           scratch_from=arena)
+            fresh = arena is not None and arena.zeroed_this_step
+            if fresh and CONFIG["wgrad_side_stream"]:
+                with _SideSection(dy.device, dy, x):
+                    gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=True,
+                                   scratch_from=arena)
+            else:
+                gw = run_wgrad(plan.wgrad, [dy], fine, (D, H, W), B, x, tuple(weight.shape), impl, out=slot, out_is_zero=fresh,
+                               scratch_from=arena)
             if arena is not None:
                 arena.mark_ready(weight)
         if ctx.needs_input_grad[3]:

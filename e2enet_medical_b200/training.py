@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib
+from . import _lib, ops
 
 POOLS = {
     "btcv": [[1, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2], [2, 2, 2]],
@@ -191,8 +191,14 @@ class TrainStep(object):
         import torch.distributed as dist
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
+        ev_side = None
+        if ops.side_pending():                      # weight gradients of this bucket may still be running on the side stream
+            ev_side = torch.cuda.Event()
+            ev_side.record(ops.side_stream(self.device))
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(ev)
+            if ev_side is not None:
+                self._comm.wait_event(ev_side)
             dist.all_reduce(self.arena.bucket(b), group=self.group)
         self._reduced.add(b)
 
@@ -231,6 +237,7 @@ class TrainStep(object):
         output = self.network(data)
         l = self.loss(output, targets)
         self._backward(l)
+        ops.side_join()                       # weight gradients launched on the side stream (ops._SideSection)
         if self.world_size > 1:
             for b in range(self.arena.n_buckets):        # buckets whose completion the hooks did not see
                 if b not in self._reduced:
@@ -282,7 +289,10 @@ class TrainStep(object):
         self.optimizer.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph):
+        # the iteration is captured on a HIGH-priority stream: the weight-gradient GEMMs forked to ops' side stream (default
+        # priority) then yield the SMs to the data-gradient chain whenever both are ready
+        hi = torch.cuda.Stream(device=self.device, priority=-1)
+        with torch.cuda.graph(graph, stream=hi):
             self._static_loss = self._device_step(self._static_data, self._static_targets)
             if not self.fused_optimizer:
                 self.mask.apply_mask()
