@@ -250,6 +250,7 @@ class TrainStep(object):
                                        "bucketed all-reduce would miss it")
             self._arena_checked = True
         self.optimizer.step()                 # clip + Nesterov SGD + apply_mask, three launches
+        self.arena.zeroed_this_step = False   # a further backward before the next begin_step() must not assume empty slots
         return l.detach()
 
     _arena_checked = False
