@@ -192,3 +192,28 @@ def test_fp16_reference_loop_autocast_gradscaler(fp16, reference_names):
     here the GradScaler's scaled loss really flows through fp16 gradients, as in the reference"""
     import test_gpu_boundary as TB
     TB.test_reference_loop_through_aliases(reference_names)
+
+
+def test_fp16_sliding_window_inference(fp16):
+    """config 3's path on the fp16 library: predict_3D (Gaussian, step 0.5, head folded into the accumulate kernel)
+    agrees with the bf16 library to the precision of the two formats and returns normalised probabilities"""
+    from e2enet_medical_b200 import ops
+    from e2enet_medical_b200.network_architecture.unetpp_d import softmax_helper
+    from e2enet_medical_b200.training import POOLS, build_network
+    dev = fp16
+    pools, patch, ncls = POOLS["btcv"], (32, 64, 64), 5
+    vol = np.random.RandomState(0).randn(1, 40, 90, 100).astype(np.float32)
+    res = {}
+    for prec in ("fp16", "bf16"):
+        ops.set_precision(prec)
+        torch.manual_seed(0)
+        net = build_network(1, ncls, pools, patch, 16, deep_supervision=True).to(dev).eval()
+        net.do_ds = False
+        net.inference_apply_nonlin = softmax_helper
+        seg, probs = net.predict_3D(vol, False, (0, 1, 2), True, 0.5, patch, None, True, "constant", None, False, False, True)
+        assert probs.shape == (ncls,) + vol.shape[1:] and seg.shape == vol.shape[1:]
+        assert np.isfinite(probs).all() and float(np.abs(probs.sum(0) - 1).max()) < 1e-4
+        res[prec] = (seg, probs)
+    ops.set_precision("fp16")
+    assert float(np.abs(res["fp16"][1] - res["bf16"][1]).max()) < 0.1
+    assert float((res["fp16"][0] == res["bf16"][0]).mean()) > 0.97
