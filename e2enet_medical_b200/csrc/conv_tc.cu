@@ -50,6 +50,7 @@ struct TcParams {
   int serial_prod;                 // halo form: one thread issues all TMA ops of a stage (A/B test)
   int pps;                         // K pairs (16 channels each) per pipeline stage
   int poll;                        // E2E_TC_POLL: 0 all lanes poll, 1 one lane, 2 one lane + backoff
+  int dbg;                         // E2E_TC_DBG (timing experiments, results wrong): 1 = no epilogue work, 2 = no MMAs
   int b_res;                       // packed weights of the CTA's (fixed) column chunk stay resident in smem
   int b_region_bytes;              // size of that region (then the A stages follow)
   int n_cent, Npad, m, stages, acc_stages;
@@ -78,6 +79,12 @@ struct TcParams {
 
 struct alignas(64) TcMaps {
   CUtensorMap m[E2E_MAX_SRC];
+};
+// conv_tc3: m2 = the same tensors with a box of TWO consecutive 8-channel blocks (two adjacent K entries of one source
+// with the same depth offset are fetched by one TMA instruction; the producer thread is an instruction stream)
+struct alignas(64) S3Maps {
+  CUtensorMap m[E2E_MAX_SRC];
+  CUtensorMap m2[E2E_MAX_SRC];
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -451,6 +458,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
             const uint32_t first = pr ? 1u : 0u;
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
+              if (p.dbg & 2) break;
 #pragma unroll
               for (int j = 0; j < MS; ++j)
                 tc_mma_f16_lh(acc0 + (uint32_t)(j * Npad), a_lo + tapu[t] + (uint32_t)(j * 8), a_hi,
@@ -550,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcMap
       mbar_wait_warp(tfull_bar(as), aphase, 64, p.poll);
       tc_fence_after();
       const uint32_t acc0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * MS * Npad);
-      for (int ci = grp; ci < MS * nchunk; ci += (epi_warps >> 2)) {
+      for (int ci = (p.dbg & 1) ? MS * nchunk : grp; ci < MS * nchunk; ci += (epi_warps >> 2)) {
         const int j = ci / nchunk, c0 = (ci - j * nchunk) << 5;
         const int w = (wt * MS + j) * 8 + (r & 7);
         const int ws = w * p.osw;
@@ -763,6 +771,7 @@ struct S3Params {
   int B, D, H, W;
   int n_cent, Np, N3, ivd;          // Np = padded Cout (multiple of 8), N3 = 3 * Np (multiple of 16)
   int prefetch;                     // L2 prefetch distance in tiles of this CTA (0 = off)
+  int no_runs;                      // E2E_TC3_RUNS=0: one TMA box per K entry (A/B)
   int seq_mt;                       // 1: one issuer thread per M tile of a work item (E2E_TC3_SEQ=0: one warp issues both, interleaved)
   int dbg;                          // E2E_TC3_DBG (timing experiments only, results are wrong): 1 = the epilogue only hands the
                                     // accumulator slots back, 2 = the issuer skips the MMAs, 4 = no TMA loads, 8 = 128-byte aligned boxes
@@ -788,7 +797,7 @@ __device__ __forceinline__ void s3_commit(int dbg, uint32_t bar) {
 // kernel mostly serves): one TMEM round trip per M tile and no per-block guards
 template <bool FULL>
 __global__ void __launch_bounds__(S3_THREADS, 1)
-conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMaps maps) {
+conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ S3Maps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[32];
   __shared__ uint32_t tmem_base_s;
@@ -803,9 +812,24 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
   auto tempty_bar = [&](int a) { return smem_u32(&bars[20 + a]); };
   const uint32_t bfull_bar = smem_u32(&bars[24]);
 
-  for (int i = threadIdx.x; i < p.n_cent; i += blockDim.x) {
-    const e2e_centry_t ce = p.cents[i];
-    s_box[i] = make_int4(ce.src, ce.dd, ce.blk, p.src_cb[ce.src]);
+  // box table, one record per K entry: {source | run << 8, depth offset, channel block, blocks per sample}.  Entries k, k+1
+  // of one pipeline stage that are consecutive blocks of one source at the same depth form a run of 2 (one box through
+  // maps.m2); the second entry of a run has run = 0 and is skipped by the producer.
+  for (int g0 = threadIdx.x * 2 * S3_PPS; g0 < p.n_cent; g0 += blockDim.x * 2 * S3_PPS) {
+    const int n = min(2 * S3_PPS, p.n_cent - g0);
+    for (int k = 0; k < n;) {
+      const e2e_centry_t ce = p.cents[g0 + k];
+      int run = 1;
+      if (k + 1 < n && !p.no_runs) {
+        const e2e_centry_t c2 = p.cents[g0 + k + 1];
+        if (c2.src == ce.src && c2.dd == ce.dd && c2.blk == ce.blk + 1) {
+          run = 2;
+          s_box[g0 + k + 1] = make_int4(c2.src, c2.dd, c2.blk, p.src_cb[c2.src]);
+        }
+      }
+      s_box[g0 + k] = make_int4(ce.src | (run << 8), ce.dd, ce.blk, p.src_cb[ce.src]);
+      k += run;
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.seq_mt ? S3_MT : 1); }
@@ -856,8 +880,11 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ TcMa
               mbar_expect_tx(full_bar(stage), (uint32_t)(nb * S3_SLAB));
               const uint32_t dst0 = sa + (uint32_t)(stage * p.stage_bytes);
               for (int k = 0; k < nb; ++k) {
-                const int4 bx = s_box[2 * pr0 + k];              // {source, depth offset, channel block, blocks per sample}
-                tma_load_4d(dst0 + (uint32_t)(k * S3_SLAB), &maps.m[bx.x], full_bar(stage), c0, h0, d + bx.y, b * bx.w + bx.z);
+                const int4 bx = s_box[2 * pr0 + k];
+                const int run = bx.x >> 8, src = bx.x & 0xff;
+                if (run == 0) continue;                          // covered by the previous entry's two-block box
+                tma_load_4d(dst0 + (uint32_t)(k * S3_SLAB), run == 2 ? &maps.m2[src] : &maps.m[src], full_bar(stage), c0, h0,
+                            d + bx.y, b * bx.w + bx.z);
               }
             }
           }
@@ -1195,21 +1222,28 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   p.wpacked = reinterpret_cast<const act16*>(g->wpacked);
   p.dst = reinterpret_cast<act16*>(g->dst[0]);
   p.dst_cb = g->dst_cb[0];
-  TcMaps maps;
+  {
+    static int runs = -1;
+    if (runs < 0) { const char* e = getenv("E2E_TC3_RUNS"); runs = e ? atoi(e) : 1; }
+    p.no_runs = runs ? 0 : 1;
+  }
+  S3Maps maps;
   memset(&maps, 0, sizeof(maps));
   for (int i = 0; i < E2E_MAX_SRC; ++i) {
     const int si = i < g->n_src ? i : 0;
     p.src_cb[i] = g->src_cb[si];
     cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
     cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
-    cuuint32_t box[4] = {(cuuint32_t)(S3_TW * 4), (cuuint32_t)S3_ROWS, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      e2e_set_error("conv_tc3: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
-      return E2E_ERR_CUDA;
+    for (int nb = 1; nb <= 2; ++nb) {
+      cuuint32_t box[4] = {(cuuint32_t)(S3_TW * 4), (cuuint32_t)S3_ROWS, 1, (cuuint32_t)nb};
+      CUresult r = encode(nb == 1 ? &maps.m[i] : &maps.m2[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim,
+                          gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        e2e_set_error("conv_tc3: cuTensorMapEncodeTiled failed with %d (src %d, %d blocks)", (int)r, i, nb);
+        return E2E_ERR_CUDA;
+      }
     }
   }
   const int smem_bytes = p.b_region_bytes + p.stages * p.stage_bytes + stats_bytes + 1024;
@@ -1303,6 +1337,9 @@ static int conv_tc_fwd_impl(const e2e_gemm_t* gs, int n, cudaStream_t st, int* s
     static int poll = -1;
     if (poll < 0) { const char* e = getenv("E2E_TC_POLL"); poll = e ? atoi(e) : 0; }
     p.poll = poll;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("E2E_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
   }
   p.merged = (halo || g->isw == 1) ? 1 : 0;
   p.need_bounds = g->col_bounds & 7;
@@ -1482,6 +1519,7 @@ struct WgParams {
 struct alignas(64) WgMaps {
   CUtensorMap x[E2E_MAX_SRC];
   CUtensorMap g;
+  CUtensorMap x2[E2E_MAX_SRC];     // wgrad_gshift: boxes of two consecutive 8-channel blocks (see S3Maps)
 };
 
 constexpr int WG_MAX_ENT = 64;             // entries per CTA (G <= 4 groups of 16)
@@ -1682,7 +1720,7 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
 // -------------------------------------------------------------------------------------
 struct WgsParams {
   int B, D, H, W;
-  int n_cent, Npad, ivd;
+  int n_cent, Npad, ivd, no_runs;
   int tiles_h, tiles_w, n_tiles;
   int n_groups, splits, tiles_per_split;
   int x_slab_bytes, g_slab_bytes, x_bytes, stage_bytes, stages;
@@ -1700,7 +1738,12 @@ struct WgsParams {
 constexpr int GS_TH = 8;                    // tile rows
 constexpr int GS_WROWS = GS_TH + 2;         // gradient window rows (H halo)
 
-constexpr int GS_NPROD = 3;                 // TMA producer threads; then one MMA issuer thread, then 4 epilogue warps
+#ifndef E2E_GS_NPROD
+#define E2E_GS_NPROD 7
+#endif
+constexpr int GS_NPROD = E2E_GS_NPROD;      // TMA producer threads (3 or 7: the epilogue warps start at a multiple of 4); then
+                                            // one MMA issuer thread, then 4 epilogue warps.  A box costs a producer ~100 cycles of
+                                            // dependent instructions, a 64-voxel tile has up to 19 boxes and 860 cycles of MMAs
 constexpr int GS_THREADS = 32 * (GS_NPROD + 1 + 4);
 
 __global__ void __launch_bounds__(GS_THREADS, 1)
@@ -1709,6 +1752,8 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
   __shared__ __align__(8) uint64_t bars[20];
   __shared__ uint32_t tmem_base_s;
   __shared__ e2e_centry_t s_cents[16];
+  __shared__ int4 s_xbox[16];               // x boxes of a tile: {source | blocks << 8 | first entry << 16, depth offset, block, blocks per sample}
+  __shared__ int s_nrun;
   __shared__ int s_tap_of[9];               // [kh * 3 + kw] -> tap index of the plan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1727,6 +1772,21 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
   const uint32_t done_bar = smem_u32(&bars[16]);
 
   if (threadIdx.x < ne) s_cents[threadIdx.x] = p.cents[e0 + threadIdx.x];
+  if (threadIdx.x == 32) {
+    // x boxes of a tile: runs of one or two K entries (consecutive blocks of one source at the same depth offset)
+    int nr = 0;
+    for (int k = 0; k < ne;) {
+      const e2e_centry_t ce = p.cents[e0 + k];
+      int run = 1;
+      if (k + 1 < ne && !p.no_runs) {
+        const e2e_centry_t c2 = p.cents[e0 + k + 1];
+        if (c2.src == ce.src && c2.dd == ce.dd && c2.blk == ce.blk + 1) run = 2;
+      }
+      s_xbox[nr++] = make_int4(ce.src | (run << 8) | (k << 16), ce.dd, ce.blk, p.src_cb[ce.src]);
+      k += run;
+    }
+    s_nrun = nr;
+  }
   if (threadIdx.x < 9) {
     const e2e_tap_t t = p.taps[threadIdx.x];
     s_tap_of[(t.dh + 1) * 3 + (t.dw + 1)] = threadIdx.x;
@@ -1762,20 +1822,21 @@ wgrad_gshift_kernel(const __grid_constant__ WgsParams p, const __grid_constant__
         int wt = t % p.tiles_w; t /= p.tiles_w;
         int ht = t % p.tiles_h; t /= p.tiles_h;
         int d = t % p.D, b = t / p.D;
-        const int nb = ne + 3;
+        const int nr = s_nrun, nb = nr + 3;
         for (int tile = tile_lo; tile < tile_hi; ++tile) {
           const int h0 = ht * GS_TH, w0 = wt * 8;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           if (warp == 0) mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sx = smem_base + stage * p.stage_bytes;
           for (int k = warp; k < nb; k += GS_NPROD) {
-            if (k < ne) {
-              const e2e_centry_t ce = s_cents[k];
-              tma_load_4d(sx + k * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), w0 * 4, h0, d + p.ivd + ce.dd,
-                          b * p.src_cb[ce.src] + ce.blk);
+            if (k < nr) {
+              const int4 bx = s_xbox[k];
+              const int src = bx.x & 0xff, e = bx.x >> 16;
+              tma_load_4d(sx + e * p.x_slab_bytes, ((bx.x >> 8) & 0xff) == 2 ? &maps.x2[src] : &maps.x[src], full_bar(stage), w0 * 4,
+                          h0, d + p.ivd + bx.y, b * bx.w + bx.z);
             } else {
               // three kw-shifted copies of the haloed gradient window: copy kw holds g[., w - (kw - 1)]
-              const int kw = k - ne;
+              const int kw = k - nr;
               tma_load_4d(sx + p.x_bytes + kw * (Npad >> 3) * p.g_slab_bytes, &maps.g, full_bar(stage),
                           (w0 - (kw - 1)) * 4, h0 - 1, d, b * p.grad_cb);
             }
@@ -1910,15 +1971,22 @@ static int wgrad_gshift_launch(const e2e_wgrad_t* g, PFN_cuTensorMapEncodeTiled_
     p.src_cb[i] = g->src_cb[si];
     cuuint64_t gdim[4] = {(cuuint64_t)g->Wi * 4, (cuuint64_t)g->Hi, (cuuint64_t)g->Di, (cuuint64_t)p.B * g->src_cb[si]};
     cuuint64_t gstr[3] = {(cuuint64_t)g->Wi * 16, (cuuint64_t)g->Wi * g->Hi * 16, (cuuint64_t)g->Wi * g->Hi * g->Di * 16};
-    cuuint32_t box[4] = {32, (cuuint32_t)GS_TH, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&maps.x[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      e2e_set_error("wgrad_gshift: cuTensorMapEncodeTiled failed with %d (src %d)", (int)r, i);
-      return E2E_ERR_CUDA;
+    for (int nb = 1; nb <= 2; ++nb) {
+      cuuint32_t box[4] = {32, (cuuint32_t)GS_TH, 1, (cuuint32_t)nb};
+      CUresult r = encode(nb == 1 ? &maps.x[i] : &maps.x2[i], CU_TENSOR_MAP_DATA_TYPE_INT32, 4, const_cast<void*>(g->src[si]), gdim,
+                          gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        e2e_set_error("wgrad_gshift: cuTensorMapEncodeTiled failed with %d (src %d, %d blocks)", (int)r, i, nb);
+        return E2E_ERR_CUDA;
+      }
     }
+  }
+  {
+    static int runs = -1;
+    if (runs < 0) { const char* e = getenv("E2E_TC3_RUNS"); runs = e ? atoi(e) : 1; }
+    p.no_runs = runs ? 0 : 1;
   }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)p.W * 4, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.B * g->grad_cb};

@@ -27,6 +27,10 @@ CONVS = [  # name, sources, cout, stride, input (D,H,W), count in the network
     ("ctx3.1/loc0.1.1 320->320 @16x20x20", [320], 320, (1, 1, 1), (16, 20, 20), 2),
     ("ctx3.0 192->320 s2 @32x40x40", [192], 320, (2, 2, 2), (32, 40, 40), 1),
     ("loc0.0.0 960->320 @8x10x10", [320, 320, 320], 320, (1, 1, 1), (8, 10, 10), 1),
+    # probes (count 0: not in the totals): channel counts whose 5 depth-shift groups start on 8-channel block boundaries,
+    # so no block is loaded / multiplied twice (C = 48 has 9 K entries for 6 blocks, C = 40 has 5 for 5)
+    ("probe 40->48 aligned groups @64x160x160", [40], 48, (1, 1, 1), (64, 160, 160), 0),
+    ("probe 80->48 aligned groups @64x160x160", [40, 40], 48, (1, 1, 1), (64, 160, 160), 0),
 ]
 TCONVS = [  # name, cin, cout, k, input (D,H,W), count
     ("up 96->48 k(1,2,2) @64x80x80", 96, 48, (1, 2, 2), (64, 80, 80), 5),
