@@ -1524,8 +1524,14 @@ struct alignas(64) WgMaps {
 
 constexpr int WG_MAX_ENT = 64;             // entries per CTA (G <= 4 groups of 16)
 
+#ifndef E2E_WG_NPROD
+#define E2E_WG_NPROD 7
+#endif
+constexpr int WG_NPROD = E2E_WG_NPROD;       // 3 or 7 producer threads, then the issuer warp, then 4 epilogue warps
+constexpr int WG_THREADS = 32 * (WG_NPROD + 1 + 4);
+
 template <bool HALO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(WG_THREADS, 1)
 wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bars[20];
@@ -1581,51 +1587,59 @@ wgrad_tc_kernel(const __grid_constant__ WgParams p, const __grid_constant__ WgMa
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
   if (my_tiles > 0) {
-    if (warp == 0) {
-      // producer WARP: lane 0 waits for the stage and arms the barrier; then every lane issues the boxes
-      // of its entries (lane, lane + 32) and lane 31 the gradient tile, in parallel
-      int stage = 0, phase = 0;
-      const uint32_t tx = (uint32_t)ne * (uint32_t)(p.x_rows * p.x_rowpitch) + (uint32_t)ncol * 256u;
-      for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        int t = tile;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h; t /= p.tiles_h;
-        const int d = t % p.D;
-        const int b = t / p.D;
-        const int h0 = ht * TH, w0 = wt * 8;
-        if (lane == 0) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_expect_tx(full_bar(stage), tx);
+    if (warp < WG_NPROD) {
+      // TMA producers: ONE thread each (lane 0 of warps 0 .. WG_NPROD-1); the x boxes of the job's entries and the
+      // gradient tile are dealt round-robin (see wgrad_gshift_kernel: a box costs its issuing thread ~100 cycles, the
+      // 1-tap jobs have up to 65 boxes per 128-voxel tile against 8 - 32 MMAs).  Producer 0 arms the barrier.
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = (uint32_t)ne * (uint32_t)(p.x_rows * p.x_rowpitch) + (uint32_t)ncol * 256u;
+        int t = tile_lo;
+        int wt = t % p.tiles_w; t /= p.tiles_w;
+        int ht = t % p.tiles_h; t /= p.tiles_h;
+        int d = t % p.D, b = t / p.D;
+        const int ngb = ncol == Nc ? 1 : (ncol >> 3);      // gradient boxes: one sized for Nc, or block by block
+        const int nb = ne + ngb;
+        for (int tile = tile_lo; tile < tile_hi; ++tile) {
+          const int h0 = ht * TH, w0 = wt * 8;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (warp == 0) mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sx = smem_base + stage * p.stage_bytes;
+          for (int k = warp; k < nb; k += WG_NPROD) {
+            if (k < ne) {
+              const e2e_centry_t ce = s_cents[k];
+              const int cb = b * p.src_cb[ce.src] + ce.blk;
+              if (HALO)
+                tma_load_4d(sx + k * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
+                            d + p.ivd + ce.dd, cb);
+              else if (p.merged)
+                tma_load_4d(sx + k * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
+                            h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
+              else
+                tma_load_5d(sx + k * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
+                            h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
+            } else if (ncol == Nc) {
+              // gradient tile: ncol / 8 channel blocks starting at block n0 / 8 (the 4-D box is sized for Nc)
+              tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb + (n0 >> 3));
+            } else {
+              const int q = k - ne;                          // a narrower last chunk is loaded block by block
+              tma_load_4d(sx + p.x_bytes + q * p.g_slab_bytes, &maps.x[E2E_MAX_SRC - 1], full_bar(stage), w0 * 4, h0, d,
+                          b * p.grad_cb + (n0 >> 3) + q);
+            }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1u; }
+          if (++wt == p.tiles_w) {
+            wt = 0;
+            if (++ht == p.tiles_h) {
+              ht = 0;
+              if (++d == p.D) { d = 0; ++b; }
+            }
+          }
         }
-        __syncwarp();
-        const uint32_t sx = smem_base + stage * p.stage_bytes;
-        for (int e = lane; e < ne; e += 32) {
-          const e2e_centry_t ce = s_cents[e];
-          const int cb = b * p.src_cb[ce.src] + ce.blk;
-          if (HALO)
-            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 - 1) * 4, h0 - 1,
-                        d + p.ivd + ce.dd, cb);
-          else if (p.merged)
-            tma_load_4d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), (w0 + p.ivw + ce.dw) * 4,
-                        h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
-          else
-            tma_load_5d(sx + e * p.x_slab_bytes, &maps.x[ce.src], full_bar(stage), 0, w0 * p.isw + p.ivw + ce.dw,
-                        h0 * p.ish + p.ivh + ce.dh, d * p.isd + p.ivd + ce.dd, cb);
-        }
-        // gradient tile: ncol / 8 channel blocks starting at block n0 / 8 (the 4-D box is sized for Nc:
-        // a narrower last chunk is loaded block by block)
-        if (ncol == Nc) {
-          if (lane == 31)
-            tma_load_4d(sx + p.x_bytes, &maps.g, full_bar(stage), w0 * 4, h0, d, b * p.grad_cb + (n0 >> 3));
-        } else {
-          for (int q = lane; q < (ncol >> 3); q += 32)
-            tma_load_4d(sx + p.x_bytes + q * p.g_slab_bytes, &maps.x[E2E_MAX_SRC - 1], full_bar(stage), w0 * 4, h0, d,
-                        b * p.grad_cb + (n0 >> 3) + q);
-        }
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
-    } else if (warp == 1) {
-      // D=f32, A=B=bf16, A and B MN-major, N=ncol, M=128
+    } else if (warp == WG_NPROD) {
+      // MMA issuer.  D=f32, A=B=the 16-bit type, A and B MN-major, N=ncol, M=128
       const uint32_t idesc = (1u << 4) | (E2E_UMMA_FMT << 7) | (E2E_UMMA_FMT << 10) | (1u << 15) | (1u << 16) |
                              ((uint32_t)(ncol >> 3) << 17) | (8u << 24);
       int stage = 0, phase = 0;
@@ -2139,9 +2153,9 @@ int e2e_wgrad_tc(const e2e_wgrad_t* g, cudaStream_t st) {
     E2E_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 6 * 1024));
   }
   if (halo)
-    wgrad_tc_kernel<true><<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+    wgrad_tc_kernel<true><<<jobs * splits, WG_THREADS, smem_bytes, st>>>(p, maps);
   else
-    wgrad_tc_kernel<false><<<jobs * splits, TC_THREADS, smem_bytes, st>>>(p, maps);
+    wgrad_tc_kernel<false><<<jobs * splits, WG_THREADS, smem_bytes, st>>>(p, maps);
   E2E_LAUNCHED("wgrad_tc");
   return E2E_OK;
 }
