@@ -1004,7 +1004,7 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ S3Ma
     // row), the warps of a quadrant take the 8-channel blocks of the result round-robin
     const int q = warp & 3;                    // tile row
     const int grp = (warp - S3_EPI0) >> 2;
-    const int nblk = Np >> 3;
+    const int nblk = min(Np >> 3, p.dst_cb);      // Np is padded to 16 channels: the destination may have one block less
     uint32_t mcount = 0;
     // InstanceNorm statistics: every thread keeps the running sums of ITS voxels' values for the (at most S3_UB) channel
     // blocks its warp handles in registers -- no shuffles per tile -- and the lanes / warps are combined only when
@@ -1259,7 +1259,7 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   }
   int grid = e2e_num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  if ((p.Np >> 3) == S3_UB * (S3_EPI_WARPS / 4))
+  if ((p.Np >> 3) == S3_UB * (S3_EPI_WARPS / 4) && p.dst_cb == (p.Np >> 3))
     conv_tc3_kernel<true><<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);
   else
     conv_tc3_kernel<false><<<grid, S3_THREADS, smem_bytes, st>>>(p, maps);

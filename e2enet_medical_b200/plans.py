@@ -144,6 +144,9 @@ class ShiftConvPlan:
                      for n, o, s, e in zip((D, H, W), var.iter_off, self.stride, var.iter_extra))
 
 
+S3_MIN_PAIRS = int(__import__("os").environ.get("E2E_S3_MIN_PAIRS", "1"))
+
+
 def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1), shift: bool = True) -> ShiftConvPlan:
     src_channels = [int(c) for c in src_channels]
     cin = sum(src_channels)
@@ -199,8 +202,9 @@ def build_shiftconv_plan(src_channels: Sequence[int], cout: int, stride=(1, 1, 1
     fwd_chunks = [fwd] if len(chunks) == 1 else [mk(cols[a:b], rowoff[8 * a:8 * b]) for a, b in chunks]
     fwd3 = None
     npo = ceil_to(cout, 16)
-    # (measured: 17 % faster than the 9-tap form on loc4, slower when the K loop is very short)
-    if unit and npo <= 80 and len(cents) // 2 >= 5 and (len(cents) // 2) * 3 * 2 * 16 * 3 * npo <= 120 * 1024:
+    # (measured: 17 % faster than the 9-tap form on loc4; since the role warps of conv_tc3 became single threads it also
+    # wins on the shortest K loop, the 1-channel input layer: E2E_S3_MIN_PAIRS restores the round-1 threshold of 5)
+    if unit and npo <= 80 and len(cents) // 2 >= S3_MIN_PAIRS and (len(cents) // 2) * 3 * 2 * 16 * 3 * npo <= 120 * 1024:
         # kw-stacked forward: column kw*Np + n holds W[:, :, kh, kw] of output channel n; the kernel adds the
         # three column groups with a W shift of -1 / 0 / +1 (one A read per three taps)
         row3 = [(n * cin * 9 + kw) if n < cout else -1 for kw in range(3) for n in range(npo)]

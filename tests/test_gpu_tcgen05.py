@@ -141,6 +141,8 @@ def test_tcgen05_point_form_tconv(cin, cout, k, spatial, B):
     ([48], 48, (2, 160, 160), 1),           # full-resolution rows
     ([96], 16, (5, 16, 33), 2),             # Np = 16, 6 K pairs
     ([80], 8, (4, 7, 31), 1),               # Cout 8 padded to 16, one W tile + 1 voxel
+    ([1], 48, (6, 16, 40), 2),              # the 1-channel input layer: one K pair
+    ([20], 8, (6, 19, 21), 2),              # three K pairs (the last stage half full), Cout 8, B = 2
 ])
 def test_tcgen05_kw_stacked_forward(src, cout, spatial, B):
     """kw-stacked forward kernel (N = 3 x Cout per MMA, W shift applied in the epilogue by lane shuffles)
@@ -158,10 +160,15 @@ def test_tcgen05_kw_stacked_forward(src, cout, spatial, B):
     w = bf(torch.from_numpy((rs.standard_normal((cout, cin, 1, 3, 3)) / np.sqrt(cin * 9)).astype(np.float32))).to(dev)
     Cb = cout // 8
     a = torch.full((B, Cb, D, H, W, 8), float("nan"), dtype=_act(), device=dev)
-    b_ = torch.full_like(a, float("nan"))
+    # the destination of the stacked kernel sits in front of a guard area: Cout = 8 is padded to 16 columns inside the
+    # kernel, and the padding block must never be stored (it would land in the next sample / past the tensor)
+    n = a.numel()
+    buf = torch.full((n + D * H * W * 8,), float("nan"), dtype=_act(), device=dev)
+    b_ = buf[:n].view(a.shape)
     ops.run_gemm_chunks(plan.fwd_chunks, w, None, xs8, (D, H, W), (D, H, W), B, [a], (D, H, W), [Cb], 1)
     ops.run_gemm(plan.fwd3, ops.pack_weights(plan.fwd3, w, None), xs8, (D, H, W), (D, H, W), B, [b_], (D, H, W), [Cb], 1)
     torch.cuda.synchronize()
+    assert torch.isnan(buf[n:].float()).all(), "the stacked kernel stored a padding channel block"
     assert not torch.isnan(b_.float()).any()
     assert rel(b_, a) <= 2 * _ulp(), rel(b_, a)       # two roundings of sums in different order: one spacing apart
 
