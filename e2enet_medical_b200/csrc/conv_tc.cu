@@ -912,7 +912,9 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ S3Ma
       // The two issuers also decouple the tiles' accumulator slots: tile k waits only for the epilogue of tile k - 3
       // (3 slots), where the interleaved single issuer needed BOTH slots of the next item before its first MMA.
       // Both read the same K stages; a stage is released when both have committed (empty barrier count S3_MT).
-      if (lane == 0 && (int)blockIdx.x < p.n_tiles) {
+      // (the loop is warp-uniform and one elected lane issues: descriptor arithmetic then stays in uniform registers, which
+      // UTCHMMA reads directly -- inside an `if (lane == 0)` every operand needs an R2UR first)
+      if ((int)blockIdx.x < p.n_tiles) {
         const int mt = warp - S3_NPROD;
         mbar_wait(bfull_bar, 0);
         tc_fence_after();
@@ -928,23 +930,27 @@ conv_tc3_kernel(const __grid_constant__ S3Params p, const __grid_constant__ S3Ma
             const int np = min(S3_PPS, npairs - pr0);
             mbar_wait(full_bar(stage), (uint32_t)phase);
             tc_fence_after();
-            const uint32_t a_st = a_mt + (uint32_t)stage * stage_units;
+            if (elect_one_sync()) {
+              const uint32_t a_st = a_mt + (uint32_t)stage * stage_units;
 #pragma unroll
-            for (int i = 0; i < S3_PPS; ++i) {
-              if (i < np && !(p.dbg & 2)) {
-                const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
-                const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
+              for (int i = 0; i < S3_PPS; ++i) {
+                if (i < np && !(p.dbg & 2)) {
+                  const uint32_t a_lo = a_st + (uint32_t)(i * (2 * S3_SLAB >> 4));
+                  const uint32_t b_lo = b_st + (uint32_t)i * 3u * b_tap_units;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-                  tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
-                                (i + kh) ? 1u : (pr0 ? 1u : 0u));
+                  for (int kh = 0; kh < 3; ++kh)
+                    tc_mma_f16_lh(acc, a_lo + (uint32_t)(kh * 32), a_hi, b_lo + (uint32_t)kh * b_tap_units, b_hi, idesc,
+                                  (i + kh) ? 1u : (pr0 ? 1u : 0u));
+                }
               }
+              s3_commit(p.dbg, empty_bar(stage));
             }
-            s3_commit(p.dbg, empty_bar(stage));
+            __syncwarp();
             b_st += (uint32_t)S3_PPS * 3u * b_tap_units;
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
-          s3_commit(p.dbg, tfull_bar(slot));
+          if (elect_one_sync()) s3_commit(p.dbg, tfull_bar(slot));
+          __syncwarp();
           slot += S3_MT;
           if (slot >= AS) { slot -= AS; sphase ^= 1u; }
         }
