@@ -201,7 +201,10 @@ def test_real_layer_plans_are_consistent():
             assert sorted(set(int(m) for m in v0.emask if m)) == [8, 10, 12, 15]
 
 
-@pytest.mark.parametrize("src,cout,spatial", [([72], 8, (3, 4, 6)), ([40, 40], 16, (4, 3, 5))])
+@pytest.mark.parametrize("src,cout,spatial", [([72], 8, (3, 4, 6)), ([40, 40], 16, (4, 3, 5)),
+                                              ([1], 48, (5, 3, 4)),       # the 1-channel input layer: one K pair
+                                              ([4], 16, (6, 3, 3)),       # BraTS input: four single-channel shift groups
+                                              ([20], 8, (6, 4, 3))])      # three K pairs, ragged last channel block
 def test_kw_stacked_forward_plan(src, cout, spatial):
     """fwd3 (narrow layers, tcgen05 only): column kw*Np + n of the 3-tap (kh) GEMM holds
     D'[v] = sum_{kh,c} x~[v + (kh-1) rows][c] W[n,c,kh,kw]; the kernel's epilogue adds the three column
