@@ -756,7 +756,10 @@ struct TileWalk {
 constexpr int S3_MT = 2;                            // M tiles (4 rows each) per work item: they share one window
 constexpr int S3_TH = 4 * S3_MT, S3_TW = 32, S3_ADV = 30, S3_ROWS = S3_TH + 2;
 constexpr int S3_SLAB = S3_ROWS * S3_TW * 16;      // 5120 B: [10 rows][32 voxels][8 ch]
-constexpr int S3_PPS = 2;                           // K pairs per pipeline stage (2 * 3 * S3_MT = 12 MMAs)
+#ifndef E2E_S3_PPS
+#define E2E_S3_PPS 2
+#endif
+constexpr int S3_PPS = E2E_S3_PPS;                           // K pairs per pipeline stage (2 * 3 * S3_MT = 12 MMAs)
 #ifndef E2E_S3_EPI_WARPS
 #define E2E_S3_EPI_WARPS 12
 #endif
