@@ -168,6 +168,26 @@ __global__ void __launch_bounds__(1024) in_stats_from_slots_kernel(const float* 
   rstd[b * C + c] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Block -> (plane, chunk) of the grid (nchunk, planes).  order 0: plane-major (blockIdx as is).  order 1 / 2: chunk-major
+// (all planes of a voxel chunk before the next chunk: the order in which the GEMM kernels walk a tensor), descending /
+// ascending.  A kernel that reads what its predecessor wrote LAST first finds that part still in the 126 MB L2: the forward
+// apply and the first backward pass walk downwards (the conv / data-gradient kernel before them ended at the top), the
+// second backward pass walks upwards again from where the first one ended.  E2E_EW_ORDER=0 restores plane-major order.
+__device__ __forceinline__ void ew_block(int order, int& plane, int& chunk) {
+  if (order == 0) { plane = blockIdx.y; chunk = blockIdx.x; return; }
+  const int nch = gridDim.x, npl = gridDim.y;
+  const int L = blockIdx.y * nch + blockIdx.x;
+  const int inner = L % npl, outer = L / npl;
+  plane = order == 1 ? npl - 1 - inner : inner;
+  chunk = order == 1 ? nch - 1 - outer : outer;
+}
+
+static int ew_order(int which) {            // which: 1 = descending, 2 = ascending
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("E2E_EW_ORDER"); on = e ? atoi(e) : 1; }
+  return on ? which : 0;
+}
+
 // Plane statistics inside the consumer kernel (no separate tiny launch): every block of a (chunk, plane) grid forms
 // the SAME fixed-order fp64 sums, so all blocks of a plane see bit-identical values; block (chunk 0) publishes them.
 //   mean / rstd of plane (b, cb) from the per-CTA slots a fused conv epilogue wrote: stats[slot][b][{sum, sumsq}][C]
@@ -225,8 +245,9 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_kernel(const uint4* __res
                                                               const float* __restrict__ beta, float slope, int Cb,
                                                               long long V, int nchunk, uint4* __restrict__ out,
                                                               const float* __restrict__ stats, int n_slots, int B, float eps,
-                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int plane = blockIdx.y, chunk = blockIdx.x;
+                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out, int order) {
+  int plane, chunk;
+  ew_block(order, plane, chunk);
   const int cb = plane % Cb;
   __shared__ float s_mean[8], s_rstd[8];
   if (stats) {                      // statistics straight from the conv epilogue's slots (see plane_mean_rstd_from_slots)
@@ -277,8 +298,9 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_reduce_kernel(const uint4* 
                                                                    const float* __restrict__ rstd,
                                                                    const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float slope, int Cb,
-                                                                   long long V, int nchunk, float* __restrict__ partial) {
-  const int plane = blockIdx.y, chunk = blockIdx.x;
+                                                                   long long V, int nchunk, float* __restrict__ partial, int order) {
+  int plane, chunk;
+  ew_block(order, plane, chunk);
   const int cb = plane % Cb;
   float mu[8], rs[8], ga[8], be[8];
 #pragma unroll
@@ -339,8 +361,9 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_apply_kernel(const uint4* _
                                                                   const float* __restrict__ partial1,
                                                                   float* __restrict__ sums, float slope, int Cb,
                                                                   long long V, int nchunk, uint4* __restrict__ draw,
-                                                                  float* __restrict__ partial2) {
-  const int plane = blockIdx.y, chunk = blockIdx.x;
+                                                                  float* __restrict__ partial2, int order) {
+  int plane, chunk;
+  ew_block(order, plane, chunk);
   const int cb = plane % Cb;
   const float invV = 1.0f / (float)V;
   __shared__ float s_sums[16];
@@ -438,8 +461,9 @@ __global__ void __launch_bounds__(EW_THREADS) in_apply_pool_kernel(const uint4* 
                                                                    int nchunk, uint4* __restrict__ out, uint4* __restrict__ pooled,
                                                                    uint2* __restrict__ amax, const float* __restrict__ stats,
                                                                    int n_slots, int B, float eps, float* __restrict__ mean_out,
-                                                                   float* __restrict__ rstd_out) {
-  const int plane = blockIdx.y, chunk = blockIdx.x;
+                                                                   float* __restrict__ rstd_out, int order) {
+  int plane, chunk;
+  ew_block(order, plane, chunk);
   const int cb = plane % Cb;
   const long long V = (long long)g.D * g.H * g.W;
   __shared__ float s_mean[8], s_rstd[8];
@@ -517,8 +541,9 @@ __global__ void __launch_bounds__(EW_THREADS) in_bwd_pool_kernel(const uint4* __
                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                  const float* __restrict__ partial1, float* __restrict__ sums,
                                                                  float slope, int Cb, PoolGeo g, int nchunk,
-                                                                 uint4* __restrict__ draw, float* __restrict__ partial) {
-  const int plane = blockIdx.y, chunk = blockIdx.x;
+                                                                 uint4* __restrict__ draw, float* __restrict__ partial, int order) {
+  int plane, chunk;
+  ew_block(order, plane, chunk);
   const int cb = plane % Cb;
   const long long V = (long long)g.D * g.H * g.W;
   const long long Vo = V / (g.kd * g.kh * g.kw);
@@ -962,7 +987,8 @@ extern "C" int e2e_in_apply(const void* raw, const float* mean, const float* rst
   if (nchunk > want) nchunk = want;
   if (nchunk < 1) nchunk = 1;
   in_apply_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
-      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, V, nchunk, (uint4*)out, nullptr, 0, B, 0.f, nullptr, nullptr);
+      (const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, V, nchunk, (uint4*)out, nullptr, 0, B, 0.f, nullptr, nullptr,
+      ew_order(1));
   E2E_LAUNCHED("in_apply");
   return E2E_OK;
 }
@@ -980,7 +1006,7 @@ extern "C" int e2e_in_apply_from_slots(const void* raw, const float* stats, int3
   if (nchunk < 1) nchunk = 1;
   in_apply_kernel<<<dim3(nchunk, B * Cb), EW_THREADS, 0, (cudaStream_t)stream>>>(
       (const uint4*)raw, nullptr, nullptr, gamma, beta, slope, Cb, V, nchunk, (uint4*)out, stats, n_slots, B, eps, mean_out,
-      rstd_out);
+      rstd_out, ew_order(1));
   E2E_LAUNCHED("in_apply_from_slots");
   return E2E_OK;
 }
@@ -995,11 +1021,11 @@ extern "C" int e2e_in_bwd(const void* dy, const void* raw, const float* mean, co
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 grid(nchunk, B * Cb);
   in_bwd_reduce_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta,
-                                                    slope, Cb, V, nchunk, partial);
+                                                    slope, Cb, V, nchunk, partial, ew_order(1));
   E2E_LAUNCHED("in_bwd_reduce");
   float* partial2 = partial + (size_t)B * Cb * nchunk * 16;        // pass 2 reads ALL of pass 1's partials: separate region
   in_bwd_apply_kernel<<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)raw, mean, rstd, gamma, beta, partial,
-                                                   sums, slope, Cb, V, nchunk, (uint4*)draw, partial2);
+                                                   sums, slope, Cb, V, nchunk, (uint4*)draw, partial2, ew_order(2));
   E2E_LAUNCHED("in_bwd_apply");
   in_bwd_param_kernel<<<(Cb * 8 * 32 + 127) / 128, 128, 0, st>>>(sums, partial2, B, Cb, nchunk, dgamma, dbeta, dbias);
   E2E_LAUNCHED("in_bwd_param");
@@ -1069,11 +1095,11 @@ static int in_apply_pool_impl(const void* raw, const float* mean, const float* r
   if (kd == 1 && kh == 2 && kw == 2)
     in_apply_pool_kernel<1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
                                                                  (uint4*)out, (uint4*)pooled, (uint2*)argmax, stats, n_slots, B, eps,
-                                                                 mean_out, rstd_out);
+                                                                 mean_out, rstd_out, ew_order(1));
   else if (kd == 2 && kh == 2 && kw == 2)
     in_apply_pool_kernel<2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)raw, mean, rstd, gamma, beta, slope, Cb, g, nchunk,
                                                                  (uint4*)out, (uint4*)pooled, (uint2*)argmax, stats, n_slots, B, eps,
-                                                                 mean_out, rstd_out);
+                                                                 mean_out, rstd_out, ew_order(1));
   else {
     e2e_set_error("in_apply_pool: window (%d,%d,%d) is not instantiated (use the separate max-pool kernel)", kd, kh, kw);
     return E2E_ERR_UNSUPPORTED;
@@ -1123,11 +1149,11 @@ extern "C" int e2e_in_bwd_pool(const void* dy, const void* dyp, const uint8_t* a
     if (k122)                                                                                                              \
       in_bwd_pool_kernel<PASS, 1, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
                                                                      (const uint4*)raw, mean, rstd, gamma, beta, partial, SUMS, slope, \
-                                                                     Cb, g, nchunk, DRAW, POUT);                          \
+                                                                     Cb, g, nchunk, DRAW, POUT, ew_order(PASS ? 2 : 1));  \
     else                                                                                                                   \
       in_bwd_pool_kernel<PASS, 2, 2, 2><<<grid, EW_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)dyp, (const uint2*)argmax, \
                                                                      (const uint4*)raw, mean, rstd, gamma, beta, partial, SUMS, slope, \
-                                                                     Cb, g, nchunk, DRAW, POUT);                          \
+                                                                     Cb, g, nchunk, DRAW, POUT, ew_order(PASS ? 2 : 1));  \
   } while (0)
   float* partial2 = partial + (size_t)B * Cb * nchunk * 16;
   E2E_BWD_POOL(0, nullptr, nullptr, partial);
