@@ -152,13 +152,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// TMA prefetch of a box into L2 (no shared memory, no barrier): issued a few tiles ahead so that the
-// real load finds its data in L2 and the pipeline depth only has to cover L2 latency
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -773,7 +766,6 @@ constexpr int S3_THREADS = 32 * (S3_EPI0 + S3_EPI_WARPS);
 struct S3Params {
   int B, D, H, W;
   int n_cent, Np, N3, ivd;          // Np = padded Cout (multiple of 8), N3 = 3 * Np (multiple of 16)
-  int prefetch;                     // L2 prefetch distance in tiles of this CTA (0 = off)
   int no_runs;                      // E2E_TC3_RUNS=0: one TMA box per K entry (A/B)
   int seq_mt;                       // 1: one issuer thread per M tile of a work item (E2E_TC3_SEQ=0: one warp issues both, interleaved)
   int dbg;                          // E2E_TC3_DBG (timing experiments only, results are wrong): 1 = the epilogue only hands the
@@ -1220,9 +1212,6 @@ static int conv_tc3_launch(const e2e_gemm_t* g, PFN_cuTensorMapEncodeTiled_v1200
   p.stats_ctot = g->stats_ctot;
   p.stats_smem_off = p.b_region_bytes + p.stages * p.stage_bytes;
   {
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("E2E_TC_PREFETCH"); pf = e ? atoi(e) : 0; }   // measured: 0.34 -> 0.44 ms with prefetch on (the TMA unit, not latency, is the limit)
-    p.prefetch = pf;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("E2E_TC3_DBG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
