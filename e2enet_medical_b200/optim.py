@@ -252,6 +252,8 @@ class FusedSGD(torch.optim.Optimizer):
         if not ps[0].is_cuda:
             raise _lib.E2EError("FusedSGD runs on CUDA only (no CPU fallback)")
         lib = _lib.load()
+        from . import ops
+        ops.side_join()                  # weight gradients still running on ops' side stream (no-op when there are none)
         self._ensure(ps)
         if not torch.cuda.is_current_stream_capturing():
             self.sync_hyper()
@@ -262,6 +264,5 @@ class FusedSGD(torch.optim.Optimizer):
                                          _p(self._partial), _p(self._norm_coef), st), "sgd_clip_coef")
         _lib.check(lib.e2e_sgd_update(_p(self._table), self._n, self._max_numel, _p(self._hyper), _p(self._norm_coef),
                                       1 if self.param_groups[0]['nesterov'] else 0, st), "sgd_update")
-        from . import ops
         ops.bump_weight_epoch()          # weights changed behind torch's version counters
         return None
