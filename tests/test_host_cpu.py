@@ -362,3 +362,34 @@ def test_grad_arena_layout_and_bucket_callbacks():
         done = all(id(q) not in arena._pending[b] for q in members)
         assert (len(fired) > before) == done
     assert sorted(fired) == list(range(arena.n_buckets))
+
+
+def test_grad_arena_scratch_and_loss_scale_state():
+    """host logic added in round 2: the per-step weight-gradient scratch of the arena (sized from the first step's
+    demand, handed out as disjoint zeroed slices, None when it does not fit) and the loss-scale state of FusedSGD
+    (GradScaler defaults; `loss_scale()` is a view of the device state the kernels advance)."""
+    import torch
+    from e2enet_medical_b200.optim import FusedSGD, GradArena
+    ps = [torch.nn.Parameter(torch.zeros(s)) for s in ((8, 8, 1, 3, 3), (8,))]
+    arena = GradArena(ps, n_buckets=1)
+    arena.begin_step()
+    assert arena.zeroed_this_step
+    assert arena.take_scratch(100) is None and arena.take_scratch(1000) is None        # first step: demand is recorded
+    arena.begin_step()                                                                 # ... and allocated here
+    a, b = arena.take_scratch(100), arena.take_scratch(1000)
+    assert a is not None and b is not None and a.numel() == 128 and b.numel() == 1024  # rounded to 64 floats
+    assert a.data_ptr() + a.numel() * 4 == b.data_ptr() and float(a.abs().sum() + b.abs().sum()) == 0.0
+    assert arena.take_scratch(64) is None                                              # more than the first step asked for
+    a.fill_(1.0)
+    arena.begin_step()
+    assert float(arena.take_scratch(100).abs().sum()) == 0.0                           # zeroed again every step
+
+    opt = FusedSGD(ps, lr=1e-2)
+    assert opt.loss_scale() is None                                                    # bf16: no scaling
+    opt.enable_loss_scale()
+    s = opt.loss_scale(torch.device("cpu"))
+    assert float(s) == 65536.0 and opt._scaler.tolist() == [65536.0, 0.0, 2000.0, 0.5, 2.0]
+    opt._scaler[0] = 1024.0
+    assert float(opt.loss_scale()) == 1024.0                                           # a view, not a copy
+    with pytest.raises(NotImplementedError):
+        FusedSGD([{"params": ps[:1]}, {"params": ps[1:]}])
