@@ -157,6 +157,7 @@ SIGNATURES = {
                                              _I32, _I32, _I32, _F, _I32, _VP]),
     "e2e_resample_argmax": (C.c_int, [_VP, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),
     "e2e_window_finalize": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP]),
+    "e2e_window_finalize_range": (C.c_int, [_VP, _VP, _I32, _I32, _I32, _I32, _I32, _I32, _VP, _VP]),
 }
 
 _libs = {}

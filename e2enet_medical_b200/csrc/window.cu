@@ -156,10 +156,13 @@ __global__ void __launch_bounds__(256) window_head_accumulate_kernel(const uint4
   }
 }
 
+// voxels [v0, v1) of the flattened volume (a range of x-planes: the tiled predictor finalises the planes no later tile
+// touches while the remaining tiles are still being computed)
 template <int NC>
 __global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict__ agg, const float* __restrict__ wsum, int ncls,
-                                                              long long V, long long* __restrict__ seg) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V;
+                                                              long long V, long long v0, long long v1,
+                                                              long long* __restrict__ seg) {
+  for (long long i = v0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < v1;
        i += (long long)gridDim.x * blockDim.x) {
     const float w = wsum[i];
     float a[NC];
@@ -231,18 +234,31 @@ extern "C" int e2e_window_head_accumulate(const void* x, int32_t Cb, const float
   return E2E_OK;
 }
 
+static int window_finalize_impl(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z, int32_t x0,
+                                int32_t x1, int64_t* seg, void* stream) {
+  const long long V = (long long)X * Y * Z, v0 = (long long)x0 * Y * Z, v1 = (long long)x1 * Y * Z;
+  if (v1 <= v0) return E2E_OK;
+  long long blocks = (v1 - v0 + 255) / 256;
+  const long long cap = (long long)e2e_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (ncls <= 4) window_finalize_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, v0, v1, (long long*)seg);
+  else if (ncls <= 16) window_finalize_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, v0, v1, (long long*)seg);
+  else window_finalize_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, v0, v1, (long long*)seg);
+  E2E_LAUNCHED("window_finalize");
+  return E2E_OK;
+}
+
 extern "C" int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
                                    int64_t* seg, void* stream) {
   E2E_ARG(agg && wsum && seg && ncls >= 1, "window_finalize: bad arguments");
-  const long long V = (long long)X * Y * Z;
-  long long blocks = (V + 255) / 256;
-  const long long cap = (long long)e2e_num_sms() * 16;
-  if (blocks > cap) blocks = cap;
   E2E_ARG(ncls <= MAXC, "window_finalize: ncls %d outside [1,%d]", ncls, MAXC);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (ncls <= 4) window_finalize_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
-  else if (ncls <= 16) window_finalize_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
-  else window_finalize_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(agg, wsum, ncls, V, (long long*)seg);
-  E2E_LAUNCHED("window_finalize");
-  return E2E_OK;
+  return window_finalize_impl(agg, wsum, ncls, X, Y, Z, 0, X, seg, stream);
+}
+
+extern "C" int e2e_window_finalize_range(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
+                                         int32_t x0, int32_t x1, int64_t* seg, void* stream) {
+  E2E_ARG(agg && wsum && seg && ncls >= 1 && x0 >= 0 && x0 <= x1 && x1 <= X, "window_finalize_range: bad arguments");
+  E2E_ARG(ncls <= MAXC, "window_finalize_range: ncls %d outside [1,%d]", ncls, MAXC);
+  return window_finalize_impl(agg, wsum, ncls, X, Y, Z, x0, x1, seg, stream);
 }

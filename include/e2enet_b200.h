@@ -342,6 +342,10 @@ int e2e_window_head_accumulate(const void* x, int32_t Cb, const float* w, int32_
 /* agg /= wsum (in place, cropped region), seg = argmax over classes (first max wins) */
 int e2e_window_finalize(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z,
                         int64_t* seg, void* stream);
+/* the same for the x-planes [x0, x1) only: the tiled predictor finalises (and starts copying to the host) the planes
+ * that no later tile touches while the remaining tiles are still being computed (neural_network.py:396-426) */
+int e2e_window_finalize_range(float* agg, const float* wsum, int32_t ncls, int32_t X, int32_t Y, int32_t Z, int32_t x0,
+                              int32_t x1, int64_t* seg, void* stream);
 
 /* ---------------------------------------------------------------- export: resample + argmax */
 /*

@@ -841,3 +841,27 @@ def test_train_step_fused_optimizer_matches_stock_torch_loop(dev):
             assert rel2(w0[k], w1[k]) < 1e-4, (k, rel2(w0[k], w1[k]))
     for a_, b_ in zip(l0, l1):
         assert abs(a_ - b_) < 5e-3 * abs(b_), (l0, l1)
+
+
+def test_predict_3d_streamed_results_equal_unstreamed(dev):
+    """single-GPU predict_3D finalises and copies the x-planes no later tile touches while the remaining tiles are still
+    being computed (e2e_window_finalize_range + a copy stream); the result must be bit-identical to finalising and
+    copying everything at the end, incl. a volume that needs padding in x (un-padded range inside the planes)."""
+    from e2enet_medical_b200.network_architecture.unetpp_d import softmax_helper
+    from e2enet_medical_b200.training import POOLS, build_network
+    pools, patch, ncls = POOLS["btcv"], (32, 64, 64), 5
+    torch.manual_seed(0)
+    net = build_network(1, ncls, pools, patch, 16, deep_supervision=True).to(dev).eval()
+    net.do_ds = False
+    net.inference_apply_nonlin = softmax_helper
+    rs = np.random.RandomState(3)
+    for shape in ((1, 70, 100, 64), (1, 20, 64, 90)):          # 3 x-steps; x shorter than the patch (padded)
+        vol = rs.randn(*shape).astype(np.float32)
+        out = {}
+        for streamed in (True, False):
+            net.stream_results = streamed
+            seg, probs = net.predict_3D(vol, False, (0, 1, 2), True, 0.5, patch, None, True, "constant", None, False, False, True)
+            out[streamed] = (seg.copy(), probs.copy())
+        assert out[True][0].shape == shape[1:] and out[True][1].shape == (ncls,) + shape[1:]
+        assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
+    net.stream_results = True
